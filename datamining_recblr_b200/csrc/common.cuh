@@ -1,0 +1,134 @@
+// Shared device/host helpers for libbdlru.so (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <atomic>
+
+#include "../../include/bdlru.h"
+
+#define BDLRU_API __attribute__((visibility("default")))
+
+namespace bdlru {
+
+// ----------------------------------------------------------------------------- error plumbing
+void set_error(const char* fmt, ...);
+extern std::atomic<uint64_t> g_launches;
+
+#define BDLRU_REQUIRE(cond, ...)              \
+  do {                                        \
+    if (!(cond)) {                            \
+      ::bdlru::set_error(__VA_ARGS__);        \
+      return BDLRU_ERR_INVALID;               \
+    }                                         \
+  } while (0)
+
+#define BDLRU_CUDA(call)                                                                   \
+  do {                                                                                     \
+    cudaError_t e_ = (call);                                                               \
+    if (e_ != cudaSuccess) {                                                               \
+      ::bdlru::set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, \
+                         __LINE__);                                                        \
+      return BDLRU_ERR_CUDA;                                                               \
+    }                                                                                      \
+  } while (0)
+
+// call after every <<<>>> launch
+#define BDLRU_LAUNCHED()                                   \
+  do {                                                     \
+    ::bdlru::g_launches.fetch_add(1);                      \
+    BDLRU_CUDA(cudaGetLastError());                        \
+  } while (0)
+
+int sm_count();  // SMs of the current device (cached)
+
+inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+
+// ----------------------------------------------------------------------------- 4-wide I/O
+template <typename T>
+struct IO;
+
+template <>
+struct IO<float> {
+  static constexpr int BYTES = 16;
+  __device__ __forceinline__ static void load(const void* p, float (&v)[4]) {
+    float4 f = *reinterpret_cast<const float4*>(p);
+    v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+  }
+  __device__ __forceinline__ static void store(void* p, const float (&v)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+};
+
+template <>
+struct IO<__nv_bfloat16> {
+  static constexpr int BYTES = 8;
+  __device__ __forceinline__ static void load(const void* p, float (&v)[4]) {
+    uint2 u = *reinterpret_cast<const uint2*>(p);
+    v[0] = __uint_as_float(u.x << 16); v[1] = __uint_as_float(u.x & 0xffff0000u);
+    v[2] = __uint_as_float(u.y << 16); v[3] = __uint_as_float(u.y & 0xffff0000u);
+  }
+  __device__ __forceinline__ static void store(void* p, const float (&v)[4]) {
+    __nv_bfloat162 lo = __floats2bfloat162_rn(v[0], v[1]);
+    __nv_bfloat162 hi = __floats2bfloat162_rn(v[2], v[3]);
+    uint2 u;
+    u.x = *reinterpret_cast<uint32_t*>(&lo);
+    u.y = *reinterpret_cast<uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(p) = u;
+  }
+};
+
+// ----------------------------------------------------------------------------- cp.async (LDGSTS)
+template <int BYTES>
+__device__ __forceinline__ void cp_async(void* smem_dst, const void* gmem_src) {
+  unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+  if constexpr (BYTES == 16) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src) : "memory");
+  } else {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;\n" ::"r"(s), "l"(gmem_src), "n"(BYTES) : "memory");
+  }
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+// ----------------------------------------------------------------------------- math
+__device__ __forceinline__ float sigmoid_f(float x) { return __frcp_rn(1.0f + __expf(-x)); }
+__device__ __forceinline__ float silu_f(float x) { return x * sigmoid_f(x); }
+// d/dx silu(x) given s = sigmoid(x)
+__device__ __forceinline__ float silu_grad_f(float x, float s) { return s * (1.0f + x * (1.0f - s)); }
+__device__ __forceinline__ float softplus_acc(float x) { return x > 20.0f ? x : log1pf(expf(x)); }
+
+// 1 - exp(-u) for u >= 0 without cancellation; e = exp(-u) already computed.
+__device__ __forceinline__ float one_minus_exp_neg(float u, float e) {
+  float p = 1.0f - u * (1.0f / 7.0f);
+  p = 1.0f - u * (1.0f / 6.0f) * p;
+  p = 1.0f - u * (1.0f / 5.0f) * p;
+  p = 1.0f - u * (1.0f / 4.0f) * p;
+  p = 1.0f - u * (1.0f / 3.0f) * p;
+  p = 1.0f - u * 0.5f * p;
+  p = u * p;
+  return u < 0.25f ? p : 1.0f - e;
+}
+
+// The BD-LRU gates (RecBLR.py:197-198) for one element.  c = softplus(Lambda).
+struct Gate {
+  float sr, si, a, rq, q;  // sigmoid(r), sigmoid(i), alpha, 1/sqrt(1-a^2+1e-8), sqrt(1-a^2+1e-8)
+};
+__device__ __forceinline__ float gate_alpha(float c, float r, float& sr) {
+  sr = sigmoid_f(r);
+  return __expf(-c * sr);
+}
+__device__ __forceinline__ Gate gate_full(float c, float r, float i) {
+  Gate g;
+  g.a = gate_alpha(c, r, g.sr);
+  g.si = sigmoid_f(i);
+  float v = one_minus_exp_neg(2.0f * c * g.sr, g.a * g.a) + 1e-8f;
+  g.rq = rsqrtf(v);
+  g.q = v * g.rq;
+  return g;
+}
+
+}  // namespace bdlru

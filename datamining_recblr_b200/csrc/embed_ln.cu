@@ -1,0 +1,290 @@
+// Front end of RecBLR.forward (RecBLR.py:76-78): item-embedding gather -> dropout -> LayerNorm(eps),
+// fused so the [B, L, D] activation makes one HBM round trip (one 4*D-byte random row read + one write).
+//
+// One warp per token; lanes hold 4-channel vectors (128-bit row reads), mean/variance by warp shuffles,
+// fp32 statistics.  Dropout uses Philox-4x32-10 keyed by (seed, token, channel vector) so the backward
+// regenerates the mask instead of storing it.  Backward: LayerNorm backward per token, scatter-add of the
+// row gradient into dtable with vector atomics (red.global.add.v4.f32), dgamma/dbeta accumulated in
+// registers across a grid-stride loop and reduced deterministically in a second pass.
+#include "common.cuh"
+
+namespace bdlru {
+
+constexpr int kMaxV = 4;  // 4-channel vectors per lane: D <= 32 * 4 * kMaxV = 512
+
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                              uint32_t k1, uint32_t (&out)[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// keep-mask * 1/(1-p) for the 4 channels of vector `vec` of token `tok`
+__device__ __forceinline__ void dropout_scale4(uint64_t seed, long tok, int vec, float p, float (&m)[4]) {
+  uint32_t r[4];
+  philox4x32_10((uint32_t)tok, (uint32_t)((uint64_t)tok >> 32), (uint32_t)vec, 0x5bd1e995u, (uint32_t)seed,
+                (uint32_t)(seed >> 32), r);
+  const float inv = 1.0f / (1.0f - p);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float u = (float)(r[e] >> 8) * (1.0f / 16777216.0f);  // [0, 1)
+    m[e] = u >= p ? inv : 0.f;
+  }
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) embed_ln_fwd_kernel(const int64_t* __restrict__ ids, const T* __restrict__ table,
+                                                           const float* __restrict__ gamma,
+                                                           const float* __restrict__ beta, T* __restrict__ out,
+                                                           float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                                                           long n_tokens, long n_items, int D, float eps, float p,
+                                                           uint64_t seed) {
+  const int lane = threadIdx.x & 31;
+  const long gw = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long nw = ((long)gridDim.x * blockDim.x) >> 5;
+  const int nvec = D / 4;
+  for (long n = gw; n < n_tokens; n += nw) {
+    long id = ids[n];
+    id = id < 0 ? 0 : (id >= n_items ? n_items - 1 : id);
+    const T* row = table + id * D;
+    float x[kMaxV][4];
+    float s = 0.f;
+#pragma unroll
+    for (int v = 0; v < kMaxV; ++v) {
+      const int vec = lane + 32 * v;
+      if (vec < nvec) {
+        IO<T>::load(row + vec * 4, x[v]);
+        if (p > 0.f) {
+          float m[4];
+          dropout_scale4(seed, n, vec, p, m);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) x[v][e] *= m[e];
+        }
+        s += (x[v][0] + x[v][1]) + (x[v][2] + x[v][3]);
+      }
+    }
+    const float mean = warp_sum(s) / (float)D;
+    float q = 0.f;
+#pragma unroll
+    for (int v = 0; v < kMaxV; ++v) {
+      if (lane + 32 * v < nvec) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float d = x[v][e] - mean;
+          q = fmaf(d, d, q);
+        }
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(q) / (float)D + eps);
+#pragma unroll
+    for (int v = 0; v < kMaxV; ++v) {
+      const int vec = lane + 32 * v;
+      if (vec < nvec) {
+        const float4 g4 = *reinterpret_cast<const float4*>(gamma + vec * 4);
+        const float4 b4 = *reinterpret_cast<const float4*>(beta + vec * 4);
+        float o[4];
+        o[0] = fmaf((x[v][0] - mean) * rstd, g4.x, b4.x);
+        o[1] = fmaf((x[v][1] - mean) * rstd, g4.y, b4.y);
+        o[2] = fmaf((x[v][2] - mean) * rstd, g4.z, b4.z);
+        o[3] = fmaf((x[v][3] - mean) * rstd, g4.w, b4.w);
+        IO<T>::store(out + n * D + vec * 4, o);
+      }
+    }
+    if (lane == 0) {
+      mean_out[n] = mean;
+      rstd_out[n] = rstd;
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) embed_ln_bwd_kernel(const int64_t* __restrict__ ids, const T* __restrict__ table,
+                                                           const float* __restrict__ gamma, const T* __restrict__ dy,
+                                                           const float* __restrict__ mean_in,
+                                                           const float* __restrict__ rstd_in, float* __restrict__ dtable,
+                                                           float* __restrict__ part /* [grid][2][D] */, long n_tokens,
+                                                           long n_items, int D, float p, uint64_t seed, long padding_idx) {
+  extern __shared__ float red[];  // [warps][2][D]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const long gw = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long nw = ((long)gridDim.x * blockDim.x) >> 5;
+  const int nvec = D / 4;
+  float dg[kMaxV][4], db[kMaxV][4];
+#pragma unroll
+  for (int v = 0; v < kMaxV; ++v)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) dg[v][e] = db[v][e] = 0.f;
+
+  for (long n = gw; n < n_tokens; n += nw) {
+    long id = ids[n];
+    id = id < 0 ? 0 : (id >= n_items ? n_items - 1 : id);
+    const T* row = table + id * D;
+    const float mean = mean_in[n], rstd = rstd_in[n];
+    float xh[kMaxV][4], dxh[kMaxV][4], msk[kMaxV][4];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int v = 0; v < kMaxV; ++v) {
+      const int vec = lane + 32 * v;
+      if (vec < nvec) {
+        float x[4], g[4];
+        IO<T>::load(row + vec * 4, x);
+        IO<T>::load(dy + n * D + vec * 4, g);
+        if (p > 0.f) {
+          dropout_scale4(seed, n, vec, p, msk[v]);
+        } else {
+          msk[v][0] = msk[v][1] = msk[v][2] = msk[v][3] = 1.f;
+        }
+        const float4 g4 = *reinterpret_cast<const float4*>(gamma + vec * 4);
+        const float gm[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          xh[v][e] = (x[e] * msk[v][e] - mean) * rstd;
+          dxh[v][e] = g[e] * gm[e];
+          dg[v][e] = fmaf(g[e], xh[v][e], dg[v][e]);
+          db[v][e] += g[e];
+          s1 += dxh[v][e];
+          s2 = fmaf(dxh[v][e], xh[v][e], s2);
+        }
+      }
+    }
+    s1 = warp_sum(s1) / (float)D;
+    s2 = warp_sum(s2) / (float)D;
+    if (id != padding_idx) {
+#pragma unroll
+      for (int v = 0; v < kMaxV; ++v) {
+        const int vec = lane + 32 * v;
+        if (vec < nvec) {
+          float4 d;
+          d.x = rstd * (dxh[v][0] - s1 - xh[v][0] * s2) * msk[v][0];
+          d.y = rstd * (dxh[v][1] - s1 - xh[v][1] * s2) * msk[v][1];
+          d.z = rstd * (dxh[v][2] - s1 - xh[v][2] * s2) * msk[v][2];
+          d.w = rstd * (dxh[v][3] - s1 - xh[v][3] * s2) * msk[v][3];
+          atomicAdd(reinterpret_cast<float4*>(dtable + id * D + vec * 4), d);
+        }
+      }
+    }
+  }
+  // block reduce dgamma / dbeta over warps -> one partial row per CTA
+#pragma unroll
+  for (int v = 0; v < kMaxV; ++v) {
+    const int vec = lane + 32 * v;
+    if (vec < nvec) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        red[((size_t)warp * 2 + 0) * D + vec * 4 + e] = dg[v][e];
+        red[((size_t)warp * 2 + 1) * D + vec * 4 + e] = db[v][e];
+      }
+    }
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < 2 * D; idx += blockDim.x) {
+    float s = 0.f;
+    for (int w = 0; w < nwarp; ++w) s += red[(size_t)w * 2 * D + idx];
+    part[(size_t)blockIdx.x * 2 * D + idx] = s;
+  }
+}
+
+__global__ void embed_ln_reduce(const float* __restrict__ part, int grid, int D, float* __restrict__ dgamma,
+                                float* __restrict__ dbeta) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 2 * D) return;
+  float s = 0.f;
+  for (int g = 0; g < grid; ++g) s += part[(size_t)g * 2 * D + idx];
+  if (idx < D)
+    dgamma[idx] = s;
+  else
+    dbeta[idx - D] = s;
+}
+
+static int embed_grid(long n_tokens) {
+  long blocks = (n_tokens + 7) / 8;
+  const long cap = (long)sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+static int embed_check(long n_tokens, long n_items, int D, int dtype, float p) {
+  BDLRU_REQUIRE(n_tokens >= 1 && n_items >= 1, "embed_ln: bad sizes n_tokens=%ld n_items=%ld", n_tokens, n_items);
+  BDLRU_REQUIRE(D >= 4 && D % 4 == 0 && D <= 128 * kMaxV, "embed_ln: D=%d must be a multiple of 4 and <= %d", D,
+                128 * kMaxV);
+  BDLRU_REQUIRE(dtype == BDLRU_F32 || dtype == BDLRU_BF16, "embed_ln: bad dtype %d", dtype);
+  BDLRU_REQUIRE(p >= 0.f && p < 1.f, "embed_ln: dropout_p=%f not in [0, 1)", p);
+  return BDLRU_OK;
+}
+
+}  // namespace bdlru
+
+using namespace bdlru;
+
+extern "C" BDLRU_API int bdlru_embed_ln_fwd(const int64_t* ids, const void* table, const float* gamma,
+                                            const float* beta, void* out, float* mean, float* rstd, int64_t n_tokens,
+                                            int64_t n_items, int D, float eps, float dropout_p, uint64_t seed,
+                                            int dtype, void* stream) {
+  int rc = embed_check(n_tokens, n_items, D, dtype, dropout_p);
+  if (rc) return rc;
+  BDLRU_REQUIRE(ids && table && gamma && beta && out && mean && rstd, "embed_ln_fwd: null pointer");
+  BDLRU_REQUIRE(aligned(table, 16) && aligned(out, 16) && aligned(gamma, 16) && aligned(beta, 16),
+                "embed_ln_fwd: pointers must be 16-byte aligned");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int grid = embed_grid(n_tokens);
+  if (dtype == BDLRU_F32)
+    embed_ln_fwd_kernel<float><<<grid, 256, 0, st>>>(ids, (const float*)table, gamma, beta, (float*)out, mean, rstd,
+                                                     n_tokens, n_items, D, eps, dropout_p, seed);
+  else
+    embed_ln_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(ids, (const __nv_bfloat16*)table, gamma, beta,
+                                                             (__nv_bfloat16*)out, mean, rstd, n_tokens, n_items, D,
+                                                             eps, dropout_p, seed);
+  BDLRU_LAUNCHED();
+  return BDLRU_OK;
+}
+
+extern "C" BDLRU_API size_t bdlru_embed_ln_bwd_workspace_bytes(int64_t n_tokens, int D) {
+  (void)n_tokens;
+  return (size_t)sm_count() * 8 * 2 * (size_t)D * sizeof(float);
+}
+
+extern "C" BDLRU_API int bdlru_embed_ln_bwd(const int64_t* ids, const void* table, const float* gamma,
+                                            const void* grad_out, const float* mean, const float* rstd, float* dtable,
+                                            float* dgamma, float* dbeta, void* workspace, size_t workspace_bytes,
+                                            int64_t n_tokens, int64_t n_items, int D, float dropout_p, uint64_t seed,
+                                            int64_t padding_idx, int dtype, void* stream) {
+  int rc = embed_check(n_tokens, n_items, D, dtype, dropout_p);
+  if (rc) return rc;
+  BDLRU_REQUIRE(ids && table && gamma && grad_out && mean && rstd && dtable && dgamma && dbeta,
+                "embed_ln_bwd: null pointer");
+  BDLRU_REQUIRE(aligned(table, 16) && aligned(grad_out, 16) && aligned(dtable, 16) && aligned(gamma, 16),
+                "embed_ln_bwd: pointers must be 16-byte aligned");
+  const int grid = embed_grid(n_tokens);
+  const size_t need = (size_t)grid * 2 * D * sizeof(float);
+  BDLRU_REQUIRE(workspace && workspace_bytes >= need, "embed_ln_bwd: workspace too small (%zu < %zu)", workspace_bytes,
+                need);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  float* part = reinterpret_cast<float*>(workspace);
+  const size_t smem = (size_t)8 * 2 * D * sizeof(float);
+  if (dtype == BDLRU_F32)
+    embed_ln_bwd_kernel<float><<<grid, 256, smem, st>>>(ids, (const float*)table, gamma, (const float*)grad_out, mean,
+                                                        rstd, dtable, part, n_tokens, n_items, D, dropout_p, seed,
+                                                        padding_idx);
+  else
+    embed_ln_bwd_kernel<__nv_bfloat16><<<grid, 256, smem, st>>>(ids, (const __nv_bfloat16*)table, gamma,
+                                                                (const __nv_bfloat16*)grad_out, mean, rstd, dtable,
+                                                                part, n_tokens, n_items, D, dropout_p, seed,
+                                                                padding_idx);
+  BDLRU_LAUNCHED();
+  embed_ln_reduce<<<(2 * D + 127) / 128, 128, 0, st>>>(part, grid, D, dgamma, dbeta);
+  BDLRU_LAUNCHED();
+  return BDLRU_OK;
+}

@@ -1,0 +1,610 @@
+// S1: fused BD-LRU gate math + chunked scan on channel-last [B, T, C] views (and the same tiling
+// without gate math = channel-last raw scan).  Replaces RecBLR.py:197-200 and, through h0/dh0, the
+// left-pad of RecBLR.py:177-179,203-204.
+//
+// Tiling.  A persistent CTA owns (batch b, channel tile) units.  Its threads form a [NS, tcn] grid:
+// tcn threads cover the channel tile with one 4-channel vector each (coalesced 16 B / 8 B per thread
+// along C), NS "time slices" each take S consecutive steps, so one iteration covers NS*S time steps.
+// Inputs are staged through shared memory with cp.async (LDGSTS) into THREAD-PRIVATE slots — a thread
+// only ever reads back what it copied itself — so the two-deep pipeline needs no block barrier for the
+// data, only cp.async.wait_group.  Per iteration:
+//   pass 1  each slice scans its S steps from a zero state, keeping the local states and the running
+//           product of gates in registers (chunk aggregate (A, H));
+//   combine aggregates go through shared memory, every thread walks the NS aggregates of its channel
+//           vector to get its carry-in and the CTA state after the block (one __syncthreads);
+//   pass 2  h_t = local_t + cumprod_t * carry_in, written straight to HBM.
+// The backward mirrors this in reverse time with u_t = a_t * dh~_t as the carried quantity.
+// HBM traffic is the algorithmic minimum: fwd reads x', r, i and writes h (4 units);
+// bwd reads x', r, i, h, g and writes dx', dr, di (8 units).   [SURVEY §8d: 12*E*s bytes fwd+bwd]
+#include "common.cuh"
+
+namespace bdlru {
+
+struct View {
+  const unsigned char* p;
+  long bs, rs;  // element strides
+};
+
+struct GScanParams {
+  View x, r, i, z;      // GATED: x', r, i (+z).  RAW: x = tokens b, r = gates a.
+  View h, y;            // fwd outputs (h is an input in bwd); y iff HAS_Z
+  View g;               // bwd: upstream grad (dL/dh, or dL/dy when HAS_Z)
+  View dx, dr, di, dz;  // bwd outputs (RAW: dx = d_tokens, dr = d_gates)
+  const float* lambda;
+  const float* h0;
+  long h0_bs;
+  float* part_dc;   // [grid, 4*tcn] partial sums of dL/dc (c = softplus(Lambda))
+  float* part_dh0;  // [grid, 4*tcn] partial sums of dh0 when h0 is broadcast
+  float* dh0;       // direct output when h0 is per batch
+  int B, T, C;
+  int tcn, NS, n_ctile, n_iter, n_units;
+};
+
+template <typename T>
+__device__ __forceinline__ const unsigned char* at(const View& v, long b, long t, int c) {
+  return v.p + ((b * v.bs + t * v.rs + c) * (long)sizeof(T));
+}
+
+// ------------------------------------------------------------------------------------------ forward
+template <typename T, int S, bool GATED, bool HAS_Z>
+__global__ void __launch_bounds__(256) gscan_fwd_kernel(const GScanParams p) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  constexpr int EB = IO<T>::BYTES;
+  constexpr int NARR = (GATED ? 3 : 2) + (HAS_Z ? 1 : 0);
+  const int NT = blockDim.x, tid = threadIdx.x;
+  const int tc = tid % p.tcn, ts = tid / p.tcn;
+  const size_t arr_bytes = (size_t)S * NT * EB;
+  const size_t stage_bytes = arr_bytes * NARR;
+  float4* agg = reinterpret_cast<float4*>(smem + 2 * stage_bytes);  // [2 parity][2 (A,H)][NT]
+
+  const int my_units = (p.n_units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const long my_total = (long)my_units * p.n_iter;
+  const int Tb = p.NS * S;
+
+  auto slot = [&](int buf, int arr, int s) -> unsigned char* {
+    return smem + buf * stage_bytes + arr * arr_bytes + ((size_t)s * NT + tid) * EB;
+  };
+  auto issue = [&](long w, int buf) {
+    if (w < my_total) {
+      const int k = (int)(w / p.n_iter), it = (int)(w % p.n_iter);
+      const int u = blockIdx.x + k * gridDim.x;
+      const long b = u / p.n_ctile;
+      const int c = ((u % p.n_ctile) * p.tcn + tc) * 4;
+      const int t0 = it * Tb + ts * S;
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        const int t = t0 + s;
+        if (t < p.T) {
+          cp_async<EB>(slot(buf, 0, s), at<T>(p.x, b, t, c));
+          cp_async<EB>(slot(buf, 1, s), at<T>(p.r, b, t, c));
+          if (GATED) cp_async<EB>(slot(buf, 2, s), at<T>(p.i, b, t, c));
+          if (HAS_Z) cp_async<EB>(slot(buf, NARR - 1, s), at<T>(p.z, b, t, c));
+        }
+      }
+    }
+    cp_async_commit();
+  };
+
+  issue(0, 0);
+  issue(1, 1);
+
+  float state[4] = {0.f, 0.f, 0.f, 0.f};
+  float csp[4] = {0.f, 0.f, 0.f, 0.f};
+  for (long w = 0; w < my_total; ++w) {
+    const int buf = (int)(w & 1);
+    const int k = (int)(w / p.n_iter), it = (int)(w % p.n_iter);
+    const int u = blockIdx.x + k * gridDim.x;
+    const long b = u / p.n_ctile;
+    const int c = ((u % p.n_ctile) * p.tcn + tc) * 4;
+    const int t0 = it * Tb + ts * S;
+    if (it == 0) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (GATED) csp[e] = softplus_acc(p.lambda[c + e]);
+        state[e] = p.h0 ? p.h0[b * p.h0_bs + c + e] : 0.f;
+      }
+    }
+    cp_async_wait<1>();
+
+    // pass 1: local scan from a zero state
+    float hloc[S][4], cum[S][4];
+    float hl[4] = {0.f, 0.f, 0.f, 0.f}, ca[4] = {1.f, 1.f, 1.f, 1.f};
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      if (t0 + s < p.T) {
+        float xv[4], rv[4], iv[4];
+        IO<T>::load(slot(buf, 0, s), xv);
+        IO<T>::load(slot(buf, 1, s), rv);
+        if (GATED) IO<T>::load(slot(buf, 2, s), iv);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float a, bb;
+          if (GATED) {
+            Gate gt = gate_full(csp[e], rv[e], iv[e]);
+            a = gt.a;
+            bb = gt.q * gt.si * xv[e];
+          } else {
+            a = rv[e];
+            bb = xv[e];
+          }
+          hl[e] = fmaf(a, hl[e], bb);
+          ca[e] *= a;
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { hloc[s][e] = hl[e]; cum[s][e] = ca[e]; }
+    }
+    if (!HAS_Z) issue(w + 2, buf);  // slots of this buffer are consumed: refill (thread-private)
+
+    // combine chunk aggregates across the NS slices
+    float4* aggA = agg + (size_t)(buf * 2 + 0) * NT;
+    float4* aggH = agg + (size_t)(buf * 2 + 1) * NT;
+    aggA[tid] = make_float4(ca[0], ca[1], ca[2], ca[3]);
+    aggH[tid] = make_float4(hl[0], hl[1], hl[2], hl[3]);
+    __syncthreads();
+    float cin[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int j = 0; j < p.NS; ++j) {
+      const float4 A = aggA[j * p.tcn + tc], H = aggH[j * p.tcn + tc];
+      if (j == ts) { cin[0] = state[0]; cin[1] = state[1]; cin[2] = state[2]; cin[3] = state[3]; }
+      state[0] = fmaf(A.x, state[0], H.x);
+      state[1] = fmaf(A.y, state[1], H.y);
+      state[2] = fmaf(A.z, state[2], H.z);
+      state[3] = fmaf(A.w, state[3], H.w);
+    }
+
+    // pass 2: apply the carry-in and write
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      const int t = t0 + s;
+      if (t < p.T) {
+        float hv[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) hv[e] = fmaf(cum[s][e], cin[e], hloc[s][e]);
+        IO<T>::store(const_cast<unsigned char*>(at<T>(p.h, b, t, c)), hv);
+        if (HAS_Z) {
+          float zv[4], yv[4];
+          IO<T>::load(slot(buf, NARR - 1, s), zv);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) yv[e] = silu_f(zv[e]) * hv[e];
+          IO<T>::store(const_cast<unsigned char*>(at<T>(p.y, b, t, c)), yv);
+        }
+      }
+    }
+    if (HAS_Z) issue(w + 2, buf);
+  }
+  cp_async_wait<0>();
+}
+
+// ------------------------------------------------------------------------------------------ backward
+// Staged arrays: GATED: x', r, i, g, hprev[S] (+ z and one more h entry when HAS_Z)
+//                RAW  : a (in p.r), g, hprev[S]
+template <typename T, int S, bool GATED, bool HAS_Z>
+__global__ void __launch_bounds__(256) gscan_bwd_kernel(const GScanParams p) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  constexpr int EB = IO<T>::BYTES;
+  constexpr int NH = S + (HAS_Z ? 1 : 0);                          // staged h entries: h[t0-1 .. t0+NH-2]
+  constexpr int NVEC = (GATED ? 4 : 2) * S + NH + (HAS_Z ? S : 0);  // vectors staged per thread
+  constexpr int OFF_X = 0, OFF_R = GATED ? S : 0, OFF_I = 2 * S, OFF_G = GATED ? 3 * S : S;
+  constexpr int OFF_H = OFF_G + S, OFF_Z = OFF_H + NH;
+  const int NT = blockDim.x, tid = threadIdx.x;
+  const int tc = tid % p.tcn, ts = tid / p.tcn;
+  const size_t stage_bytes = (size_t)NVEC * NT * EB;
+  float4* agg = reinterpret_cast<float4*>(smem + 2 * stage_bytes);  // [2][2][NT]
+  // GATED pass 1 leaves sigmoid(r) and alpha for pass 2 in thread-private fp32 scratch: for fp32 I/O it
+  // overwrites the consumed r and g staging slots, for bf16 I/O (8-byte slots) it has its own array.
+  constexpr bool INPLACE = sizeof(T) == 4;
+  float4* scr = agg + 4 * NT;  // !INPLACE: [2 (sr, a)][S][NT]
+
+  const int my_units = (p.n_units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const long my_total = (long)my_units * p.n_iter;
+  const int Tb = p.NS * S;
+
+  auto slot = [&](int buf, int v) -> unsigned char* {
+    return smem + buf * stage_bytes + ((size_t)v * NT + tid) * EB;
+  };
+  auto scr_sr = [&](int buf, int s) -> float4* {
+    return INPLACE ? reinterpret_cast<float4*>(slot(buf, OFF_R + s)) : scr + (size_t)(0 * S + s) * NT + tid;
+  };
+  auto scr_a = [&](int buf, int s) -> float4* {
+    return INPLACE ? reinterpret_cast<float4*>(slot(buf, OFF_G + s)) : scr + (size_t)(1 * S + s) * NT + tid;
+  };
+  auto issue = [&](long w, int buf) {
+    if (w < my_total) {
+      const int k = (int)(w / p.n_iter), it = p.n_iter - 1 - (int)(w % p.n_iter);
+      const int u = blockIdx.x + k * gridDim.x;
+      const long b = u / p.n_ctile;
+      const int c = ((u % p.n_ctile) * p.tcn + tc) * 4;
+      const int t0 = it * Tb + ts * S;
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        const int t = t0 + s;
+        if (t < p.T) {
+          if (GATED) cp_async<EB>(slot(buf, OFF_X + s), at<T>(p.x, b, t, c));
+          cp_async<EB>(slot(buf, OFF_R + s), at<T>(p.r, b, t, c));
+          if (GATED) cp_async<EB>(slot(buf, OFF_I + s), at<T>(p.i, b, t, c));
+          cp_async<EB>(slot(buf, OFF_G + s), at<T>(p.g, b, t, c));
+          if (HAS_Z) cp_async<EB>(slot(buf, OFF_Z + s), at<T>(p.z, b, t, c));
+        }
+      }
+#pragma unroll
+      for (int s = 0; s < NH; ++s) {
+        const int t = t0 + s - 1;
+        if (t >= 0 && t < p.T) cp_async<EB>(slot(buf, OFF_H + s), at<T>(p.h, b, t, c));
+      }
+    }
+    cp_async_commit();
+  };
+
+  issue(0, 0);
+  issue(1, 1);
+
+  float ustate[4] = {0.f, 0.f, 0.f, 0.f};
+  float csp[4] = {0.f, 0.f, 0.f, 0.f}, h0v[4] = {0.f, 0.f, 0.f, 0.f};
+  float dc_acc[4] = {0.f, 0.f, 0.f, 0.f}, dh0_acc[4] = {0.f, 0.f, 0.f, 0.f};
+
+  for (long w = 0; w < my_total; ++w) {
+    const int buf = (int)(w & 1);
+    const int k = (int)(w / p.n_iter), it = p.n_iter - 1 - (int)(w % p.n_iter);
+    const int u = blockIdx.x + k * gridDim.x;
+    const long b = u / p.n_ctile;
+    const int c = ((u % p.n_ctile) * p.tcn + tc) * 4;
+    const int t0 = it * Tb + ts * S;
+    if (it == p.n_iter - 1) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (GATED) csp[e] = softplus_acc(p.lambda[c + e]);
+        h0v[e] = p.h0 ? p.h0[b * p.h0_bs + c + e] : 0.f;
+        ustate[e] = 0.f;
+      }
+    }
+    cp_async_wait<1>();
+
+    // pass 1 (reverse time): local dh~ from u_in = 0; Pm = product of the gates AFTER step s
+    float dloc[S][4], pm[S][4];
+    float ul[4] = {0.f, 0.f, 0.f, 0.f}, pc[4] = {1.f, 1.f, 1.f, 1.f};
+#pragma unroll
+    for (int s = S - 1; s >= 0; --s) {
+      float av[4] = {1.f, 1.f, 1.f, 1.f}, gv[4] = {0.f, 0.f, 0.f, 0.f};
+      if (t0 + s < p.T) {
+        float rv[4];
+        IO<T>::load(slot(buf, OFF_R + s), rv);
+        IO<T>::load(slot(buf, OFF_G + s), gv);
+        if (HAS_Z) {
+          // upstream is dL/dy with y = silu(z) * h:  dz = dy * h_t * silu'(z),  g = dy * silu(z)
+          float zv[4], hv[4], dzv[4];
+          IO<T>::load(slot(buf, OFF_Z + s), zv);
+          IO<T>::load(slot(buf, OFF_H + s + 1), hv);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float sz = sigmoid_f(zv[e]);
+            dzv[e] = gv[e] * hv[e] * silu_grad_f(zv[e], sz);
+            gv[e] *= zv[e] * sz;
+          }
+          IO<T>::store(const_cast<unsigned char*>(at<T>(p.dz, b, t0 + s, c)), dzv);
+        }
+        if (GATED) {
+          float srv[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) av[e] = gate_alpha(csp[e], rv[e], srv[e]);
+          *scr_sr(buf, s) = make_float4(srv[0], srv[1], srv[2], srv[3]);
+          *scr_a(buf, s) = make_float4(av[0], av[1], av[2], av[3]);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) av[e] = rv[e];
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float d = gv[e] + ul[e];
+        dloc[s][e] = d;
+        pm[s][e] = pc[e];
+        ul[e] = av[e] * d;
+        pc[e] *= av[e];
+      }
+    }
+
+    // combine (carry flows from later slices to earlier ones)
+    float4* aggA = agg + (size_t)(buf * 2 + 0) * NT;
+    float4* aggU = agg + (size_t)(buf * 2 + 1) * NT;
+    aggA[tid] = make_float4(pc[0], pc[1], pc[2], pc[3]);
+    aggU[tid] = make_float4(ul[0], ul[1], ul[2], ul[3]);
+    __syncthreads();
+    float uin[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int j = p.NS - 1; j >= 0; --j) {
+      const float4 A = aggA[j * p.tcn + tc], U = aggU[j * p.tcn + tc];
+      if (j == ts) { uin[0] = ustate[0]; uin[1] = ustate[1]; uin[2] = ustate[2]; uin[3] = ustate[3]; }
+      ustate[0] = fmaf(A.x, ustate[0], U.x);
+      ustate[1] = fmaf(A.y, ustate[1], U.y);
+      ustate[2] = fmaf(A.z, ustate[2], U.z);
+      ustate[3] = fmaf(A.w, ustate[3], U.w);
+    }
+    if (it == 0 && ts == 0) {  // u flowing out of t = 0 is dL/dh0 for this (b, channel vector)
+      if (p.dh0) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) p.dh0[b * p.C + c + e] = ustate[e];
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) dh0_acc[e] += ustate[e];
+      }
+    }
+
+    // pass 2: true dh~ and the chain rule through the gate math
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      const int t = t0 + s;
+      if (t < p.T) {
+        float d[4], hp[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) d[e] = fmaf(pm[s][e], uin[e], dloc[s][e]);
+        if (t == 0) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) hp[e] = h0v[e];
+        } else {
+          IO<T>::load(slot(buf, OFF_H + s), hp);
+        }
+        if (GATED) {
+          float xv[4], iv[4], dxv[4], drv[4], div[4];
+          IO<T>::load(slot(buf, OFF_X + s), xv);
+          IO<T>::load(slot(buf, OFF_I + s), iv);
+          const float4 sr4 = *scr_sr(buf, s);
+          const float4 a4 = *scr_a(buf, s);
+          const float srv[4] = {sr4.x, sr4.y, sr4.z, sr4.w};
+          const float av[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float si = sigmoid_f(iv[e]);
+            const float v = one_minus_exp_neg(2.0f * csp[e] * srv[e], av[e] * av[e]) + 1e-8f;
+            const float rq = rsqrtf(v), q = v * rq;
+            const float dbeta = d[e] * xv[e];
+            dxv[e] = d[e] * q * si;
+            div[e] = dbeta * q * si * (1.0f - si);
+            const float da = fmaf(hp[e], d[e], -dbeta * si * av[e] * rq);
+            const float daa = da * av[e];
+            drv[e] = -csp[e] * daa * srv[e] * (1.0f - srv[e]);
+            dc_acc[e] = fmaf(-daa, srv[e], dc_acc[e]);
+          }
+          IO<T>::store(const_cast<unsigned char*>(at<T>(p.dx, b, t, c)), dxv);
+          IO<T>::store(const_cast<unsigned char*>(at<T>(p.dr, b, t, c)), drv);
+          IO<T>::store(const_cast<unsigned char*>(at<T>(p.di, b, t, c)), div);
+        } else {
+          float dgv[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) dgv[e] = hp[e] * d[e];
+          IO<T>::store(const_cast<unsigned char*>(at<T>(p.dx, b, t, c)), d);     // d_tokens
+          IO<T>::store(const_cast<unsigned char*>(at<T>(p.dr, b, t, c)), dgv);   // d_gates
+        }
+      }
+    }
+    issue(w + 2, buf);
+  }
+  cp_async_wait<0>();
+
+  // per-CTA partial sums of dL/dc and (broadcast) dh0: reduce over the NS slices, one row per CTA.
+  // The host sizes the grid as a multiple of n_ctile, so a CTA sees a single channel tile.
+  __syncthreads();
+  float4* red = agg;  // reuse: [NT]
+  if (GATED) {
+    red[tid] = make_float4(dc_acc[0], dc_acc[1], dc_acc[2], dc_acc[3]);
+    __syncthreads();
+    if (ts == 0) {
+      float4 s4 = red[tc];
+      for (int j = 1; j < p.NS; ++j) {
+        const float4 v = red[j * p.tcn + tc];
+        s4.x += v.x; s4.y += v.y; s4.z += v.z; s4.w += v.w;
+      }
+      reinterpret_cast<float4*>(p.part_dc)[(size_t)blockIdx.x * p.tcn + tc] = s4;
+    }
+  }
+  if (p.part_dh0 && ts == 0) {
+    reinterpret_cast<float4*>(p.part_dh0)[(size_t)blockIdx.x * p.tcn + tc] =
+        make_float4(dh0_acc[0], dh0_acc[1], dh0_acc[2], dh0_acc[3]);
+  }
+}
+
+// out[c] = scale(c) * sum over CTAs that own channel tile (c / ct_width)
+__global__ void gscan_reduce_partials(const float* __restrict__ part, int grid, int n_ctile, int ctw, int C,
+                                      const float* __restrict__ lambda, float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const int ct = c / ctw, cc = c % ctw;
+  float s = 0.f;
+  for (int blk = ct; blk < grid; blk += n_ctile) s += part[(size_t)blk * ctw + cc];
+  if (lambda) s *= 1.0f / (1.0f + expf(-lambda[c]));  // d softplus(L)/dL = sigmoid(L)
+  out[c] = s;
+}
+
+// ------------------------------------------------------------------------------------------ host side
+struct Tiling {
+  int tcn, NS, NT, n_ctile, n_iter, n_units, grid;
+};
+
+template <int S>
+static Tiling make_tiling(int B, int T, int C) {
+  Tiling t;
+  const int cvec = C / 4;
+  t.tcn = 1;
+  while (t.tcn < 32 && cvec % (t.tcn * 2) == 0) t.tcn *= 2;
+  t.n_ctile = cvec / t.tcn;
+  // time slices per CTA: enough to cover T when it is short, at most 256 threads / 32 slices
+  int ns = 256 / t.tcn;
+  if (ns > 32) ns = 32;
+  while (ns > 1 && (ns / 2) * S >= T) ns /= 2;
+  t.NS = ns;
+  t.NT = t.tcn * t.NS;
+  t.n_iter = (T + t.NS * S - 1) / (t.NS * S);
+  t.n_units = B * t.n_ctile;
+  return t;
+}
+
+static int pick_grid(const Tiling& t, int ctas_per_sm) {
+  long g = (long)sm_count() * ctas_per_sm;
+  if (g > t.n_units) g = t.n_units;
+  g = (g / t.n_ctile) * t.n_ctile;  // multiple of n_ctile: a CTA always sees the same channel tile
+  if (g < t.n_ctile) g = t.n_ctile;
+  return (int)g;
+}
+
+static int check_view(const char* name, const bdlru_view& v, int esize, bool required) {
+  if (!v.ptr) {
+    BDLRU_REQUIRE(!required, "%s: null pointer", name);
+    return BDLRU_OK;
+  }
+  BDLRU_REQUIRE(aligned(v.ptr, 4 * esize), "%s: pointer not aligned to %d bytes", name, 4 * esize);
+  BDLRU_REQUIRE(v.bstride % 4 == 0 && v.rstride % 4 == 0, "%s: strides must be multiples of 4 elements", name);
+  return BDLRU_OK;
+}
+static View mk(const bdlru_view& v) { return View{reinterpret_cast<const unsigned char*>(v.ptr), v.bstride, v.rstride}; }
+
+constexpr int kS = 4;  // steps per slice per iteration
+
+template <typename T, bool GATED, bool HAS_Z>
+static int launch_fwd(GScanParams& p, cudaStream_t st) {
+  Tiling t = make_tiling<kS>(p.B, p.T, p.C);
+  p.tcn = t.tcn; p.NS = t.NS; p.n_ctile = t.n_ctile; p.n_iter = t.n_iter; p.n_units = t.n_units;
+  constexpr int NARR = (GATED ? 3 : 2) + (HAS_Z ? 1 : 0);
+  const size_t smem = 2 * (size_t)NARR * kS * t.NT * IO<T>::BYTES + 4 * (size_t)t.NT * sizeof(float4);
+  auto kern = gscan_fwd_kernel<T, kS, GATED, HAS_Z>;
+  BDLRU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int occ = 1;
+  BDLRU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, t.NT, smem));
+  if (occ < 1) occ = 1;
+  const int grid = pick_grid(t, occ);
+  kern<<<grid, t.NT, smem, st>>>(p);
+  BDLRU_LAUNCHED();
+  return BDLRU_OK;
+}
+
+template <typename T, bool GATED, bool HAS_Z>
+static int launch_bwd(GScanParams& p, float* dLambda, float* dh0_out, void* ws, size_t ws_bytes, cudaStream_t st) {
+  Tiling t = make_tiling<kS>(p.B, p.T, p.C);
+  p.tcn = t.tcn; p.NS = t.NS; p.n_ctile = t.n_ctile; p.n_iter = t.n_iter; p.n_units = t.n_units;
+  constexpr int NH = kS + (HAS_Z ? 1 : 0);
+  constexpr int NVEC = (GATED ? 4 : 2) * kS + NH + (HAS_Z ? kS : 0);
+  const size_t smem = 2 * (size_t)NVEC * t.NT * IO<T>::BYTES + 4 * (size_t)t.NT * sizeof(float4) +
+                      ((GATED && sizeof(T) != 4) ? 2 * (size_t)kS * t.NT * sizeof(float4) : 0);
+  auto kern = gscan_bwd_kernel<T, kS, GATED, HAS_Z>;
+  BDLRU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int occ = 1;
+  BDLRU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, t.NT, smem));
+  if (occ < 1) occ = 1;
+  const int grid = pick_grid(t, occ);
+  const int ctw = 4 * t.tcn;
+  const size_t need = 2 * (size_t)grid * ctw * sizeof(float);
+  BDLRU_REQUIRE(ws && ws_bytes >= need, "gated_scan_bwd: workspace too small (%zu < %zu)", ws_bytes, need);
+  p.part_dc = reinterpret_cast<float*>(ws);
+  const bool bcast_h0 = dh0_out && p.h0_bs == 0;
+  p.part_dh0 = bcast_h0 ? p.part_dc + (size_t)grid * ctw : nullptr;
+  p.dh0 = (dh0_out && !bcast_h0) ? dh0_out : nullptr;
+  kern<<<grid, t.NT, smem, st>>>(p);
+  BDLRU_LAUNCHED();
+  const int thr = 128, blocks = (p.C + thr - 1) / thr;
+  if (GATED) {
+    gscan_reduce_partials<<<blocks, thr, 0, st>>>(p.part_dc, grid, t.n_ctile, ctw, p.C, p.lambda, dLambda);
+    BDLRU_LAUNCHED();
+  }
+  if (bcast_h0) {
+    gscan_reduce_partials<<<blocks, thr, 0, st>>>(p.part_dh0, grid, t.n_ctile, ctw, p.C, nullptr, dh0_out);
+    BDLRU_LAUNCHED();
+  }
+  return BDLRU_OK;
+}
+
+static int check_common(int B, int T, int C, int dtype) {
+  BDLRU_REQUIRE(B >= 1 && T >= 1 && C >= 4, "bad shape B=%d T=%d C=%d", B, T, C);
+  BDLRU_REQUIRE(C % 4 == 0, "C=%d must be a multiple of 4", C);
+  BDLRU_REQUIRE(dtype == BDLRU_F32 || dtype == BDLRU_BF16, "bad dtype %d", dtype);
+  return BDLRU_OK;
+}
+
+}  // namespace bdlru
+
+using namespace bdlru;
+
+#define CHECK_VIEW(name, v, es, req)                        \
+  do {                                                      \
+    int rc_ = check_view(name, v, es, req);                 \
+    if (rc_) return rc_;                                    \
+  } while (0)
+
+extern "C" BDLRU_API size_t bdlru_gated_scan_bwd_workspace_bytes(int B, int T, int C) {
+  (void)B; (void)T;
+  // 2 partial arrays of [grid, 4*tcn] floats; grid <= 32 CTAs/SM * SMs, 4*tcn <= 128
+  return 2 * (size_t)32 * (size_t)sm_count() * 128 * sizeof(float) + 2 * (size_t)(C / 4 + 1) * 128 * sizeof(float);
+}
+
+extern "C" BDLRU_API int bdlru_gated_scan_fwd(bdlru_view xp, bdlru_view r, bdlru_view i, const float* Lambda, const float* h0,
+                                    int64_t h0_bstride, bdlru_view z, bdlru_view h, bdlru_view y, int B, int T,
+                                    int C, int dtype, void* stream) {
+  int rc = check_common(B, T, C, dtype);
+  if (rc) return rc;
+  const int es = dtype == BDLRU_F32 ? 4 : 2;
+  CHECK_VIEW("xp", xp, es, true); CHECK_VIEW("r", r, es, true); CHECK_VIEW("i", i, es, true);
+  CHECK_VIEW("h", h, es, true); CHECK_VIEW("z", z, es, false);
+  if (z.ptr) CHECK_VIEW("y", y, es, true);
+  BDLRU_REQUIRE(Lambda, "Lambda: null pointer");
+  BDLRU_REQUIRE(h0_bstride == 0 || h0_bstride == C, "h0_bstride must be 0 or C");
+  GScanParams p{};
+  p.x = mk(xp); p.r = mk(r); p.i = mk(i); p.z = mk(z); p.h = mk(h); p.y = mk(y);
+  p.lambda = Lambda; p.h0 = h0; p.h0_bs = h0_bstride; p.B = B; p.T = T; p.C = C;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (dtype == BDLRU_F32)
+    return z.ptr ? launch_fwd<float, true, true>(p, st) : launch_fwd<float, true, false>(p, st);
+  return z.ptr ? launch_fwd<__nv_bfloat16, true, true>(p, st) : launch_fwd<__nv_bfloat16, true, false>(p, st);
+}
+
+extern "C" BDLRU_API int bdlru_gated_scan_bwd(bdlru_view xp, bdlru_view r, bdlru_view i, const float* Lambda, const float* h0,
+                                    int64_t h0_bstride, bdlru_view z, bdlru_view h, bdlru_view grad, bdlru_view dxp,
+                                    bdlru_view dr, bdlru_view di, bdlru_view dz, float* dLambda, float* dh0,
+                                    void* workspace, size_t workspace_bytes, int B, int T, int C, int dtype,
+                                    void* stream) {
+  int rc = check_common(B, T, C, dtype);
+  if (rc) return rc;
+  const int es = dtype == BDLRU_F32 ? 4 : 2;
+  CHECK_VIEW("xp", xp, es, true); CHECK_VIEW("r", r, es, true); CHECK_VIEW("i", i, es, true);
+  CHECK_VIEW("h", h, es, true); CHECK_VIEW("grad", grad, es, true); CHECK_VIEW("dxp", dxp, es, true);
+  CHECK_VIEW("dr", dr, es, true); CHECK_VIEW("di", di, es, true); CHECK_VIEW("z", z, es, false);
+  if (z.ptr) CHECK_VIEW("dz", dz, es, true);
+  BDLRU_REQUIRE(Lambda && dLambda, "Lambda/dLambda: null pointer");
+  BDLRU_REQUIRE(h0_bstride == 0 || h0_bstride == C, "h0_bstride must be 0 or C");
+  GScanParams p{};
+  p.x = mk(xp); p.r = mk(r); p.i = mk(i); p.z = mk(z); p.h = mk(h); p.g = mk(grad);
+  p.dx = mk(dxp); p.dr = mk(dr); p.di = mk(di); p.dz = mk(dz);
+  p.lambda = Lambda; p.h0 = h0; p.h0_bs = h0_bstride; p.B = B; p.T = T; p.C = C;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (dtype == BDLRU_F32)
+    return z.ptr ? launch_bwd<float, true, true>(p, dLambda, dh0, workspace, workspace_bytes, st)
+                 : launch_bwd<float, true, false>(p, dLambda, dh0, workspace, workspace_bytes, st);
+  return z.ptr ? launch_bwd<__nv_bfloat16, true, true>(p, dLambda, dh0, workspace, workspace_bytes, st)
+               : launch_bwd<__nv_bfloat16, true, false>(p, dLambda, dh0, workspace, workspace_bytes, st);
+}
+
+extern "C" BDLRU_API int bdlru_scan_cl_fwd(bdlru_view a, bdlru_view b, const float* h0, int64_t h0_bstride, bdlru_view h, int B,
+                                 int T, int C, int dtype, void* stream) {
+  int rc = check_common(B, T, C, dtype);
+  if (rc) return rc;
+  const int es = dtype == BDLRU_F32 ? 4 : 2;
+  CHECK_VIEW("a", a, es, true); CHECK_VIEW("b", b, es, true); CHECK_VIEW("h", h, es, true);
+  BDLRU_REQUIRE(h0_bstride == 0 || h0_bstride == C, "h0_bstride must be 0 or C");
+  GScanParams p{};
+  p.x = mk(b); p.r = mk(a); p.h = mk(h); p.h0 = h0; p.h0_bs = h0_bstride; p.B = B; p.T = T; p.C = C;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  return dtype == BDLRU_F32 ? launch_fwd<float, false, false>(p, st) : launch_fwd<__nv_bfloat16, false, false>(p, st);
+}
+
+extern "C" BDLRU_API int bdlru_scan_cl_bwd(bdlru_view a, const float* h0, int64_t h0_bstride, bdlru_view h, bdlru_view grad,
+                                 bdlru_view da, bdlru_view db, float* dh0, void* workspace, size_t workspace_bytes,
+                                 int B, int T, int C, int dtype, void* stream) {
+  int rc = check_common(B, T, C, dtype);
+  if (rc) return rc;
+  const int es = dtype == BDLRU_F32 ? 4 : 2;
+  CHECK_VIEW("a", a, es, true); CHECK_VIEW("h", h, es, true); CHECK_VIEW("grad", grad, es, true);
+  CHECK_VIEW("da", da, es, true); CHECK_VIEW("db", db, es, true);
+  BDLRU_REQUIRE(h0_bstride == 0 || h0_bstride == C, "h0_bstride must be 0 or C");
+  GScanParams p{};
+  p.r = mk(a); p.h = mk(h); p.g = mk(grad); p.dx = mk(db); p.dr = mk(da);
+  p.h0 = h0; p.h0_bs = h0_bstride; p.B = B; p.T = T; p.C = C;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  return dtype == BDLRU_F32
+             ? launch_bwd<float, false, false>(p, nullptr, dh0, workspace, workspace_bytes, st)
+             : launch_bwd<__nv_bfloat16, false, false>(p, nullptr, dh0, workspace, workspace_bytes, st);
+}

@@ -1,0 +1,198 @@
+"""Differentiable PyTorch operators over the C ABI (host-side plumbing only: shapes, strides, autograd).
+
+    parallel_scan(gates, tokens)                       S0, [B, C, T]      parallel_scan.py:117-118
+    gated_scan(xp, r, i, Lambda, h0=None, z=None)      S1, [B, T, C]      RecBLR.py:197-200 (+206 with z)
+    scan_channel_last(a, b, h0=None)                   raw scan, [B, T, C]
+    causal_conv1d_channel_last(x, weight, bias, silu)  [B, T, C]          RecBLR.py:185 / 188-193
+"""
+import torch
+
+from . import _lib as L
+
+
+class _ScanBCT(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, gates, tokens):
+        L.require_cuda(gates, tokens)
+        B, C, T = gates.shape
+        # same contract as the reference op (parallel_scan.py:87-89)
+        assert tokens.shape == (B, C, T)
+        assert gates.is_contiguous()
+        assert tokens.is_contiguous()
+        assert gates.dtype == torch.float32 and tokens.dtype == torch.float32
+        states = torch.empty_like(tokens)
+        L.check(L.load().bdlru_scan_fwd(L.ptr(gates), L.ptr(tokens), L.ptr(states), B * C, T, L.stream_ptr(gates)))
+        ctx.save_for_backward(states, gates)
+        return states
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        states, gates = ctx.saved_tensors
+        B, C, T = gates.shape
+        grad_output = grad_output.contiguous()
+        d_gates = torch.empty_like(gates)
+        d_tokens = torch.empty_like(gates)
+        L.check(L.load().bdlru_scan_bwd(L.ptr(gates), L.ptr(states), L.ptr(grad_output), L.ptr(d_gates),
+                                        L.ptr(d_tokens), B * C, T, L.stream_ptr(gates)))
+        return d_gates, d_tokens
+
+
+def parallel_scan(gates, tokens):
+    """Drop-in for the reference's parallel_scan (parallel_scan.py:117): h_t = gates_t*h_{t-1} + tokens_t over
+    the last axis of contiguous fp32 [B, C, T]; any T (no power-of-two restriction)."""
+    return _ScanBCT.apply(gates, tokens)
+
+
+_WS = {}
+
+
+def _workspace(device, nbytes):
+    key = (device.type, device.index)
+    buf = _WS.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _WS[key] = buf
+    return buf
+
+
+class _GatedScan(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, xp, r, i, Lambda, h0, z):
+        L.require_cuda(xp, r, i, Lambda, h0, z)
+        B, T, C = xp.shape
+        assert r.shape == (B, T, C) and i.shape == (B, T, C) and Lambda.shape == (C,)
+        dt = L.dtype_tag(xp)
+        assert r.dtype == xp.dtype and i.dtype == xp.dtype
+        xp, r, i = L.as_cl(xp), L.as_cl(r), L.as_cl(i)
+        Lf = Lambda.detach().float().contiguous()
+        h0f, h0_bs = None, 0
+        if h0 is not None:
+            h0f = h0.detach().float().contiguous()
+            assert h0f.shape in ((C,), (B, C))
+            h0_bs = C if h0f.dim() == 2 else 0
+        h = torch.empty((B, T, C), dtype=xp.dtype, device=xp.device)
+        y = None
+        if z is not None:
+            assert z.shape == (B, T, C) and z.dtype == xp.dtype
+            z = L.as_cl(z)
+            y = torch.empty_like(h)
+        L.check(L.load().bdlru_gated_scan_fwd(L.view3(xp), L.view3(r), L.view3(i), L.ptr(Lf), L.ptr(h0f), h0_bs,
+                                              L.view3(z), L.view3(h), L.view3(y), B, T, C, dt, L.stream_ptr(xp)))
+        ctx.save_for_backward(xp, r, i, Lf, h0f, z, h)
+        ctx.h0_bs = h0_bs
+        ctx.lambda_dtype = Lambda.dtype
+        ctx.h0_dtype = h0.dtype if h0 is not None else None
+        if z is not None:
+            ctx.mark_non_differentiable(h)
+            return y, h
+        return h
+
+    @staticmethod
+    def backward(ctx, grad, *unused):
+        xp, r, i, Lf, h0f, z, h = ctx.saved_tensors
+        B, T, C = xp.shape
+        dt = L.dtype_tag(xp)
+        grad = L.as_cl(grad.to(xp.dtype))
+        dxp, dr, di = torch.empty_like(h), torch.empty_like(h), torch.empty_like(h)
+        dz = torch.empty_like(h) if z is not None else None
+        dLambda = torch.empty(C, dtype=torch.float32, device=xp.device)
+        dh0 = torch.empty_like(h0f) if h0f is not None else None
+        lib = L.load()
+        nws = lib.bdlru_gated_scan_bwd_workspace_bytes(B, T, C)
+        ws = _workspace(xp.device, nws)
+        L.check(lib.bdlru_gated_scan_bwd(L.view3(xp), L.view3(r), L.view3(i), L.ptr(Lf), L.ptr(h0f), ctx.h0_bs,
+                                         L.view3(z), L.view3(h), L.view3(grad), L.view3(dxp), L.view3(dr),
+                                         L.view3(di), L.view3(dz), L.ptr(dLambda), L.ptr(dh0), L.ptr(ws), nws,
+                                         B, T, C, dt, L.stream_ptr(xp)))
+        return (dxp, dr, di, dLambda.to(ctx.lambda_dtype), dh0.to(ctx.h0_dtype) if dh0 is not None else None, dz)
+
+
+def gated_scan(xp, r, i, Lambda, h0=None, z=None):
+    """Fused BD-LRU recurrence on channel-last [B, T, C] views (RecBLR.py:197-200 without transposes/padding):
+        a = exp(-softplus(Lambda)*sigmoid(r)); b = sqrt(1-a^2+1e-8)*sigmoid(i)*xp; h_t = a_t*h_{t-1} + b_t, h_{-1}=h0.
+    Returns h, or silu(z)*h when z is given (RecBLR.py:206's gate).  fp32 or bf16 I/O, fp32 state."""
+    out = _GatedScan.apply(xp, r, i, Lambda, h0, z)
+    return out[0] if z is not None else out
+
+
+class _ScanCL(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b, h0):
+        L.require_cuda(a, b, h0)
+        B, T, C = a.shape
+        assert b.shape == (B, T, C) and a.dtype == b.dtype
+        dt = L.dtype_tag(a)
+        a, b = L.as_cl(a), L.as_cl(b)
+        h0f, h0_bs = None, 0
+        if h0 is not None:
+            h0f = h0.detach().float().contiguous()
+            h0_bs = C if h0f.dim() == 2 else 0
+        h = torch.empty((B, T, C), dtype=a.dtype, device=a.device)
+        L.check(L.load().bdlru_scan_cl_fwd(L.view3(a), L.view3(b), L.ptr(h0f), h0_bs, L.view3(h), B, T, C, dt,
+                                           L.stream_ptr(a)))
+        ctx.save_for_backward(a, h0f, h)
+        ctx.h0_bs = h0_bs
+        ctx.h0_dtype = h0.dtype if h0 is not None else None
+        return h
+
+    @staticmethod
+    def backward(ctx, grad):
+        a, h0f, h = ctx.saved_tensors
+        B, T, C = a.shape
+        grad = L.as_cl(grad.to(a.dtype))
+        da, db = torch.empty_like(h), torch.empty_like(h)
+        dh0 = torch.empty_like(h0f) if h0f is not None else None
+        lib = L.load()
+        nws = lib.bdlru_gated_scan_bwd_workspace_bytes(B, T, C)
+        ws = _workspace(a.device, nws)
+        L.check(lib.bdlru_scan_cl_bwd(L.view3(a), L.ptr(h0f), ctx.h0_bs, L.view3(h), L.view3(grad), L.view3(da),
+                                      L.view3(db), L.ptr(dh0), L.ptr(ws), nws, B, T, C, L.dtype_tag(a),
+                                      L.stream_ptr(a)))
+        return da, db, (dh0.to(ctx.h0_dtype) if dh0 is not None else None)
+
+
+def scan_channel_last(a, b, h0=None):
+    """Raw scan h_t = a_t*h_{t-1} + b_t on channel-last [B, T, C] (time along dim 1)."""
+    return _ScanCL.apply(a, b, h0)
+
+
+class _Conv1dCL(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, silu):
+        L.require_cuda(x, weight, bias)
+        B, T, C = x.shape
+        assert weight.shape[0] == C and weight.dim() == 2
+        W = weight.shape[1]
+        x = L.as_cl(x)
+        wf = weight.detach().float().contiguous()
+        bf = bias.detach().float().contiguous() if bias is not None else None
+        y = torch.empty((B, T, C), dtype=x.dtype, device=x.device)
+        L.check(L.load().bdlru_conv1d_fwd(L.view3(x), L.ptr(wf), L.ptr(bf), L.view3(y), B, T, C, W, int(silu),
+                                          L.dtype_tag(x), L.stream_ptr(x)))
+        ctx.save_for_backward(x, wf, bf)
+        ctx.silu = bool(silu)
+        ctx.w_dtype = weight.dtype
+        ctx.b_dtype = bias.dtype if bias is not None else None
+        return y
+
+    @staticmethod
+    def backward(ctx, grad_y):
+        x, wf, bf = ctx.saved_tensors
+        B, T, C = x.shape
+        W = wf.shape[1]
+        grad_y = L.as_cl(grad_y.to(x.dtype))
+        dx = torch.empty((B, T, C), dtype=x.dtype, device=x.device)
+        dw = torch.empty_like(wf)
+        db = torch.empty(C, dtype=torch.float32, device=x.device) if bf is not None else None
+        lib = L.load()
+        nws = lib.bdlru_conv1d_bwd_workspace_bytes(B, T, C, W)
+        ws = _workspace(x.device, nws)
+        L.check(lib.bdlru_conv1d_bwd(L.view3(x), L.ptr(wf), L.ptr(bf), L.view3(grad_y), L.view3(dx), L.ptr(dw),
+                                     L.ptr(db), L.ptr(ws), nws, B, T, C, W, int(ctx.silu), L.dtype_tag(x),
+                                     L.stream_ptr(x)))
+        return dx, dw.to(ctx.w_dtype), (db.to(ctx.b_dtype) if db is not None else None), None
+
+
+def causal_conv1d_channel_last(x, weight, bias=None, silu=True):
+    """y_t = act(bias + sum_j weight[:, j] * x_{t-(W-1)+j}) on channel-last [B, T, C]; weight [C, W], W <= 4."""
+    return _Conv1dCL.apply(x, weight, bias, silu)

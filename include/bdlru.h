@@ -1,0 +1,171 @@
+/*
+ * bdlru.h — C ABI of libbdlru.so: the B200 (sm_100a) implementation of RecBLR's BD-LRU hot path.
+ *
+ * Drop-in boundary.  Every entry point takes raw DEVICE pointers, explicit sizes and
+ * element strides, a dtype tag and a cudaStream_t (passed as void*); it enqueues work on that stream
+ * and returns without synchronising.  The caller owns every buffer, including outputs and workspaces
+ * (sizes from the *_workspace_bytes queries).  The library keeps no tensors and never throws across
+ * the ABI: functions return 0 on success or a BDLRU_ERR_* code, with a thread-local message available
+ * from bdlru_last_error().  There is no CPU fallback anywhere behind this header.
+ *
+ * Reference interfaces replaced (paths relative to /root/reference):
+ *   bdlru_scan_fwd / _bwd            parallel_scan.py:85-95 (Scan.forward + forward_scan 44-60)
+ *                                    parallel_scan.py:98-114 (Scan.backward + backward_scan 63-80)
+ *   bdlru_gated_scan_fwd / _bwd      RecBLR.py:197-200 (gate math + both transposes + parallel_scan)
+ *                                    and the left-pad of RecBLR.py:177-179,203-204 (as h0 / dh0)
+ *   bdlru_conv1d_fwd / _bwd          causal_conv1d_fn call site RecBLR.py:188-193 (fallback line 185)
+ *   bdlru_embed_ln_fwd / _bwd        RecBLR.py:76-78 (embedding gather -> dropout -> LayerNorm)
+ *   bdlru_fullsort_topk              RecBLR.py:114-122 + RecBole mask/top-k ([upstream])
+ *   bdlru_fullsort_ce_fwd / _bwd     RecBLR.py:99-103 (logits GEMM + nn.CrossEntropyLoss, mean)
+ */
+#ifndef BDLRU_H_
+#define BDLRU_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BDLRU_OK 0
+#define BDLRU_ERR_INVALID 1     /* bad argument (shape, stride, alignment, null pointer) */
+#define BDLRU_ERR_CUDA 2        /* a CUDA runtime / driver call failed */
+#define BDLRU_ERR_UNSUPPORTED 3 /* valid request this build does not implement */
+
+#define BDLRU_F32 0
+#define BDLRU_BF16 1
+
+/* ABI version (bumped on any signature change) and last error text of the calling thread. */
+int bdlru_version(void);
+const char* bdlru_last_error(void);
+/* Number of kernel launches enqueued by this library since process start (bench.py's gpu_launches). */
+uint64_t bdlru_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * S0 — raw first-order scan on [B, C, T] contiguous fp32, T contiguous.
+ * Replaces parallel_scan.py:85-95 / 98-114.  h_t = gates_t * h_{t-1} + tokens_t, h_{-1} = 0.
+ * Any T >= 1 (the reference's power-of-two restriction, parallel_scan.py:48, is gone).
+ *   bwd: d_tokens_t = g_t + gates_{t+1} * d_tokens_{t+1};  d_gates_t = states_{t-1} * d_tokens_t.
+ * ------------------------------------------------------------------------------------------- */
+int bdlru_scan_fwd(const float* gates, const float* tokens, float* states,
+                   int64_t rows /* B*C */, int64_t T, void* stream);
+int bdlru_scan_bwd(const float* gates, const float* states, const float* grad_out,
+                   float* d_gates, float* d_tokens, int64_t rows, int64_t T, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * S1 — fused gate math + scan on channel-last [B, T, C] views (RecBLR.py:197-200 without the
+ * transposes, the pad copy or any [B,T,C] intermediate).
+ *   a_t = exp(-softplus(Lambda) * sigmoid(r_t));  b_t = sqrt(1 - a_t^2 + 1e-8) * sigmoid(i_t) * xp_t
+ *   h_t = a_t * h_{t-1} + b_t,  h_{-1} = h0 (NULL -> 0).   Optional fused z-gate (RecBLR.py:206):
+ *   y_t = silu(z_t) * h_t  when z != NULL.
+ * Tensors are described by (pointer, batch stride, row stride) in ELEMENTS; the channel stride is 1.
+ * xp/r/i/z/h/y share `dtype` (BDLRU_F32 or BDLRU_BF16); Lambda, h0, dLambda, dh0 are fp32; the scan
+ * state is fp32.  h0_bstride is 0 for a batch-independent h0[C] (the left-pad leak) or C for h0[B,C].
+ * C % 4 == 0; pointers and strides must keep 4-element vectors aligned.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  const void* ptr;
+  int64_t bstride; /* elements between batches */
+  int64_t rstride; /* elements between time steps */
+} bdlru_view;
+
+int bdlru_gated_scan_fwd(bdlru_view xp, bdlru_view r, bdlru_view i, const float* Lambda,
+                         const float* h0, int64_t h0_bstride,
+                         bdlru_view z /* ptr NULL: no z-gate */,
+                         bdlru_view h /* out */, bdlru_view y /* out, used iff z.ptr */,
+                         int B, int T, int C, int dtype, void* stream);
+
+/* Backward.  grad is dL/dh (z.ptr == NULL) or dL/dy (z.ptr != NULL; then dz is written too and h must be
+ * the forward's h).  Outputs dxp, dr, di (dz) in `dtype`; dLambda[C], dh0 ([C] if h0_bstride == 0 else
+ * [B,C]; may be NULL) in fp32, OVERWRITTEN (not accumulated), deterministic (two-pass reduction).
+ * workspace: bdlru_gated_scan_bwd_workspace_bytes(B, T, C) bytes of device memory. */
+size_t bdlru_gated_scan_bwd_workspace_bytes(int B, int T, int C);
+int bdlru_gated_scan_bwd(bdlru_view xp, bdlru_view r, bdlru_view i, const float* Lambda,
+                         const float* h0, int64_t h0_bstride, bdlru_view z,
+                         bdlru_view h, bdlru_view grad,
+                         bdlru_view dxp, bdlru_view dr, bdlru_view di, bdlru_view dz,
+                         float* dLambda, float* dh0, void* workspace, size_t workspace_bytes,
+                         int B, int T, int C, int dtype, void* stream);
+
+/* Channel-last raw scan (no gate math): h_t = a_t * h_{t-1} + b_t on [B, T, C] views, fp32 or bf16 I/O.
+ * Same tiling as S1; used when gates are produced elsewhere.  bwd writes da, db (and dh0 like S1). */
+int bdlru_scan_cl_fwd(bdlru_view a, bdlru_view b, const float* h0, int64_t h0_bstride, bdlru_view h,
+                      int B, int T, int C, int dtype, void* stream);
+int bdlru_scan_cl_bwd(bdlru_view a, const float* h0, int64_t h0_bstride, bdlru_view h, bdlru_view grad,
+                      bdlru_view da, bdlru_view db, float* dh0, void* workspace, size_t workspace_bytes,
+                      int B, int T, int C, int dtype, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Causal depthwise conv1d (+bias, +SiLU) on channel-last [B, T, C] views.
+ * Replaces causal_conv1d_fn(x=[B,C,T] channel-last strides, weight=[C,W], bias=[C], activation)
+ * (RecBLR.py:188-193; semantics pinned by the fallback RecBLR.py:185).
+ *   y_t = act(bias + sum_{j<W} weight[c][j] * x_{t-(W-1)+j}),  x_{<0} = 0,  W in [1, 4].
+ * weight/bias/dweight/dbias are fp32; bias may be NULL; silu != 0 applies SiLU.
+ * ------------------------------------------------------------------------------------------- */
+int bdlru_conv1d_fwd(bdlru_view x, const float* weight, const float* bias, bdlru_view y,
+                     int B, int T, int C, int W, int silu, int dtype, void* stream);
+size_t bdlru_conv1d_bwd_workspace_bytes(int B, int T, int C, int W);
+int bdlru_conv1d_bwd(bdlru_view x, const float* weight, const float* bias, bdlru_view grad_y,
+                     bdlru_view dx, float* dweight /* [C,W] */, float* dbias /* [C] or NULL */,
+                     void* workspace, size_t workspace_bytes,
+                     int B, int T, int C, int W, int silu, int dtype, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Front end: out[n,:] = LayerNorm(dropout(table[ids[n],:])) * gamma + beta   (RecBLR.py:76-78).
+ * ids int64 [n_tokens]; table fp32 or bf16 [n_items, D] (dtype); out in `dtype`; gamma/beta fp32.
+ * Dropout (p in [0,1)) uses a counter-based generator keyed by (seed, token, channel); the mask is
+ * recomputed in the backward from the same seed.  rstd/mean (fp32 [n_tokens]) are saved for backward.
+ * bwd scatter-adds into dtable (fp32 [n_items, D], NOT zeroed here) skipping ids == padding_idx
+ * (pass -1 for none), and writes dgamma/dbeta.
+ * ------------------------------------------------------------------------------------------- */
+int bdlru_embed_ln_fwd(const int64_t* ids, const void* table, const float* gamma, const float* beta,
+                       void* out, float* mean, float* rstd, int64_t n_tokens, int64_t n_items, int D,
+                       float eps, float dropout_p, uint64_t seed, int dtype, void* stream);
+size_t bdlru_embed_ln_bwd_workspace_bytes(int64_t n_tokens, int D);
+int bdlru_embed_ln_bwd(const int64_t* ids, const void* table, const float* gamma, const void* grad_out,
+                       const float* mean, const float* rstd, float* dtable, float* dgamma, float* dbeta,
+                       void* workspace, size_t workspace_bytes, int64_t n_tokens, int64_t n_items, int D,
+                       float dropout_p, uint64_t seed, int64_t padding_idx, int dtype, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Full-sort scoring with fused streaming top-k (RecBLR.py:114-122 + RecBole's scores[:,0] = -inf and
+ * torch.topk).  Q [n_users, D] and E [n_rows, D] are bf16 row-major (D % 64 == 0,
+ * D <= 256), accumulated in fp32 on the tcgen05 tensor cores; the [n_users, n_rows] logits are never
+ * written to memory.  Row j of E has global item id id_offset + j (row-sharded tables); the item with
+ * global id mask_id (pass -1 for none; RecBole masks id 0) is excluded.  Results are ordered by score
+ * descending, ties broken by LOWEST item id.  1 <= k <= 32.
+ *   out_scores fp32 [n_users, k], out_ids int32 [n_users, k]  (-inf / -1 when fewer than k candidates).
+ * ------------------------------------------------------------------------------------------- */
+size_t bdlru_fullsort_topk_workspace_bytes(int64_t n_users, int64_t n_rows, int D, int k);
+int bdlru_fullsort_topk(const void* Q, const void* E, int64_t n_users, int64_t n_rows, int D, int k,
+                        int64_t id_offset, int64_t mask_id, float* out_scores, int32_t* out_ids,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* Merge of per-shard candidate lists (the NCCL top-k merge's local step): cand_* are
+ * [n_users, n_lists * k] (any order inside); keeps the k best by (score desc, id asc). */
+int bdlru_topk_merge(const float* cand_scores, const int32_t* cand_ids, int64_t n_users, int n_lists, int k,
+                     float* out_scores, int32_t* out_ids, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Full-softmax cross-entropy over all item rows (RecBLR.py:99-103) without materialising the logits.
+ * fwd: per user b, over this shard's rows: row_max[b], row_sumexp[b] = sum_j exp(l_bj - row_max[b]),
+ *      pos_logit[b] = l_{b,pos_b} if id_offset <= pos_b < id_offset + n_rows else untouched.
+ *      (single GPU: loss = mean_b(row_max + log(row_sumexp) - pos_logit); sharded: reduce first.)
+ * bwd: given the global lse[b] and the upstream scale (dloss / n_users_total), recomputes the logits
+ *      tile by tile and writes dQ (fp32 [n_users, D], overwritten) and dE (fp32 [n_rows, D],
+ *      overwritten):  P = exp(l - lse) - onehot;  dQ = scale * P E;  dE = scale * P^T Q.
+ * pos int64 [n_users] holds GLOBAL item ids.
+ * ------------------------------------------------------------------------------------------- */
+size_t bdlru_fullsort_ce_workspace_bytes(int64_t n_users, int64_t n_rows, int D);
+int bdlru_fullsort_ce_fwd(const void* Q, const void* E, const int64_t* pos, int64_t n_users, int64_t n_rows,
+                          int D, int64_t id_offset, float* row_max, float* row_sumexp, float* pos_logit,
+                          void* workspace, size_t workspace_bytes, void* stream);
+int bdlru_fullsort_ce_bwd(const void* Q, const void* E, const int64_t* pos, const float* lse, float scale,
+                          int64_t n_users, int64_t n_rows, int D, int64_t id_offset,
+                          float* dQ, float* dE, void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BDLRU_H_ */
