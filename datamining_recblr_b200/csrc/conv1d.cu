@@ -32,7 +32,7 @@ struct ConvParams {
 };
 
 template <typename T, int W, int S, bool SILU>
-__global__ void __launch_bounds__(256) conv_fwd_kernel(const ConvParams p) {
+__global__ void __launch_bounds__(256, 2) conv_fwd_kernel(const ConvParams p) {
   const int tc = threadIdx.x, ty = threadIdx.y;
   const int c = (blockIdx.x * p.tcn + tc) * 4;
   float wv[4][W], bv[4];
@@ -72,9 +72,14 @@ __global__ void __launch_bounds__(256) conv_fwd_kernel(const ConvParams p) {
   }
 }
 
-template <typename T, int W, int S, bool SILU>
-__global__ void __launch_bounds__(256) conv_bwd_kernel(const ConvParams p) {
+// Backward.  A work item is (batch row, run of RUN consecutive time steps); the thread walks the run from its
+// last chunk of S steps down to its first, carrying in registers the W-1 lowest x rows and the W-1 lowest
+// dpre rows of the chunk above, so that each x / dy row is loaded once and each activation derivative is
+// computed once (only the W-1 rows above a run are recomputed).
+template <typename T, int W, int S, int RUN, bool SILU>
+__global__ void __launch_bounds__(256, 2) conv_bwd_kernel(const ConvParams p) {
   extern __shared__ float red[];  // [ny][tcn][4*(W+1)]
+  constexpr int H = W - 1;
   const int tc = threadIdx.x, ty = threadIdx.y;
   const int c = (blockIdx.x * p.tcn + tc) * 4;
   float wv[4][W], bv[4];
@@ -91,63 +96,92 @@ __global__ void __launch_bounds__(256) conv_bwd_kernel(const ConvParams p) {
 #pragma unroll
     for (int j = 0; j < W; ++j) dw[e][j] = 0.f;
   }
-  constexpr int NX = S + 2 * (W - 1);  // x rows t0-(W-1) .. t0+S-1+(W-1)
-  constexpr int ND = S + (W - 1);      // dy / dpre rows t0 .. t0+S-1+(W-1)
+  const long xrb = p.x.rs * (long)sizeof(T), dyrb = p.dy.rs * (long)sizeof(T), dxrb = p.dx.rs * (long)sizeof(T);
+
+  auto ld_row = [&](const unsigned char* base, long rb, int t, float (&v)[4]) {
+    if (t >= 0 && t < p.T) {
+      IO<T>::load(base + t * rb, v);
+    } else {
+      v[0] = v[1] = v[2] = v[3] = 0.f;
+    }
+  };
+  // dpre_t = dy_t * act'(pre_t) with pre_t = bias + sum_j w_j x_{t-H+j}; xw[j] = x_{t-H+j}
+  auto dpre_of = [&](const float (&dyv)[4], const float (*xw)[4], float (&out)[4]) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      if (SILU) {
+        float pre = bv[e];
+#pragma unroll
+        for (int j = 0; j < W; ++j) pre = fmaf(wv[e][j], xw[j][e], pre);
+        const float sg = sigmoid_f(pre);
+        out[e] = dyv[e] * silu_grad_f(pre, sg);
+      } else {
+        out[e] = dyv[e];
+      }
+    }
+  };
+
   for (long item = (long)blockIdx.y * blockDim.y + ty; item < p.n_items; item += (long)gridDim.y * blockDim.y) {
     const long b = item / p.n_chunk;
-    const int t0 = (int)(item % p.n_chunk) * S;
-    float xs[NX][4], dp[ND][4];
+    const int t_lo = (int)(item % p.n_chunk) * RUN;
+    const int t_hi = min(p.T, t_lo + RUN);
+    const unsigned char* xb = cat<T>(p.x, b, 0, c);
+    const unsigned char* dyb = cat<T>(p.dy, b, 0, c);
+    unsigned char* dxb = const_cast<unsigned char*>(cat<T>(p.dx, b, 0, c));
+    const int n_ch = (t_hi - t_lo + S - 1) / S;
+    int t0 = t_lo + (n_ch - 1) * S;  // top chunk [t0, t0+S)
+    // rows carried from "above": xs[S .. S+2H-1] = x_{t0+S-H .. t0+S+H-1}, dp[S .. S+H-1] = dpre_{t0+S .. t0+S+H-1}
+    float xs[S + 2 * H][4], dp[S + H][4];
 #pragma unroll
-    for (int s = 0; s < NX; ++s) {
-      const int t = t0 + s - (W - 1);
-      if (t >= 0 && t < p.T) {
-        IO<T>::load(cat<T>(p.x, b, t, c), xs[s]);
-      } else {
-        xs[s][0] = xs[s][1] = xs[s][2] = xs[s][3] = 0.f;
-      }
+    for (int j = 0; j < 2 * H; ++j) ld_row(xb, xrb, t0 + S - H + j, xs[S + j]);
+#pragma unroll
+    for (int j = 0; j < H; ++j) {
+      float dyv[4];
+      ld_row(dyb, dyrb, t0 + S + j, dyv);  // zero beyond T => dpre = 0
+      dpre_of(dyv, &xs[S + j], dp[S + j]);
     }
+    for (int ch = 0; ch < n_ch; ++ch, t0 -= S) {
+      // new rows of this chunk: xs[0 .. S-1] = x_{t0-H .. t0+S-H-1}, dy rows t0 .. t0+S-1
+      float dyv[S][4];
 #pragma unroll
-    for (int s = 0; s < ND; ++s) {
-      const int t = t0 + s;
-      if (t < p.T) {
-        IO<T>::load(cat<T>(p.dy, b, t, c), dp[s]);
-      } else {
-        dp[s][0] = dp[s][1] = dp[s][2] = dp[s][3] = 0.f;
+      for (int s = 0; s < S; ++s) {
+        ld_row(xb, xrb, t0 - H + s, xs[s]);
+        ld_row(dyb, dyrb, t0 + s, dyv[s]);
       }
-    }
-    // dpre_t = dy_t * act'(pre_t); pre_t uses x rows s .. s+W-1 of the local window
 #pragma unroll
-    for (int s = 0; s < ND; ++s) {
+      for (int s = 0; s < S; ++s) {
+        dpre_of(dyv[s], &xs[s], dp[s]);  // window of x_{t-H .. t} for t = t0+s is xs[s .. s+H]
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        if (SILU) {
-          float pre = bv[e];
-#pragma unroll
-          for (int j = 0; j < W; ++j) pre = fmaf(wv[e][j], xs[s + j][e], pre);
-          const float sg = sigmoid_f(pre);
-          dp[s][e] *= silu_grad_f(pre, sg);
-        }
-        if (s < S) {  // own rows only: parameter gradients
+        for (int e = 0; e < 4; ++e) {
           db[e] += dp[s][e];
 #pragma unroll
           for (int j = 0; j < W; ++j) dw[e][j] = fmaf(dp[s][e], xs[s + j][e], dw[e][j]);
         }
       }
-    }
-    // dx_t = sum_j w_j * dpre_{t + (W-1) - j}
+      // dx_t = sum_j w_j * dpre_{t + H - j}
 #pragma unroll
-    for (int s = 0; s < S; ++s) {
-      if (t0 + s < p.T) {
-        float o[4];
+      for (int s = 0; s < S; ++s) {
+        if (t0 + s < p.T) {
+          float o[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          float acc = 0.f;
+          for (int e = 0; e < 4; ++e) {
+            float acc = 0.f;
 #pragma unroll
-          for (int j = 0; j < W; ++j) acc = fmaf(wv[e][j], dp[s + (W - 1) - j][e], acc);
-          o[e] = acc;
+            for (int j = 0; j < W; ++j) acc = fmaf(wv[e][j], dp[s + H - j][e], acc);
+            o[e] = acc;
+          }
+          IO<T>::store(dxb + (long)(t0 + s) * dxrb, o);
         }
-        IO<T>::store(const_cast<unsigned char*>(cat<T>(p.dx, b, t0 + s, c)), o);
       }
+      // hand the lowest rows down to the next (earlier) chunk
+#pragma unroll
+      for (int j = 0; j < 2 * H; ++j)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) xs[S + j][e] = xs[j][e];
+#pragma unroll
+      for (int j = 0; j < H; ++j)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) dp[S + j][e] = dp[j][e];
     }
   }
   // block reduction over ty, then one partial row per CTA
@@ -183,12 +217,14 @@ __global__ void conv_reduce_partials(const float* __restrict__ part, int GY, int
     dbias[c] = s;
 }
 
-constexpr int kConvS = 8;
+constexpr int kConvS = 8;     // steps per thread, forward
+constexpr int kConvSB = 4;    // steps per chunk, backward
+constexpr int kConvRun = 32;  // time steps per backward work item (walked chunk by chunk with carried halos)
 
 struct ConvTiling {
   int tcn, ny, n_ctile, n_chunk, gy;
 };
-static ConvTiling conv_tiling(int B, int T, int C, int ctas_per_sm) {
+static ConvTiling conv_tiling(int B, int T, int C, int ctas_per_sm, int S) {
   ConvTiling t;
   const int cvec = C / 4;
   t.tcn = 1;
@@ -196,7 +232,7 @@ static ConvTiling conv_tiling(int B, int T, int C, int ctas_per_sm) {
   t.n_ctile = cvec / t.tcn;
   t.ny = 256 / t.tcn;
   if (t.ny > 32) t.ny = 32;
-  t.n_chunk = (T + kConvS - 1) / kConvS;
+  t.n_chunk = (T + S - 1) / S;
   const long items = (long)B * t.n_chunk;
   long gy = ((long)sm_count() * ctas_per_sm + t.n_ctile - 1) / t.n_ctile;
   const long need = (items + t.ny - 1) / t.ny;
@@ -217,7 +253,7 @@ static CView cmk(const bdlru_view& v) { return CView{reinterpret_cast<const unsi
 
 template <typename T, int W>
 static int conv_fwd_launch(ConvParams& p, bool silu, cudaStream_t st) {
-  ConvTiling t = conv_tiling(p.B, p.T, p.C, 4);
+  ConvTiling t = conv_tiling(p.B, p.T, p.C, 4, kConvS);
   p.tcn = t.tcn; p.n_chunk = t.n_chunk; p.n_items = (long)p.B * t.n_chunk;
   dim3 grid(t.n_ctile, t.gy), block(t.tcn, t.ny);
   if (silu)
@@ -231,7 +267,7 @@ static int conv_fwd_launch(ConvParams& p, bool silu, cudaStream_t st) {
 template <typename T, int W>
 static int conv_bwd_launch(ConvParams& p, bool silu, float* dweight, float* dbias, void* ws, size_t ws_bytes,
                            cudaStream_t st) {
-  ConvTiling t = conv_tiling(p.B, p.T, p.C, 2);
+  ConvTiling t = conv_tiling(p.B, p.T, p.C, 4, kConvRun);
   p.tcn = t.tcn; p.n_chunk = t.n_chunk; p.n_items = (long)p.B * t.n_chunk;
   const size_t need = (size_t)t.gy * p.C * (W + 1) * sizeof(float);
   BDLRU_REQUIRE(ws && ws_bytes >= need, "conv1d_bwd: workspace too small (%zu < %zu)", ws_bytes, need);
@@ -239,9 +275,9 @@ static int conv_bwd_launch(ConvParams& p, bool silu, float* dweight, float* dbia
   dim3 grid(t.n_ctile, t.gy), block(t.tcn, t.ny);
   const size_t smem = (size_t)t.ny * t.tcn * 4 * (W + 1) * sizeof(float);
   if (silu)
-    conv_bwd_kernel<T, W, kConvS, true><<<grid, block, smem, st>>>(p);
+    conv_bwd_kernel<T, W, kConvSB, kConvRun, true><<<grid, block, smem, st>>>(p);
   else
-    conv_bwd_kernel<T, W, kConvS, false><<<grid, block, smem, st>>>(p);
+    conv_bwd_kernel<T, W, kConvSB, kConvRun, false><<<grid, block, smem, st>>>(p);
   BDLRU_LAUNCHED();
   const int n = p.C * (W + 1);
   conv_reduce_partials<<<(n + 127) / 128, 128, 0, st>>>(p.part, t.gy, p.C, W, dweight, dbias);
@@ -300,8 +336,8 @@ extern "C" BDLRU_API int bdlru_conv1d_fwd(bdlru_view x, const float* weight, con
 
 extern "C" BDLRU_API size_t bdlru_conv1d_bwd_workspace_bytes(int B, int T, int C, int W) {
   (void)B; (void)T;
-  // gy <= SMs * 2 / n_ctile + 1 partial rows of C*(W+1) floats
-  return ((size_t)sm_count() * 2 + 2) * (size_t)C * (W + 1) * sizeof(float);
+  // gy <= SMs * 4 / n_ctile + 1 partial rows of C*(W+1) floats
+  return ((size_t)sm_count() * 4 + 2) * (size_t)C * (W + 1) * sizeof(float);
 }
 
 extern "C" BDLRU_API int bdlru_conv1d_bwd(bdlru_view x, const float* weight, const float* bias, bdlru_view grad_y, bdlru_view dx,

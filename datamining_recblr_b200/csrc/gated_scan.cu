@@ -44,65 +44,77 @@ template <typename T>
 __device__ __forceinline__ const unsigned char* at(const View& v, long b, long t, int c) {
   return v.p + ((b * v.bs + t * v.rs + c) * (long)sizeof(T));
 }
+template <typename T>
+__device__ __forceinline__ long row_bytes(const View& v) { return v.rs * (long)sizeof(T); }
+
+// NTC: threads per CTA when known at compile time (256: every smem offset folds into an immediate),
+// 0: read blockDim.x (rare small-C shapes).
+template <int NTC>
+__device__ __forceinline__ int cta_threads() { return NTC ? NTC : (int)blockDim.x; }
 
 // ------------------------------------------------------------------------------------------ forward
-template <typename T, int S, bool GATED, bool HAS_Z>
+template <typename T, int S, bool GATED, bool HAS_Z, int NTC>
 __global__ void __launch_bounds__(256) gscan_fwd_kernel(const GScanParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
   constexpr int EB = IO<T>::BYTES;
   constexpr int NARR = (GATED ? 3 : 2) + (HAS_Z ? 1 : 0);
-  const int NT = blockDim.x, tid = threadIdx.x;
+  const int NT = cta_threads<NTC>(), tid = threadIdx.x;
   const int tc = tid % p.tcn, ts = tid / p.tcn;
-  const size_t arr_bytes = (size_t)S * NT * EB;
-  const size_t stage_bytes = arr_bytes * NARR;
+  const int ROW = NT * EB;                      // bytes between consecutive staged vectors of a thread
+  const int stage_bytes = NARR * S * ROW;
+  unsigned char* mine = smem + tid * EB;        // thread-private column of the staging area
   float4* agg = reinterpret_cast<float4*>(smem + 2 * stage_bytes);  // [2 parity][2 (A,H)][NT]
 
   const int my_units = (p.n_units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-  const long my_total = (long)my_units * p.n_iter;
+  const int my_total = my_units * p.n_iter;
   const int Tb = p.NS * S;
+  // channel offset is fixed per CTA (the host sizes the grid as a multiple of n_ctile); the producer
+  // side keeps its own (unit, iteration) cursor so that no division happens per iteration.
+  const int c = (((int)blockIdx.x % p.n_ctile) * p.tcn + tc) * 4;
+  const long xrb = row_bytes<T>(p.x), rrb = row_bytes<T>(p.r), irb = row_bytes<T>(p.i), zrb = row_bytes<T>(p.z);
+  const long hrb = row_bytes<T>(p.h), yrb = row_bytes<T>(p.y);
 
-  auto slot = [&](int buf, int arr, int s) -> unsigned char* {
-    return smem + buf * stage_bytes + arr * arr_bytes + ((size_t)s * NT + tid) * EB;
-  };
-  auto issue = [&](long w, int buf) {
-    if (w < my_total) {
-      const int k = (int)(w / p.n_iter), it = (int)(w % p.n_iter);
-      const int u = blockIdx.x + k * gridDim.x;
-      const long b = u / p.n_ctile;
-      const int c = ((u % p.n_ctile) * p.tcn + tc) * 4;
-      const int t0 = it * Tb + ts * S;
+  int pu = blockIdx.x, pit = 0;  // producer cursor
+  auto issue = [&](int buf) {
+    if (pu < p.n_units) {
+      const long b = pu / p.n_ctile;
+      const int t0 = pit * Tb + ts * S;
+      unsigned char* dst = mine + buf * stage_bytes;
+      const unsigned char* px = at<T>(p.x, b, t0, c);
+      const unsigned char* pr = at<T>(p.r, b, t0, c);
+      const unsigned char* pi = GATED ? at<T>(p.i, b, t0, c) : nullptr;
+      const unsigned char* pz = HAS_Z ? at<T>(p.z, b, t0, c) : nullptr;
 #pragma unroll
       for (int s = 0; s < S; ++s) {
-        const int t = t0 + s;
-        if (t < p.T) {
-          cp_async<EB>(slot(buf, 0, s), at<T>(p.x, b, t, c));
-          cp_async<EB>(slot(buf, 1, s), at<T>(p.r, b, t, c));
-          if (GATED) cp_async<EB>(slot(buf, 2, s), at<T>(p.i, b, t, c));
-          if (HAS_Z) cp_async<EB>(slot(buf, NARR - 1, s), at<T>(p.z, b, t, c));
+        if (t0 + s < p.T) {
+          cp_async<EB>(dst + (0 * S + s) * ROW, px + s * xrb);
+          cp_async<EB>(dst + (1 * S + s) * ROW, pr + s * rrb);
+          if (GATED) cp_async<EB>(dst + (2 * S + s) * ROW, pi + s * irb);
+          if (HAS_Z) cp_async<EB>(dst + ((NARR - 1) * S + s) * ROW, pz + s * zrb);
         }
       }
+      if (++pit == p.n_iter) { pit = 0; pu += gridDim.x; }
     }
     cp_async_commit();
   };
 
-  issue(0, 0);
-  issue(1, 1);
+  issue(0);
+  issue(1);
 
   float state[4] = {0.f, 0.f, 0.f, 0.f};
   float csp[4] = {0.f, 0.f, 0.f, 0.f};
-  for (long w = 0; w < my_total; ++w) {
-    const int buf = (int)(w & 1);
-    const int k = (int)(w / p.n_iter), it = (int)(w % p.n_iter);
-    const int u = blockIdx.x + k * gridDim.x;
-    const long b = u / p.n_ctile;
-    const int c = ((u % p.n_ctile) * p.tcn + tc) * 4;
+  if (GATED) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) csp[e] = softplus_acc(p.lambda[c + e]);
+  }
+  int cu = blockIdx.x, it = 0, buf = 0;  // consumer cursor
+  long b = cu / p.n_ctile;
+  for (int w = 0; w < my_total; ++w, buf ^= 1) {
     const int t0 = it * Tb + ts * S;
+    const unsigned char* src = mine + buf * stage_bytes;
     if (it == 0) {
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        if (GATED) csp[e] = softplus_acc(p.lambda[c + e]);
-        state[e] = p.h0 ? p.h0[b * p.h0_bs + c + e] : 0.f;
-      }
+      for (int e = 0; e < 4; ++e) state[e] = p.h0 ? p.h0[b * p.h0_bs + c + e] : 0.f;
     }
     cp_async_wait<1>();
 
@@ -113,9 +125,9 @@ __global__ void __launch_bounds__(256) gscan_fwd_kernel(const GScanParams p) {
     for (int s = 0; s < S; ++s) {
       if (t0 + s < p.T) {
         float xv[4], rv[4], iv[4];
-        IO<T>::load(slot(buf, 0, s), xv);
-        IO<T>::load(slot(buf, 1, s), rv);
-        if (GATED) IO<T>::load(slot(buf, 2, s), iv);
+        IO<T>::load(src + (0 * S + s) * ROW, xv);
+        IO<T>::load(src + (1 * S + s) * ROW, rv);
+        if (GATED) IO<T>::load(src + (2 * S + s) * ROW, iv);
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           float a, bb;
@@ -134,11 +146,11 @@ __global__ void __launch_bounds__(256) gscan_fwd_kernel(const GScanParams p) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) { hloc[s][e] = hl[e]; cum[s][e] = ca[e]; }
     }
-    if (!HAS_Z) issue(w + 2, buf);  // slots of this buffer are consumed: refill (thread-private)
+    if (!HAS_Z) issue(buf);  // slots of this buffer are consumed: refill (thread-private)
 
     // combine chunk aggregates across the NS slices
-    float4* aggA = agg + (size_t)(buf * 2 + 0) * NT;
-    float4* aggH = agg + (size_t)(buf * 2 + 1) * NT;
+    float4* aggA = agg + (buf * 2 + 0) * NT;
+    float4* aggH = agg + (buf * 2 + 1) * NT;
     aggA[tid] = make_float4(ca[0], ca[1], ca[2], ca[3]);
     aggH[tid] = make_float4(hl[0], hl[1], hl[2], hl[3]);
     __syncthreads();
@@ -153,32 +165,34 @@ __global__ void __launch_bounds__(256) gscan_fwd_kernel(const GScanParams p) {
     }
 
     // pass 2: apply the carry-in and write
+    unsigned char* ph = const_cast<unsigned char*>(at<T>(p.h, b, t0, c));
+    unsigned char* py = HAS_Z ? const_cast<unsigned char*>(at<T>(p.y, b, t0, c)) : nullptr;
 #pragma unroll
     for (int s = 0; s < S; ++s) {
-      const int t = t0 + s;
-      if (t < p.T) {
+      if (t0 + s < p.T) {
         float hv[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) hv[e] = fmaf(cum[s][e], cin[e], hloc[s][e]);
-        IO<T>::store(const_cast<unsigned char*>(at<T>(p.h, b, t, c)), hv);
+        IO<T>::store(ph + s * hrb, hv);
         if (HAS_Z) {
           float zv[4], yv[4];
-          IO<T>::load(slot(buf, NARR - 1, s), zv);
+          IO<T>::load(src + ((NARR - 1) * S + s) * ROW, zv);
 #pragma unroll
           for (int e = 0; e < 4; ++e) yv[e] = silu_f(zv[e]) * hv[e];
-          IO<T>::store(const_cast<unsigned char*>(at<T>(p.y, b, t, c)), yv);
+          IO<T>::store(py + s * yrb, yv);
         }
       }
     }
-    if (HAS_Z) issue(w + 2, buf);
+    if (HAS_Z) issue(buf);
+    if (++it == p.n_iter) { it = 0; cu += gridDim.x; b = cu / p.n_ctile; }
   }
   cp_async_wait<0>();
 }
 
 // ------------------------------------------------------------------------------------------ backward
-// Staged arrays: GATED: x', r, i, g, hprev[S] (+ z and one more h entry when HAS_Z)
-//                RAW  : a (in p.r), g, hprev[S]
-template <typename T, int S, bool GATED, bool HAS_Z>
+// Staged vectors per thread: GATED: x'[S], r[S], i[S], g[S], h[t0-1 ..][NH] (+ z[S] and one more h entry
+// when HAS_Z);  RAW: a[S] (in p.r), g[S], h[NH].
+template <typename T, int S, bool GATED, bool HAS_Z, int NTC>
 __global__ void __launch_bounds__(256) gscan_bwd_kernel(const GScanParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
   constexpr int EB = IO<T>::BYTES;
@@ -186,108 +200,118 @@ __global__ void __launch_bounds__(256) gscan_bwd_kernel(const GScanParams p) {
   constexpr int NVEC = (GATED ? 4 : 2) * S + NH + (HAS_Z ? S : 0);  // vectors staged per thread
   constexpr int OFF_X = 0, OFF_R = GATED ? S : 0, OFF_I = 2 * S, OFF_G = GATED ? 3 * S : S;
   constexpr int OFF_H = OFF_G + S, OFF_Z = OFF_H + NH;
-  const int NT = blockDim.x, tid = threadIdx.x;
+  const int NT = cta_threads<NTC>(), tid = threadIdx.x;
   const int tc = tid % p.tcn, ts = tid / p.tcn;
-  const size_t stage_bytes = (size_t)NVEC * NT * EB;
+  const int ROW = NT * EB;
+  const int stage_bytes = NVEC * ROW;
+  unsigned char* mine = smem + tid * EB;
   float4* agg = reinterpret_cast<float4*>(smem + 2 * stage_bytes);  // [2][2][NT]
   // GATED pass 1 leaves sigmoid(r) and alpha for pass 2 in thread-private fp32 scratch: for fp32 I/O it
   // overwrites the consumed r and g staging slots, for bf16 I/O (8-byte slots) it has its own array.
   constexpr bool INPLACE = sizeof(T) == 4;
-  float4* scr = agg + 4 * NT;  // !INPLACE: [2 (sr, a)][S][NT]
+  float4* scr = agg + 4 * NT + tid;  // !INPLACE: [2 (sr, a)][S][NT]
 
   const int my_units = (p.n_units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-  const long my_total = (long)my_units * p.n_iter;
+  const int my_total = my_units * p.n_iter;
   const int Tb = p.NS * S;
+  const int c = (((int)blockIdx.x % p.n_ctile) * p.tcn + tc) * 4;  // fixed per CTA
+  const long xrb = row_bytes<T>(p.x), rrb = row_bytes<T>(p.r), irb = row_bytes<T>(p.i), zrb = row_bytes<T>(p.z);
+  const long hrb = row_bytes<T>(p.h), grb = row_bytes<T>(p.g);
+  const long dxrb = row_bytes<T>(p.dx), drrb = row_bytes<T>(p.dr), dirb = row_bytes<T>(p.di), dzrb = row_bytes<T>(p.dz);
 
-  auto slot = [&](int buf, int v) -> unsigned char* {
-    return smem + buf * stage_bytes + ((size_t)v * NT + tid) * EB;
-  };
-  auto scr_sr = [&](int buf, int s) -> float4* {
-    return INPLACE ? reinterpret_cast<float4*>(slot(buf, OFF_R + s)) : scr + (size_t)(0 * S + s) * NT + tid;
-  };
-  auto scr_a = [&](int buf, int s) -> float4* {
-    return INPLACE ? reinterpret_cast<float4*>(slot(buf, OFF_G + s)) : scr + (size_t)(1 * S + s) * NT + tid;
-  };
-  auto issue = [&](long w, int buf) {
-    if (w < my_total) {
-      const int k = (int)(w / p.n_iter), it = p.n_iter - 1 - (int)(w % p.n_iter);
-      const int u = blockIdx.x + k * gridDim.x;
-      const long b = u / p.n_ctile;
-      const int c = ((u % p.n_ctile) * p.tcn + tc) * 4;
-      const int t0 = it * Tb + ts * S;
+  int pu = blockIdx.x, pit = p.n_iter - 1;  // producer cursor (time blocks run backwards)
+  auto issue = [&](int buf) {
+    if (pu < p.n_units) {
+      const long b = pu / p.n_ctile;
+      const int t0 = pit * Tb + ts * S;
+      unsigned char* dst = mine + buf * stage_bytes;
+      const unsigned char* px = GATED ? at<T>(p.x, b, t0, c) : nullptr;
+      const unsigned char* pr = at<T>(p.r, b, t0, c);
+      const unsigned char* pi = GATED ? at<T>(p.i, b, t0, c) : nullptr;
+      const unsigned char* pg = at<T>(p.g, b, t0, c);
+      const unsigned char* pz = HAS_Z ? at<T>(p.z, b, t0, c) : nullptr;
+      const unsigned char* ph = at<T>(p.h, b, t0 - 1, c);
 #pragma unroll
       for (int s = 0; s < S; ++s) {
-        const int t = t0 + s;
-        if (t < p.T) {
-          if (GATED) cp_async<EB>(slot(buf, OFF_X + s), at<T>(p.x, b, t, c));
-          cp_async<EB>(slot(buf, OFF_R + s), at<T>(p.r, b, t, c));
-          if (GATED) cp_async<EB>(slot(buf, OFF_I + s), at<T>(p.i, b, t, c));
-          cp_async<EB>(slot(buf, OFF_G + s), at<T>(p.g, b, t, c));
-          if (HAS_Z) cp_async<EB>(slot(buf, OFF_Z + s), at<T>(p.z, b, t, c));
+        if (t0 + s < p.T) {
+          if (GATED) cp_async<EB>(dst + (OFF_X + s) * ROW, px + s * xrb);
+          cp_async<EB>(dst + (OFF_R + s) * ROW, pr + s * rrb);
+          if (GATED) cp_async<EB>(dst + (OFF_I + s) * ROW, pi + s * irb);
+          cp_async<EB>(dst + (OFF_G + s) * ROW, pg + s * grb);
+          if (HAS_Z) cp_async<EB>(dst + (OFF_Z + s) * ROW, pz + s * zrb);
         }
       }
 #pragma unroll
       for (int s = 0; s < NH; ++s) {
         const int t = t0 + s - 1;
-        if (t >= 0 && t < p.T) cp_async<EB>(slot(buf, OFF_H + s), at<T>(p.h, b, t, c));
+        if (t >= 0 && t < p.T) cp_async<EB>(dst + (OFF_H + s) * ROW, ph + s * hrb);
       }
+      if (--pit < 0) { pit = p.n_iter - 1; pu += gridDim.x; }
     }
     cp_async_commit();
   };
 
-  issue(0, 0);
-  issue(1, 1);
+  issue(0);
+  issue(1);
 
   float ustate[4] = {0.f, 0.f, 0.f, 0.f};
   float csp[4] = {0.f, 0.f, 0.f, 0.f}, h0v[4] = {0.f, 0.f, 0.f, 0.f};
   float dc_acc[4] = {0.f, 0.f, 0.f, 0.f}, dh0_acc[4] = {0.f, 0.f, 0.f, 0.f};
+  if (GATED) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) csp[e] = softplus_acc(p.lambda[c + e]);
+  }
 
-  for (long w = 0; w < my_total; ++w) {
-    const int buf = (int)(w & 1);
-    const int k = (int)(w / p.n_iter), it = p.n_iter - 1 - (int)(w % p.n_iter);
-    const int u = blockIdx.x + k * gridDim.x;
-    const long b = u / p.n_ctile;
-    const int c = ((u % p.n_ctile) * p.tcn + tc) * 4;
+  int cu = blockIdx.x, it = p.n_iter - 1, buf = 0;  // consumer cursor
+  long b = cu / p.n_ctile;
+  for (int w = 0; w < my_total; ++w, buf ^= 1) {
     const int t0 = it * Tb + ts * S;
+    unsigned char* src = mine + buf * stage_bytes;
+    auto scr_sr = [&](int s) -> float4* {
+      return INPLACE ? reinterpret_cast<float4*>(src + (OFF_R + s) * ROW) : scr + (0 * S + s) * NT;
+    };
+    auto scr_a = [&](int s) -> float4* {
+      return INPLACE ? reinterpret_cast<float4*>(src + (OFF_G + s) * ROW) : scr + (1 * S + s) * NT;
+    };
     if (it == p.n_iter - 1) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        if (GATED) csp[e] = softplus_acc(p.lambda[c + e]);
         h0v[e] = p.h0 ? p.h0[b * p.h0_bs + c + e] : 0.f;
         ustate[e] = 0.f;
       }
     }
     cp_async_wait<1>();
 
-    // pass 1 (reverse time): local dh~ from u_in = 0; Pm = product of the gates AFTER step s
+    // pass 1 (reverse time): local dh~ from u_in = 0; pm = product of the gates AFTER step s
     float dloc[S][4], pm[S][4];
     float ul[4] = {0.f, 0.f, 0.f, 0.f}, pc[4] = {1.f, 1.f, 1.f, 1.f};
+    unsigned char* pdz = HAS_Z ? const_cast<unsigned char*>(at<T>(p.dz, b, t0, c)) : nullptr;
 #pragma unroll
     for (int s = S - 1; s >= 0; --s) {
       float av[4] = {1.f, 1.f, 1.f, 1.f}, gv[4] = {0.f, 0.f, 0.f, 0.f};
       if (t0 + s < p.T) {
         float rv[4];
-        IO<T>::load(slot(buf, OFF_R + s), rv);
-        IO<T>::load(slot(buf, OFF_G + s), gv);
+        IO<T>::load(src + (OFF_R + s) * ROW, rv);
+        IO<T>::load(src + (OFF_G + s) * ROW, gv);
         if (HAS_Z) {
           // upstream is dL/dy with y = silu(z) * h:  dz = dy * h_t * silu'(z),  g = dy * silu(z)
           float zv[4], hv[4], dzv[4];
-          IO<T>::load(slot(buf, OFF_Z + s), zv);
-          IO<T>::load(slot(buf, OFF_H + s + 1), hv);
+          IO<T>::load(src + (OFF_Z + s) * ROW, zv);
+          IO<T>::load(src + (OFF_H + s + 1) * ROW, hv);
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const float sz = sigmoid_f(zv[e]);
             dzv[e] = gv[e] * hv[e] * silu_grad_f(zv[e], sz);
             gv[e] *= zv[e] * sz;
           }
-          IO<T>::store(const_cast<unsigned char*>(at<T>(p.dz, b, t0 + s, c)), dzv);
+          IO<T>::store(pdz + s * dzrb, dzv);
         }
         if (GATED) {
           float srv[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) av[e] = gate_alpha(csp[e], rv[e], srv[e]);
-          *scr_sr(buf, s) = make_float4(srv[0], srv[1], srv[2], srv[3]);
-          *scr_a(buf, s) = make_float4(av[0], av[1], av[2], av[3]);
+          *scr_sr(s) = make_float4(srv[0], srv[1], srv[2], srv[3]);
+          *scr_a(s) = make_float4(av[0], av[1], av[2], av[3]);
         } else {
 #pragma unroll
           for (int e = 0; e < 4; ++e) av[e] = rv[e];
@@ -304,8 +328,8 @@ __global__ void __launch_bounds__(256) gscan_bwd_kernel(const GScanParams p) {
     }
 
     // combine (carry flows from later slices to earlier ones)
-    float4* aggA = agg + (size_t)(buf * 2 + 0) * NT;
-    float4* aggU = agg + (size_t)(buf * 2 + 1) * NT;
+    float4* aggA = agg + (buf * 2 + 0) * NT;
+    float4* aggU = agg + (buf * 2 + 1) * NT;
     aggA[tid] = make_float4(pc[0], pc[1], pc[2], pc[3]);
     aggU[tid] = make_float4(ul[0], ul[1], ul[2], ul[3]);
     __syncthreads();
@@ -329,6 +353,9 @@ __global__ void __launch_bounds__(256) gscan_bwd_kernel(const GScanParams p) {
     }
 
     // pass 2: true dh~ and the chain rule through the gate math
+    unsigned char* pdx = const_cast<unsigned char*>(at<T>(p.dx, b, t0, c));
+    unsigned char* pdr = const_cast<unsigned char*>(at<T>(p.dr, b, t0, c));
+    unsigned char* pdi = GATED ? const_cast<unsigned char*>(at<T>(p.di, b, t0, c)) : nullptr;
 #pragma unroll
     for (int s = 0; s < S; ++s) {
       const int t = t0 + s;
@@ -340,21 +367,21 @@ __global__ void __launch_bounds__(256) gscan_bwd_kernel(const GScanParams p) {
 #pragma unroll
           for (int e = 0; e < 4; ++e) hp[e] = h0v[e];
         } else {
-          IO<T>::load(slot(buf, OFF_H + s), hp);
+          IO<T>::load(src + (OFF_H + s) * ROW, hp);
         }
         if (GATED) {
           float xv[4], iv[4], dxv[4], drv[4], div[4];
-          IO<T>::load(slot(buf, OFF_X + s), xv);
-          IO<T>::load(slot(buf, OFF_I + s), iv);
-          const float4 sr4 = *scr_sr(buf, s);
-          const float4 a4 = *scr_a(buf, s);
+          IO<T>::load(src + (OFF_X + s) * ROW, xv);
+          IO<T>::load(src + (OFF_I + s) * ROW, iv);
+          const float4 sr4 = *scr_sr(s);
+          const float4 a4 = *scr_a(s);
           const float srv[4] = {sr4.x, sr4.y, sr4.z, sr4.w};
           const float av[4] = {a4.x, a4.y, a4.z, a4.w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const float si = sigmoid_f(iv[e]);
             const float v = one_minus_exp_neg(2.0f * csp[e] * srv[e], av[e] * av[e]) + 1e-8f;
-            const float rq = rsqrtf(v), q = v * rq;
+            const float rq = rsqrt_ftz(v), q = v * rq;
             const float dbeta = d[e] * xv[e];
             dxv[e] = d[e] * q * si;
             div[e] = dbeta * q * si * (1.0f - si);
@@ -363,19 +390,20 @@ __global__ void __launch_bounds__(256) gscan_bwd_kernel(const GScanParams p) {
             drv[e] = -csp[e] * daa * srv[e] * (1.0f - srv[e]);
             dc_acc[e] = fmaf(-daa, srv[e], dc_acc[e]);
           }
-          IO<T>::store(const_cast<unsigned char*>(at<T>(p.dx, b, t, c)), dxv);
-          IO<T>::store(const_cast<unsigned char*>(at<T>(p.dr, b, t, c)), drv);
-          IO<T>::store(const_cast<unsigned char*>(at<T>(p.di, b, t, c)), div);
+          IO<T>::store(pdx + s * dxrb, dxv);
+          IO<T>::store(pdr + s * drrb, drv);
+          IO<T>::store(pdi + s * dirb, div);
         } else {
           float dgv[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) dgv[e] = hp[e] * d[e];
-          IO<T>::store(const_cast<unsigned char*>(at<T>(p.dx, b, t, c)), d);     // d_tokens
-          IO<T>::store(const_cast<unsigned char*>(at<T>(p.dr, b, t, c)), dgv);   // d_gates
+          IO<T>::store(pdx + s * dxrb, d);     // d_tokens
+          IO<T>::store(pdr + s * drrb, dgv);   // d_gates
         }
       }
     }
-    issue(w + 2, buf);
+    issue(buf);
+    if (--it < 0) { it = p.n_iter - 1; cu += gridDim.x; b = cu / p.n_ctile; }
   }
   cp_async_wait<0>();
 
@@ -427,9 +455,9 @@ static Tiling make_tiling(int B, int T, int C) {
   t.n_ctile = cvec / t.tcn;
   // time slices per CTA: enough to cover T when it is short, at most 256 threads / 32 slices
   int ns = 256 / t.tcn;
-  if (ns > 32) ns = 32;
-  while (ns > 1 && (ns / 2) * S >= T) ns /= 2;
+  if (ns > 32) ns = 32;  // tcn < 8 (C/4 not a multiple of 8): fewer threads rather than a long combine loop
   t.NS = ns;
+  (void)T;
   t.NT = t.tcn * t.NS;
   t.n_iter = (T + t.NS * S - 1) / (t.NS * S);
   t.n_units = B * t.n_ctile;
@@ -463,7 +491,7 @@ static int launch_fwd(GScanParams& p, cudaStream_t st) {
   p.tcn = t.tcn; p.NS = t.NS; p.n_ctile = t.n_ctile; p.n_iter = t.n_iter; p.n_units = t.n_units;
   constexpr int NARR = (GATED ? 3 : 2) + (HAS_Z ? 1 : 0);
   const size_t smem = 2 * (size_t)NARR * kS * t.NT * IO<T>::BYTES + 4 * (size_t)t.NT * sizeof(float4);
-  auto kern = gscan_fwd_kernel<T, kS, GATED, HAS_Z>;
+  auto kern = t.NT == 256 ? gscan_fwd_kernel<T, kS, GATED, HAS_Z, 256> : gscan_fwd_kernel<T, kS, GATED, HAS_Z, 0>;
   BDLRU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 1;
   BDLRU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, t.NT, smem));
@@ -482,7 +510,7 @@ static int launch_bwd(GScanParams& p, float* dLambda, float* dh0_out, void* ws, 
   constexpr int NVEC = (GATED ? 4 : 2) * kS + NH + (HAS_Z ? kS : 0);
   const size_t smem = 2 * (size_t)NVEC * t.NT * IO<T>::BYTES + 4 * (size_t)t.NT * sizeof(float4) +
                       ((GATED && sizeof(T) != 4) ? 2 * (size_t)kS * t.NT * sizeof(float4) : 0);
-  auto kern = gscan_bwd_kernel<T, kS, GATED, HAS_Z>;
+  auto kern = t.NT == 256 ? gscan_bwd_kernel<T, kS, GATED, HAS_Z, 256> : gscan_bwd_kernel<T, kS, GATED, HAS_Z, 0>;
   BDLRU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 1;
   BDLRU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, t.NT, smem));
