@@ -1,0 +1,407 @@
+#!/usr/bin/env python
+"""bench.py — the hot path of BASELINE.json on N B200s of one node; prints ONE JSON line (rank 0).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload beauty|ml1m|score1m|score10m]
+
+Workloads (BASELINE.json `configs`):
+  beauty   (default) configs[1]: RecBLR at the Amazon-Beauty shape — n_items 12 102, L = 50, D = 64 (C = 128),
+           2 layers, train batch 2 048 per GPU.  A step is RecBole's `_train_epoch` body for one batch:
+           zero_grad -> calculate_loss (front end, 2 x (BD-LRU + FFN), CE over all items) -> backward -> Adam.
+           metric = BD-LRU fwd+bwd seq-tokens/s = B*L*N / step time.  A `fullsort` sub-object reports the other half
+           of the metric (full-sort scored users/s, eval batch 4 096) measured the same way.
+  ml1m     configs[0]'s shape (n_items 3 417, L = 200) through the same step.
+  score1m / score10m   configs[3]: synthetic full-sort scoring, D = 128, 4 096 users, item table row-sharded over
+           the N ranks with an NCCL top-k merge; metric = full-sort scored users/s.
+
+`--impl reference` times the CPU restatement of the reference (oracle/torch_port.py: literal pad, F.conv1d,
+separate gate ops, sequential scan) with all host threads on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: n_items, L, D, layers, train B, eval B
+    "beauty": dict(n_items=12102, L=50, D=64, layers=2, B=2048, eval_B=4096),
+    "ml1m": dict(n_items=3417, L=200, D=64, layers=2, B=2048, eval_B=4096),
+}
+SCORE_WORKLOADS = {"score1m": 1_000_000, "score10m": 10_000_000}
+
+
+# ----------------------------------------------------------------------------- helpers
+def peaks():
+    try:
+        d = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return dict(hbm=d["hbm_gbs"], tf=d["bf16_tflops"], tf_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    src="measured")
+    except Exception:
+        return dict(hbm=6650.0, tf=1590.0, tf_sustained=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled every 200 ms DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx = float(f[2])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def make_config(w, dev, dropout=0.2):
+    cfg = dict(hidden_size=w["D"], num_layers=w["layers"], dropout_prob=dropout, expand=2, d_conv=4, loss_type="CE",
+               USER_ID_FIELD="user_id", ITEM_ID_FIELD="item_id", LIST_SUFFIX="_list",
+               ITEM_LIST_LENGTH_FIELD="item_length", NEG_PREFIX="neg_", MAX_ITEM_LIST_LENGTH=w["L"], device=dev)
+
+    class Cfg(dict):  # RecBole's Config returns None for unknown keys
+        def __getitem__(self, k):
+            return self.get(k, None)
+    return Cfg(cfg)
+
+
+class _DS:
+    def __init__(self, n):
+        self.n = n
+
+    def num(self, field):
+        return self.n
+
+
+def synthetic_batch(B, L, n_items, seed):
+    """ids uniform in [1, n_items), lengths uniform in [min(5, L), L], right-padded with 0, targets uniform (§8d)."""
+    g = torch.Generator().manual_seed(seed)
+    lens = torch.randint(min(5, L), L + 1, (B,), generator=g)
+    seq = torch.randint(1, n_items, (B, L), generator=g)
+    seq = seq * (torch.arange(L)[None, :] < lens[:, None])
+    pos = torch.randint(1, n_items, (B,), generator=g)
+    return seq, lens, pos
+
+
+# ----------------------------------------------------------------------------- reference arm (CPU)
+def cpu_train_baseline(w, steps, warmup, sample_B):
+    """The reference's PyTorch path with the sequential scan on the host cores (oracle/torch_port.py), same step
+    (zero_grad, CE loss over all items, backward, Adam), on a bounded sample of sample_B sequences per step."""
+    from oracle import torch_port as TP
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    wts = TP.init_weights(w["n_items"], w["D"], w["layers"], seed=2020)
+    params = [v.requires_grad_(True) for v in wts.values()]
+    opt = torch.optim.Adam(params, lr=1e-3)
+    seq, lens, pos = synthetic_batch(sample_B, w["L"], w["n_items"], seed=2020)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        opt.zero_grad(set_to_none=True)
+        loss = TP.ce_loss(wts, seq, lens, pos, w["layers"], dropout_p=0.2)
+        loss.backward()
+        opt.step()
+        loss.item()
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    t = sum(times) / len(times)
+    return dict(value=sample_B * w["L"] / t, unit="seq-tokens/s", cores=cores, kind="port",
+                sample=f"{sample_B} sequences x L={w['L']} per step ({len(times)} timed steps, {t:.2f} s/step), "
+                       f"fp32, torch {torch.__version__} CPU, oracle/torch_port.py"), t
+
+
+def cpu_score_baseline(n_rows, D, users, k, steps, warmup):
+    """Reference full-sort eval on CPU: dense fp32 scores = Q @ E^T, scores[:, 0] = -inf, torch.topk (RecBLR.py:118-122
+    + RecBole's collector) on a bounded number of users against the full table."""
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    g = torch.Generator().manual_seed(2020)
+    E = torch.randn(n_rows, D, generator=g) * 0.02
+    Q = torch.randn(users, D, generator=g)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        s = Q @ E.T
+        s[:, 0] = float("-inf")
+        torch.topk(s, k)
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    t = sum(times) / len(times)
+    return dict(value=users / t, unit="users/s", cores=cores, kind="port",
+                sample=f"{users} users x {n_rows} items per step ({len(times)} timed steps, {t:.2f} s/step), fp32 "
+                       f"matmul + torch.topk on CPU"), t
+
+
+def run_reference(args):
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return
+    if args.workload in WORKLOADS:
+        w = WORKLOADS[args.workload]
+        base, t = cpu_train_baseline(w, args.steps, max(1, min(args.warmup, 2)), sample_B=args.cpu_sample or 256)
+        line = dict(metric="bdlru_fwd_bwd_seq_tokens_per_s", value=base["value"], unit="seq-tokens/s",
+                    config=dict(workload=f"{args.workload}: n_items={w['n_items']} L={w['L']} D={w['D']} "
+                                         f"layers={w['layers']} train step (CE over all items + Adam)"),
+                    dtype="f32")
+    else:
+        n = SCORE_WORKLOADS[args.workload]
+        base, t = cpu_score_baseline(n, 128, args.cpu_sample or 64, 10, args.steps, max(1, min(args.warmup, 2)))
+        line = dict(metric="fullsort_scored_users_per_s", value=base["value"], unit="users/s",
+                    config=dict(workload=f"{args.workload}: {n} items D=128 top-10"), dtype="f32")
+    line.update(impl="reference", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=t * 1e3,
+                higher_is_better=True, scaling="weak", vs_baseline=None, data="synthetic", cpu_baseline=base,
+                e2e=dict(value=base["value"], unit=base["unit"], h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                gpu_launches=0)
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- our arm: training step
+def run_train(args):
+    import torch.distributed as dist
+    from datamining_recblr_b200 import _lib
+    from datamining_recblr_b200.recblr import RecBLR
+    from datamining_recblr_b200.timing import flush_l2
+
+    rank, world, local = dist_env()
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU path)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    w = WORKLOADS[args.workload]
+    B, L, D = w["B"], w["L"], w["D"]
+    torch.manual_seed(2020)
+    model = RecBLR(make_config(w, dev), _DS(w["n_items"])).to(dev)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, fused=True)
+    params = [p for p in model.parameters()]
+    amp = args.dtype == "bf16"
+
+    # distinct batches per step (and per rank): > L2 is not reachable at this shape, so L2 is flushed between steps
+    n_batches = 4
+    host = [synthetic_batch(B, L, w["n_items"], seed=2020 + 97 * rank + i) for i in range(n_batches)]
+    host = [tuple(t.pin_memory() for t in b) for b in host]
+    devb = [tuple(t.to(dev) for t in b) for b in host]
+
+    def step(batch):
+        inter = {"item_id_list": batch[0], "item_length": batch[1], "item_id": batch[2]}
+        opt.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
+            loss = model.calculate_loss(inter)
+        loss.backward()
+        if world > 1:  # data-parallel gradient all-reduce (mean), one flat NCCL call
+            flat = torch.cat([p.grad.reshape(-1) for p in params])
+            dist.all_reduce(flat, op=dist.ReduceOp.AVG)
+            off = 0
+            for p in params:
+                p.grad.copy_(flat[off:off + p.numel()].view_as(p))
+                off += p.numel()
+        opt.step()
+        return loss
+
+    model.train()
+    for i in range(max(args.warmup, 3)):
+        step(devb[i % n_batches])
+    torch.cuda.synchronize()
+
+    # ---- timed region: K steps, inputs resident in HBM, CUDA events per step, L2 flushed between steps
+    timed = ["bdlru_gated_scan_fwd", "bdlru_gated_scan_bwd", "bdlru_conv1d_fwd", "bdlru_conv1d_bwd",
+             "bdlru_embed_ln_fwd", "bdlru_embed_ln_bwd", "bdlru_fullsort_ce_fwd", "bdlru_fullsort_ce_bwd"]
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    n0 = _lib.launch_count()
+    _lib.kernel_timer(timed)
+    evs = []
+    for i in range(args.steps):
+        flush_l2(dev)
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        step(devb[i % n_batches])
+        e.record()
+        evs.append((s, e))
+    torch.cuda.synchronize()
+    ktimes = _lib.kernel_timer_stop()
+    launches = _lib.launch_count() - n0
+    if world > 1:
+        dist.barrier()
+    total_ms = sum(s.elapsed_time(e) for s, e in evs)
+    tt = torch.tensor([total_ms], device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    total_ms = float(tt)
+    ms_per_step = total_ms / args.steps
+    value = world * B * L / (ms_per_step * 1e-3)
+
+    # ---- e2e: same step through the public API from pinned HOST buffers, loss read back every step
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        hb = host[i % n_batches]
+        db = tuple(t.to(dev, non_blocking=True) for t in hb)
+        float(step(db))
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_s = float(te)
+    clocks = sampler.stop() if rank == 0 else None
+    h2d = sum(t.numel() * t.element_size() for t in host[0])
+
+    # ---- the other half of the metric: full-sort scored users/s at the eval batch (forward + scoring + top-k)
+    fullsort = None
+    if rank == 0:
+        model.eval()
+        EB = w["eval_B"]
+        eb = tuple(t.to(dev) for t in synthetic_batch(EB, L, w["n_items"], seed=7))
+        inter = {"item_id_list": eb[0], "item_length": eb[1], "item_id": eb[2]}
+        from datamining_recblr_b200 import ops
+
+        def score():
+            with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
+                if ops.fullsort_supported(D):
+                    return model.full_sort_topk(inter, 10)
+                s = model.full_sort_predict(inter)  # dense fallback of the stock trainer until the fused kernel lands
+                s[:, 0] = float("-inf")
+                return torch.topk(s, 10)
+        for _ in range(3):
+            score()
+        ts = []
+        for _ in range(max(args.steps, 5)):
+            flush_l2(dev)
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            score()
+            e.record()
+            e.synchronize()
+            ts.append(s.elapsed_time(e))
+        fullsort = dict(metric="fullsort_scored_users_per_s", value=EB / (statistics.median(ts) * 1e-3), unit="users/s",
+                        users=EB, n_items=w["n_items"], k=10, ms=statistics.median(ts),
+                        fused_topk=bool(ops.fullsort_supported(D)))
+        model.train()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel of libbdlru.so in the step (live CUDA-event durations)
+    P = peaks()
+    es = 2 if amp else 4
+    C = 2 * D
+    E_l = B * L * C  # elements of one [B, L, C] activation
+    # algorithmic bytes per launch: z-fused gated scan fwd reads x', r, i, z and writes h, y;
+    # bwd reads x', r, i, z, h, g and writes dx', dr, di, dz
+    alg = {"bdlru_gated_scan_fwd": 6 * E_l * es, "bdlru_gated_scan_bwd": 10 * E_l * es,
+           "bdlru_conv1d_fwd": 2 * E_l * es, "bdlru_conv1d_bwd": 4 * E_l * es,
+           "bdlru_embed_ln_fwd": B * L * (8 + 2 * D * 4), "bdlru_embed_ln_bwd": B * L * (8 + 3 * D * 4)}
+    per_kernel = {}
+    for name, ts in ktimes.items():
+        if ts:
+            per_kernel[name] = dict(calls_per_step=len(ts) / args.steps, avg_ms=sum(ts) / len(ts),
+                                    share_of_step=sum(ts) / total_ms if world == 1 else None,
+                                    gbs=(alg[name] / (sum(ts) / len(ts)) / 1e6) if name in alg else None)
+    dom = max((n for n in per_kernel if n in alg), key=lambda n: per_kernel[n]["avg_ms"] * per_kernel[n]["calls_per_step"])
+    roofline = dict(bound="hbm", kernel=dom, achieved=per_kernel[dom]["gbs"], peak=P["hbm"], unit="GB/s",
+                    frac=per_kernel[dom]["gbs"] / P["hbm"], traffic=None, peak_source=P["src"],
+                    algorithmic_bytes_per_launch=alg[dom], avg_launch_ms=per_kernel[dom]["avg_ms"],
+                    note="events bracket the C-ABI call on the launching stream (includes its dLambda/dh0 reduction "
+                         "launch); working set is L2-resident at this shape, see DESIGN.md")
+
+    base, _ = cpu_train_baseline(w, steps=3, warmup=1, sample_B=args.cpu_sample or 256) if not args.no_cpu else (None, 0)
+    line = dict(metric="bdlru_fwd_bwd_seq_tokens_per_s", value=value, unit="seq-tokens/s", n_gpus=world,
+                steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=ms_per_step, higher_is_better=True,
+                scaling="weak", vs_baseline=None, dtype="bf16" if amp else "f32", data="synthetic",
+                config=dict(workload=f"{args.workload}: RecBLR n_items={w['n_items']} L={L} D={D} C={C} "
+                                     f"layers={w['layers']} batch {B}/GPU, train step = zero_grad + calculate_loss "
+                                     f"(CE over all items) + backward + Adam",
+                            l2="flushed between steps (256 MB write); per-step working set < L2",
+                            parallelism=f"dp{world}" if world > 1 else "single",
+                            ce_impl=model.ce_impl, scan_state="fp32"),
+                e2e=dict(value=world * B * L * args.steps / e2e_s, unit="seq-tokens/s", h2d_bytes_per_step=h2d,
+                         d2h_bytes_per_step=4, ms_per_step=e2e_s / args.steps * 1e3),
+                gpu_launches=launches, clocks=clocks, roofline=roofline, kernels=per_kernel, fullsort=fullsort,
+                cpu_baseline=base)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="beauty", choices=list(WORKLOADS) + list(SCORE_WORKLOADS))
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
+    ap.add_argument("--cpu-sample", type=int, default=0, help="sequences (train) / users (scoring) per CPU step")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    if args.workload in WORKLOADS:
+        return run_train(args)
+    from bench_score import run_score  # noqa: WPS433  (kept separate: needs the tcgen05 kernels)
+    return run_score(args)
+
+
+if __name__ == "__main__":
+    main()

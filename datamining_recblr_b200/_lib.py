@@ -42,6 +42,7 @@ SIGNATURES = {
     "bdlru_embed_ln_fwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i, _f, _f, _u64, _i, _p]),
     "bdlru_embed_ln_bwd_workspace_bytes": (_sz, [_i64, _i]),
     "bdlru_embed_ln_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _i64, _i64, _i, _f, _u64, _i64, _i, _p]),
+    "bdlru_fullsort_available": (_i, []),
     "bdlru_fullsort_topk_workspace_bytes": (_sz, [_i64, _i64, _i, _i]),
     "bdlru_fullsort_topk": (_i, [_p, _p, _i64, _i64, _i, _i, _i64, _i64, _p, _p, _p, _sz, _p]),
     "bdlru_topk_merge": (_i, [_p, _p, _i64, _i, _i, _p, _p, _p]),
@@ -52,6 +53,33 @@ SIGNATURES = {
 
 _lib = None
 MISSING = []
+# name of a C-ABI entry point -> list of (start, end) CUDA events; filled only while bench.py asks for it
+# (kernel_timer below), so the per-kernel launch durations behind `roofline.achieved` are measured live, on the
+# stream the kernels are launched on, inside the timed region.
+TIMERS = {}
+
+
+class _Timed:
+    """Callable proxy for one entry point: records a CUDA-event pair around the call when its name is in TIMERS."""
+    __slots__ = ("name", "fn")
+
+    def __init__(self, name, fn):
+        self.name, self.fn = name, fn
+
+    def __call__(self, *args):
+        rec = TIMERS.get(self.name)
+        if rec is None:
+            return self.fn(*args)
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        rc = self.fn(*args)
+        e.record()
+        rec.append((s, e))
+        return rc
+
+
+class _Lib:
+    pass
 
 
 def load():
@@ -62,17 +90,37 @@ def load():
     if not os.path.exists(LIB_PATH):
         raise BdlruError(f"{LIB_PATH} not found: build it with `python -m datamining_recblr_b200.build` "
                          "(there is no CPU or PyTorch fallback for this path)")
-    lib = ctypes.CDLL(LIB_PATH)
+    cdll = ctypes.CDLL(LIB_PATH)
+    lib = _Lib()
+    lib.cdll = cdll
     for name, (res, args) in SIGNATURES.items():
-        fn = getattr(lib, name, None)
-        if fn is None:
+        try:
+            fn = getattr(cdll, name)
+        except AttributeError:
             MISSING.append(name)  # tests/test_abi.py requires this list to be empty
             continue
         fn.restype, fn.argtypes = res, args
+        setattr(lib, name, _Timed(name, fn) if res is _i and args else fn)
     if lib.bdlru_version() != ABI_VERSION:
         raise BdlruError(f"libbdlru.so ABI {lib.bdlru_version()} != expected {ABI_VERSION}: rebuild")
     _lib = lib
     return lib
+
+
+def kernel_timer(names):
+    """Start recording per-call CUDA-event pairs for the given entry points; returns the dict to read back."""
+    TIMERS.clear()
+    for n in names:
+        TIMERS[n] = []
+    return TIMERS
+
+
+def kernel_timer_stop():
+    """Stops recording; returns {name: [ms, ...]} (synchronises)."""
+    torch.cuda.synchronize()
+    out = {n: [s.elapsed_time(e) for s, e in ev] for n, ev in TIMERS.items()}
+    TIMERS.clear()
+    return out
 
 
 def check(rc):

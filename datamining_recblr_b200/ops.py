@@ -196,3 +196,54 @@ class _Conv1dCL(torch.autograd.Function):
 def causal_conv1d_channel_last(x, weight, bias=None, silu=True):
     """y_t = act(bias + sum_j weight[:, j] * x_{t-(W-1)+j}) on channel-last [B, T, C]; weight [C, W], W <= 4."""
     return _Conv1dCL.apply(x, weight, bias, silu)
+
+
+class _EmbedLN(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, ids, table, gamma, beta, eps, p, seed, padding_idx):
+        L.require_cuda(ids, table, gamma, beta)
+        assert ids.dtype == torch.int64 and table.dim() == 2
+        n_items, D = table.shape
+        ids_c = ids.contiguous()
+        tab = table.detach().contiguous()
+        gf, bf = gamma.detach().float().contiguous(), beta.detach().float().contiguous()
+        n = ids_c.numel()
+        out = torch.empty((*ids.shape, D), dtype=table.dtype, device=table.device)
+        mean = torch.empty(n, dtype=torch.float32, device=table.device)
+        rstd = torch.empty_like(mean)
+        L.check(L.load().bdlru_embed_ln_fwd(L.ptr(ids_c), L.ptr(tab), L.ptr(gf), L.ptr(bf), L.ptr(out), L.ptr(mean),
+                                            L.ptr(rstd), n, n_items, D, float(eps), float(p), int(seed),
+                                            L.dtype_tag(tab), L.stream_ptr(tab)))
+        ctx.save_for_backward(ids_c, tab, gf, mean, rstd)
+        ctx.args = (float(p), int(seed), int(padding_idx), gamma.dtype, beta.dtype)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        ids_c, tab, gf, mean, rstd = ctx.saved_tensors
+        p, seed, padding_idx, g_dtype, b_dtype = ctx.args
+        n_items, D = tab.shape
+        n = ids_c.numel()
+        grad_out = grad_out.to(tab.dtype).contiguous()
+        dtable = torch.zeros((n_items, D), dtype=torch.float32, device=tab.device)
+        dgamma = torch.empty(D, dtype=torch.float32, device=tab.device)
+        dbeta = torch.empty_like(dgamma)
+        lib = L.load()
+        nws = lib.bdlru_embed_ln_bwd_workspace_bytes(n, D)
+        ws = _workspace(tab.device, nws)
+        L.check(lib.bdlru_embed_ln_bwd(L.ptr(ids_c), L.ptr(tab), L.ptr(gf), L.ptr(grad_out), L.ptr(mean), L.ptr(rstd),
+                                       L.ptr(dtable), L.ptr(dgamma), L.ptr(dbeta), L.ptr(ws), nws, n, n_items, D, p,
+                                       seed, padding_idx, L.dtype_tag(tab), L.stream_ptr(tab)))
+        return None, dtable.to(tab.dtype), dgamma.to(g_dtype), dbeta.to(b_dtype), None, None, None, None
+
+
+def embed_layernorm(ids, table, gamma, beta, eps=1e-12, dropout_p=0.0, seed=0, padding_idx=-1):
+    """LayerNorm(dropout(table[ids])) in one kernel (RecBLR.py:76-78).  ids int64 [...]; returns [..., D] in
+    table.dtype.  Rows equal to padding_idx receive no gather gradient (nn.Embedding(padding_idx=0) semantics)."""
+    return _EmbedLN.apply(ids, table, gamma, beta, eps, dropout_p, seed, padding_idx)
+
+
+# ----------------------------------------------------------------------------- full-sort scoring / CE (tcgen05)
+def fullsort_supported(D):
+    """Shapes the tcgen05 full-sort kernels take: bf16 operands, D a multiple of 64 up to 256."""
+    return D % 64 == 0 and D <= 256 and bool(L.load().bdlru_fullsort_available())

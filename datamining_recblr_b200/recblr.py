@@ -1,0 +1,255 @@
+"""Host-side mirror of the reference model file (RecBLR.py) over the sm_100a kernels.
+
+Same class names, constructor arguments, config keys, parameter names/shapes (checkpoints of the reference
+load unchanged: SURVEY.md §8b) and the same four entry points RecBole's trainer calls
+(`forward`, `calculate_loss`, `predict`, `full_sort_predict`), so `run.py` switches to this path by
+importing `RecBLR` from here instead of from the reference's `RecBLR.py`.
+
+What differs is only HOW `GatedRecurrentLayer.forward` and the front end are evaluated:
+  * no left pad to a power of two (RecBLR.py:177-179, 203-204): the P phantom steps the reference feeds
+    through the conv bias are folded into the batch-independent initial state h0[C] (closed form,
+    differentiable), so results are identical while 28 % fewer steps are computed;
+  * conv + SiLU, gate math + scan + z-gate, and gather + dropout + LayerNorm are one kernel each,
+    all on the native channel-last [B, T, C] layout (no transposes);
+  * `full_sort_topk` / the CE branch of `calculate_loss` use the fused tcgen05 kernels that never write the
+    [B, n_items] logits (`full_sort_predict` still returns the dense matrix RecBole's stock trainer needs).
+
+There is no CPU path: the ops raise on non-CUDA tensors.
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from . import ops
+
+try:  # RecBole is the host framework of the reference (requirements.txt:3); absent in the build image
+    from recbole.model.abstract_recommender import SequentialRecommender
+    from recbole.model.loss import BPRLoss
+except ImportError:  # the attributes RecBLR.py:20,37-38,83,87-92 rely on
+    class SequentialRecommender(nn.Module):
+        def __init__(self, config, dataset):
+            super().__init__()
+            self.USER_ID = config["USER_ID_FIELD"]
+            self.ITEM_ID = config["ITEM_ID_FIELD"]
+            self.ITEM_SEQ = self.ITEM_ID + config["LIST_SUFFIX"]
+            self.ITEM_SEQ_LEN = config["ITEM_LIST_LENGTH_FIELD"]
+            self.POS_ITEM_ID = self.ITEM_ID
+            self.NEG_ITEM_ID = config["NEG_PREFIX"] + self.ITEM_ID
+            self.max_seq_length = config["MAX_ITEM_LIST_LENGTH"]
+            self.n_items = dataset.num(self.ITEM_ID)
+            self.device = config["device"]
+
+        def gather_indexes(self, output, gather_index):
+            index = gather_index.view(-1, 1, 1).expand(-1, -1, output.shape[-1])
+            return output.gather(dim=1, index=index).squeeze(1)
+
+    class BPRLoss(nn.Module):
+        def __init__(self, gamma=1e-10):
+            super().__init__()
+            self.gamma = gamma
+
+        def forward(self, pos_score, neg_score):
+            return -torch.log(self.gamma + torch.sigmoid(pos_score - neg_score)).mean()
+
+
+def softplus_inverse(x):
+    return torch.log(torch.expm1(x))
+
+
+def _cfg(config, key, default=None):
+    """RecBole's Config returns None for unknown keys; plain dicts raise — accept both."""
+    try:
+        v = config[key]
+    except KeyError:
+        v = None
+    return default if v is None else v
+
+
+class RecBLR(SequentialRecommender):
+    """RecBLR.py:18-122.  Extra (optional) config keys, all defaulting to the fast path:
+        ce_impl      'fused' (tcgen05 online-softmax CE, bf16 operands / fp32 accumulate) | 'dense' (fp32 logits)
+        fused_front  True: gather+dropout+LayerNorm in one kernel
+    """
+
+    def __init__(self, config, dataset):
+        super().__init__(config, dataset)
+        self.hidden_size = config["hidden_size"]
+        self.loss_type = config["loss_type"]
+        self.num_layers = config["num_layers"]
+        self.dropout_prob = config["dropout_prob"]
+        self.expand = config["expand"]
+        self.d_conv = config["d_conv"]
+        self.bd_lru_only = _cfg(config, "bd_lru_only")
+        self.disable_conv1d = _cfg(config, "disable_conv1d")
+        self.disable_ffn = _cfg(config, "disable_ffn")
+        if self.bd_lru_only:  # RecBLR.py:33-35
+            self.disable_conv1d = True
+            self.disable_ffn = True
+        self.ce_impl = _cfg(config, "ce_impl", "fused")
+        self.fused_front = bool(_cfg(config, "fused_front", True))
+
+        self.item_embedding = nn.Embedding(self.n_items, self.hidden_size, padding_idx=0)
+        self.layer_norm = nn.LayerNorm(self.hidden_size, eps=1e-12)
+        self.dropout = nn.Dropout(self.dropout_prob)
+        self.recurrent_layers = nn.ModuleList([
+            RecurrentLayer(d_model=self.hidden_size, d_conv=self.d_conv, expand=self.expand,
+                           dropout=self.dropout_prob, num_layers=self.num_layers, bd_lru_only=self.bd_lru_only,
+                           disable_conv1d=self.disable_conv1d, disable_ffn=self.disable_ffn)
+            for _ in range(self.num_layers)
+        ])
+        if self.loss_type == "BPR":
+            self.loss_fct = BPRLoss()
+        elif self.loss_type == "CE":
+            self.loss_fct = nn.CrossEntropyLoss()
+        else:
+            raise NotImplementedError("Make sure 'loss_type' in ['BPR', 'CE']!")
+        self.apply(self._init_weights)
+        self._step = 0  # advances the dropout counter stream of the fused front end
+
+    def _init_weights(self, module):  # RecBLR.py:66-73 (the pad row 0 is re-randomised too: SURVEY quirk 2)
+        if isinstance(module, (nn.Linear, nn.Embedding)):
+            module.weight.data.normal_(std=0.02)
+        elif isinstance(module, nn.LayerNorm):
+            module.bias.data.zero_()
+            module.weight.data.fill_(1.0)
+        if isinstance(module, nn.Linear) and module.bias is not None:
+            module.bias.data.zero_()
+
+    # ------------------------------------------------------------------ RecBLR.py:75-84
+    def _front(self, item_seq):
+        p = self.dropout_prob if self.training else 0.0
+        D = self.hidden_size
+        if self.fused_front and D % 4 == 0 and D <= 512:
+            self._step += 1
+            seed = (torch.initial_seed() * 0x9E3779B97F4A7C15 + self._step) & 0xFFFFFFFFFFFFFFFF
+            return ops.embed_layernorm(item_seq, self.item_embedding.weight, self.layer_norm.weight,
+                                       self.layer_norm.bias, eps=self.layer_norm.eps, dropout_p=p, seed=seed,
+                                       padding_idx=0)
+        return self.layer_norm(self.dropout(self.item_embedding(item_seq)))
+
+    def forward(self, item_seq, item_seq_len):
+        item_emb = self._front(item_seq)
+        for layer in self.recurrent_layers:
+            item_emb = layer(item_emb)
+        return self.gather_indexes(item_emb, item_seq_len - 1)
+
+    # ------------------------------------------------------------------ RecBLR.py:86-103
+    def calculate_loss(self, interaction):
+        item_seq = interaction[self.ITEM_SEQ]
+        item_seq_len = interaction[self.ITEM_SEQ_LEN]
+        seq_output = self.forward(item_seq, item_seq_len)
+        pos_items = interaction[self.POS_ITEM_ID]
+        if self.loss_type == "BPR":
+            neg_items = interaction[self.NEG_ITEM_ID]
+            pos_score = torch.sum(seq_output * self.item_embedding(pos_items), dim=-1)
+            neg_score = torch.sum(seq_output * self.item_embedding(neg_items), dim=-1)
+            return self.loss_fct(pos_score, neg_score)
+        table = self.item_embedding.weight
+        if self.ce_impl == "fused" and ops.fullsort_supported(self.hidden_size):
+            return ops.fullsort_cross_entropy(seq_output, table, pos_items)
+        logits = torch.matmul(seq_output, table.transpose(0, 1))
+        return self.loss_fct(logits, pos_items)
+
+    # ------------------------------------------------------------------ RecBLR.py:105-122
+    def predict(self, interaction):
+        seq_output = self.forward(interaction[self.ITEM_SEQ], interaction[self.ITEM_SEQ_LEN])
+        test_item_emb = self.item_embedding(interaction[self.ITEM_ID])
+        return torch.mul(seq_output, test_item_emb).sum(dim=1)
+
+    def full_sort_predict(self, interaction):
+        seq_output = self.forward(interaction[self.ITEM_SEQ], interaction[self.ITEM_SEQ_LEN])
+        return torch.matmul(seq_output, self.item_embedding.weight.transpose(0, 1))
+
+    @torch.no_grad()
+    def full_sort_topk(self, interaction, k, mask_padding_item=True):
+        """Fused form of `full_sort_predict` + RecBole's `scores[:, 0] = -inf; torch.topk(scores, k)`
+        (SURVEY §3.5): returns (scores [B, k] fp32, ids [B, k] int64) ordered by score descending with the
+        LOWEST item id first among ties, without materialising [B, n_items]."""
+        seq_output = self.forward(interaction[self.ITEM_SEQ], interaction[self.ITEM_SEQ_LEN])
+        scores, ids = ops.fullsort_topk(seq_output, self.item_embedding.weight, k,
+                                        mask_id=0 if mask_padding_item else -1)
+        return scores, ids.long()
+
+
+class RecurrentLayer(nn.Module):
+    """RecBLR.py:124-145."""
+
+    def __init__(self, d_model, d_conv, expand, dropout, num_layers, bd_lru_only, disable_conv1d, disable_ffn):
+        super().__init__()
+        self.num_layers = num_layers
+        self.disable_ffn = disable_ffn
+        self.behavior_modeling = GatedRecurrentLayer(d_model=d_model, expansion_factor=expand, kernel_size=d_conv,
+                                                     bd_lru_only=bd_lru_only, disable_conv1d=disable_conv1d)
+        self.dropout = nn.Dropout(dropout)
+        self.layer_norm = nn.LayerNorm(d_model, eps=1e-12)
+        self.ffn = FeedForward(d_model=d_model, inner_size=d_model * 4, dropout=dropout)
+
+    def forward(self, input_tensor):
+        hidden_states = self.behavior_modeling(input_tensor)
+        hidden_states = self.layer_norm(self.dropout(hidden_states) + input_tensor)
+        if not self.disable_ffn:
+            hidden_states = self.ffn(hidden_states)
+        return hidden_states
+
+
+class GatedRecurrentLayer(nn.Module):
+    """RecBLR.py:148-207 — the BD-LRU layer."""
+
+    def __init__(self, d_model=64, expansion_factor=2, kernel_size=4, bd_lru_only=False, disable_conv1d=False):
+        super().__init__()
+        self.bd_lru_only = bd_lru_only
+        self.disable_conv1d = disable_conv1d
+        r_min, r_max = 0.9, 0.999  # exp(-softplus(Lambda)) spans [0.9, 0.999] at init (RecBLR.py:153-158)
+        lo = softplus_inverse(torch.tensor(-math.log(r_min))).item()
+        hi = softplus_inverse(torch.tensor(-math.log(r_max))).item()
+        hidden = int(d_model * expansion_factor)
+        self.input = nn.Linear(d_model, 2 * hidden, bias=False)
+        self.conv1d = nn.Conv1d(in_channels=hidden, out_channels=hidden, bias=True, kernel_size=kernel_size,
+                                groups=hidden, padding=kernel_size - 1)
+        self.gates = nn.Linear(hidden, 2 * hidden, bias=True)
+        self.Lambda = nn.Parameter(torch.linspace(lo, hi, hidden))
+        self.output = nn.Linear(hidden, d_model, bias=False)
+
+    def phantom_state(self, seq_len):
+        """State the reference's left zero-pad leaves in front of the first real step (RecBLR.py:177-199):
+        on the P = 2^ceil(log2 T) - T padded steps the conv emits silu(conv bias) =: s, so
+            h0 = b' (1 - a^P) / (1 - a),   a, b' = gate math at the constant input s.
+        Batch independent, [C], fp32, differentiable w.r.t. conv1d.bias, gates.*, Lambda.  None when P == 0
+        or the conv is disabled (then padded steps are exactly zero)."""
+        pad_len = 2 ** ((seq_len - 1).bit_length()) - seq_len
+        if pad_len == 0 or self.disable_conv1d:
+            return None
+        s = F.silu(self.conv1d.bias.float())
+        rec, inp = F.linear(s, self.gates.weight.float(), self.gates.bias.float()).chunk(2, dim=-1)
+        a = torch.exp(-F.softplus(self.Lambda.float()) * torch.sigmoid(rec))
+        b = torch.sqrt(1 - a.pow(2) + 1e-8) * torch.sigmoid(inp) * s
+        # (1 - a^P)/(1 - a) as the explicit geometric sum's closed form; a < 1 strictly since softplus > 0
+        return b * (1 - a.pow(pad_len)) / (1 - a)
+
+    def forward(self, x):
+        _, seq_len, _ = x.shape
+        xz = self.input(x)
+        x, z = xz.chunk(2, dim=-1)  # strided channel-last views, consumed in place by the kernels
+        if not self.disable_conv1d:
+            x = ops.causal_conv1d_channel_last(x, self.conv1d.weight.squeeze(1), self.conv1d.bias, silu=True)
+        recurrence, inp = self.gates(x).chunk(2, dim=-1)
+        y = ops.gated_scan(x, recurrence, inp, self.Lambda, h0=self.phantom_state(seq_len), z=z)
+        return self.output(y)
+
+
+class FeedForward(nn.Module):
+    """RecBLR.py:210-227."""
+
+    def __init__(self, d_model, inner_size, dropout=0.2):
+        super().__init__()
+        self.w_1 = nn.Linear(d_model, inner_size)
+        self.w_2 = nn.Linear(inner_size, d_model)
+        self.dropout = nn.Dropout(dropout)
+        self.layer_norm = nn.LayerNorm(d_model, eps=1e-12)
+
+    def forward(self, input_tensor):
+        hidden_states = self.dropout(F.silu(self.w_1(input_tensor)))
+        hidden_states = self.dropout(self.w_2(hidden_states))
+        return self.layer_norm(hidden_states + input_tensor)

@@ -137,6 +137,8 @@ int bdlru_embed_ln_bwd(const int64_t* ids, const void* table, const float* gamma
  * descending, ties broken by LOWEST item id.  1 <= k <= 32.
  *   out_scores fp32 [n_users, k], out_ids int32 [n_users, k]  (-inf / -1 when fewer than k candidates).
  * ------------------------------------------------------------------------------------------- */
+/* 1 when the tcgen05 full-sort kernels are compiled into this library (else they return UNSUPPORTED). */
+int bdlru_fullsort_available(void);
 size_t bdlru_fullsort_topk_workspace_bytes(int64_t n_users, int64_t n_rows, int D, int k);
 int bdlru_fullsort_topk(const void* Q, const void* E, int64_t n_users, int64_t n_rows, int D, int k,
                         int64_t id_offset, int64_t mask_id, float* out_scores, int32_t* out_ids,
