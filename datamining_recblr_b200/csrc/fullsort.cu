@@ -1,30 +1,539 @@
-// Full-sort scoring / full-softmax CE entry points (include/bdlru.h).  Placeholder bodies until the tcgen05
-// kernels land: every call reports BDLRU_ERR_UNSUPPORTED (never a silent fallback).
+// Full-sort scoring (RecBLR.py:114-122 + RecBole's mask/top-k) and the forward of the full-softmax CE
+// (RecBLR.py:99-103) as ONE warp-specialised tcgen05 kernel family: S = Q E^T is accumulated in TMEM and consumed
+// straight out of TMEM by the epilogue (streaming per-user top-k, or online max / sum-exp), so the [users, items]
+// logits never exist in memory.
+//
+// Tiling.  A CTA owns UB (1 or 2) blocks of 128 users, kept resident in shared memory as the A operand
+// (K-major, 128-byte swizzle, one 16 KB slab per 64 channels), and walks a contiguous range of 128-item tiles of E
+// streamed by TMA through a multi-stage ring (B operand, same layout).  Per tile it issues UB x D/16
+// tcgen05.mma (M=128, N=128, K=16, bf16 x bf16 -> fp32) into one of two TMEM accumulator sets, so the epilogue of
+// tile t overlaps the MMAs of tile t+1.  Using both user blocks against each E tile halves the L2->SM operand
+// traffic per flop (at D=128 one user block alone would need ~10 TB/s of L2 bandwidth to keep the tensor pipe fed).
+//
+// Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one lane), warps 2.. = epilogue,
+// one warp per 32 TMEM lanes per user block (a warp may only touch TMEM lanes 32*(warp%4)..+31): thread == user.
+//
+// Top-k epilogue: every thread keeps its user's k best (score, id) sorted in shared memory ([k][users] so lanes hit
+// distinct banks) and the k-th score in a register.  A 32-score chunk is first reduced to its maximum; only if that
+// beats the threshold are the 32 scores inspected one by one (rare after the first few tiles: the expected number of
+// insertions over n items is ~k ln(n/k)).  Items arrive in increasing id order and an item is inserted only if it is
+// STRICTLY better than the k-th, after all entries with an equal score, so ties resolve to the lowest id.
+// The grid splits the item range S ways; a second kernel merges the S (or, multi-GPU, G) sorted lists per user by
+// (score desc, id asc).
+#include <cuda.h>
+
 #include "common.cuh"
+#include "tc05.cuh"
+
+namespace bdlru {
+
+constexpr int kTile = 128;                 // users per block (TMEM lanes) and items per E tile (MMA N)
+constexpr uint32_t kSlab = 128 * 128;      // bytes of one [128 rows x 64 bf16] swizzled slab
+constexpr int kMaxSmem = 227 * 1024;
+constexpr int kMaxStages = 6;
+
+enum { MODE_TOPK = 0, MODE_CE = 1 };
+
+struct FsParams {
+  int D, k, stages, splits, n_ug;
+  long n_users, n_rows;       // rows of Q, rows of this E shard
+  long id_offset, mask_local; // global id of E row 0; LOCAL row to exclude (-1: none)
+  long tiles_total;
+  // top-k partials [n_users][splits][k]
+  float* part_scores;
+  int* part_ids;
+  // CE partials [n_users][splits] and direct outputs
+  float* part_max;
+  float* part_sum;
+  const int64_t* pos;
+  float* pos_logit;
+};
+
+struct FsPlan {
+  int UB, stages, splits, n_ug, threads;
+  size_t smem;
+  long tiles_total;
+};
+
+// One plan for (n_users, n_rows, D, k): used by the launch AND by the workspace query, so both agree.
+static bool fs_plan(long n_users, long n_rows, int D, int k, FsPlan* pl) {
+  const int n_slab = D / 64;
+  const long tiles = (n_rows + kTile - 1) / kTile;
+  for (int UB = 2; UB >= 1; --UB) {
+    const size_t q = (size_t)UB * n_slab * kSlab;
+    const size_t lists = (size_t)8 * k * kTile * UB;
+    const size_t fixed = 1024 /*align slack*/ + q + lists + 256 /*barriers*/;
+    if (fixed >= (size_t)kMaxSmem) continue;
+    int stages = (int)(((size_t)kMaxSmem - fixed) / ((size_t)n_slab * kSlab));
+    if (stages > kMaxStages) stages = kMaxStages;
+    if (stages < 2 || (UB == 2 && stages < 3 && n_slab > 1)) continue;
+    if (UB == 2 && n_users <= kTile) continue;  // a single user block: do not waste the second one
+    pl->UB = UB;
+    pl->stages = stages;
+    pl->n_ug = (int)((n_users + (long)kTile * UB - 1) / ((long)kTile * UB));
+    long max_s = tiles / 4 > 0 ? tiles / 4 : 1;
+    long want = ((long)sm_count() * 4 + pl->n_ug - 1) / pl->n_ug;
+    long s = want < max_s ? want : max_s;
+    if (s < 1) s = 1;
+    pl->splits = (int)s;
+    pl->threads = 64 + 128 * UB;
+    pl->smem = 1024 + q + (size_t)stages * n_slab * kSlab + lists + 256;
+    pl->tiles_total = tiles;
+    return true;
+  }
+  return false;
+}
+
+// ----------------------------------------------------------------------------- per-thread sorted list in smem
+// Inserts (v, id) after every entry with score >= v; the caller has checked v > list[k-1].  Returns the new k-th.
+__device__ __noinline__ float topk_insert(float* ls, int* li, int LW, int k, float v, int id) {
+  int j = k - 1;
+  while (j > 0) {
+    const float pv = ls[(j - 1) * LW];
+    if (!(pv < v)) break;
+    ls[j * LW] = pv;
+    li[j * LW] = li[(j - 1) * LW];
+    --j;
+  }
+  ls[j * LW] = v;
+  li[j * LW] = id;
+  return ls[(k - 1) * LW];
+}
+
+__device__ __forceinline__ float max32(const float (&v)[32]) {
+  float m[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) m[i] = fmaxf(fmaxf(v[4 * i], v[4 * i + 1]), fmaxf(v[4 * i + 2], v[4 * i + 3]));
+  return fmaxf(fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3])), fmaxf(fmaxf(m[4], m[5]), fmaxf(m[6], m[7])));
+}
+
+template <int UB, int MODE>
+__global__ void __launch_bounds__(64 + 128 * UB, 1)
+fullsort_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmE, const FsParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_slab = p.D >> 6;
+  constexpr int LW = kTile * UB;  // list row width (threads of the epilogue)
+
+  uint8_t* sQ = smem;
+  uint8_t* sE = sQ + (size_t)UB * n_slab * kSlab;
+  float* lsc = reinterpret_cast<float*>(sE + (size_t)p.stages * n_slab * kSlab);
+  int* lid = reinterpret_cast<int*>(lsc + (size_t)p.k * LW);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(lid + (size_t)p.k * LW);
+  uint64_t* q_full = bars;
+  uint64_t* e_full = bars + 1;
+  uint64_t* e_empty = e_full + kMaxStages;
+  uint64_t* acc_full = e_empty + kMaxStages;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  // work assignment: consecutive CTAs share an item range and differ in user group -> E tiles hit in L2
+  const int ug = blockIdx.x % p.n_ug;
+  const int split = blockIdx.x / p.n_ug;
+  const long t_begin = p.tiles_total * split / p.splits;
+  const long t_end = p.tiles_total * (split + 1) / p.splits;
+  const int n_iter = (int)(t_end - t_begin);
+  const long user0 = (long)ug * kTile * UB;
+
+  if (warp == 0 && lane == 0) {
+    tc::prefetch_tensormap(&tmQ);
+    tc::prefetch_tensormap(&tmE);
+    tc::mbar_init(q_full, 1);
+    for (int s = 0; s < p.stages; ++s) {
+      tc::mbar_init(&e_full[s], 1);
+      tc::mbar_init(&e_empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      tc::mbar_init(&acc_full[b], 1);
+      tc::mbar_init(&acc_empty[b], 4 * UB);
+    }
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) {
+    tc::tmem_alloc(tmem_slot, 256 * UB);
+    tc::tmem_relinquish();
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    if (lane == 0) {
+      tc::mbar_arrive_expect_tx(q_full, (uint32_t)(UB * n_slab) * kSlab);
+      for (int ub = 0; ub < UB; ++ub)
+        for (int sl = 0; sl < n_slab; ++sl)
+          tc::tma_load_2d(sQ + (size_t)(ub * n_slab + sl) * kSlab, &tmQ, q_full, sl * 64, (int)(user0 + ub * kTile));
+      for (int it = 0; it < n_iter; ++it) {
+        const int s = it % p.stages;
+        const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+        tc::mbar_wait(&e_empty[s], ph ^ 1u);
+        tc::mbar_arrive_expect_tx(&e_full[s], (uint32_t)n_slab * kSlab);
+        for (int sl = 0; sl < n_slab; ++sl)
+          tc::tma_load_2d(sE + (size_t)(s * n_slab + sl) * kSlab, &tmE, &e_full[s], sl * 64,
+                          (int)((t_begin + it) * kTile));
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = tc::idesc_bf16_f32(kTile, kTile, 0, 0);
+      tc::mbar_wait(q_full, 0);
+      tc::fence_after_sync();
+      for (int it = 0; it < n_iter; ++it) {
+        const int s = it % p.stages;
+        const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+        const int b = it & 1;
+        const uint32_t bph = (uint32_t)(it >> 1) & 1u;
+        tc::mbar_wait(&acc_empty[b], bph ^ 1u);
+        tc::mbar_wait(&e_full[s], ph);
+        tc::fence_after_sync();
+#pragma unroll
+        for (int ub = 0; ub < UB; ++ub) {
+          const uint32_t d_tmem = tmem_base + (uint32_t)((b * UB + ub) * kTile);
+          for (int sl = 0; sl < n_slab; ++sl) {
+            const uint32_t a0 = tc::smem_u32(sQ + (size_t)(ub * n_slab + sl) * kSlab);
+            const uint32_t b0 = tc::smem_u32(sE + (size_t)(s * n_slab + sl) * kSlab);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              const uint64_t ad = tc::smem_desc_sw128(a0 + kk * 32, 16, 1024);
+              const uint64_t bd = tc::smem_desc_sw128(b0 + kk * 32, 16, 1024);
+              tc::umma_bf16(d_tmem, ad, bd, idesc, (uint32_t)((sl | kk) != 0));
+            }
+          }
+        }
+        tc::umma_commit(&e_empty[s]);   // smem stage reusable once these MMAs have read it
+        tc::umma_commit(&acc_full[b]);  // accumulators complete
+      }
+    }
+  } else {
+    // ===================================================================== epilogue: thread == user
+    const int e = warp - 2;
+    const int ub = e >> 2;
+    const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;          // user row inside the block
+    const int col = ub * kTile + row;       // this thread's list column
+    const long user = user0 + col;
+    float* ls = lsc + col;
+    int* li = lid + col;
+    float thr = -INFINITY;                  // top-k: current k-th best; CE: unused
+    float run_m = -INFINITY, run_s = 0.f;   // CE: online max / sum of exp
+    long pos_local = -1;
+    if (MODE == MODE_TOPK) {
+      for (int j = 0; j < p.k; ++j) {
+        ls[j * LW] = -INFINITY;
+        li[j * LW] = -1;
+      }
+    } else {
+      if (user < p.n_users) pos_local = p.pos[user] - p.id_offset;
+    }
+    constexpr float kLog2e = 1.4426950408889634f;
+    for (int it = 0; it < n_iter; ++it) {
+      const int b = it & 1;
+      const uint32_t bph = (uint32_t)(it >> 1) & 1u;
+      const long base = (t_begin + it) * kTile;  // local row index of the tile's first item
+      const bool special = (base + kTile > p.n_rows) || (p.mask_local >= base && p.mask_local < base + kTile);
+      tc::mbar_wait(&acc_full[b], bph);
+      tc::fence_after_sync();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((b * UB + ub) * kTile);
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t raw[32];
+        tc::tmem_ld_32x32(taddr + c * 32, raw);
+        tc::tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
+        const long cbase = base + c * 32;
+        if (special) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (cbase + i >= p.n_rows || cbase + i == p.mask_local) v[i] = -INFINITY;
+        }
+        const float m = max32(v);
+        if (MODE == MODE_TOPK) {
+          if (m > thr) {
+            const int id0 = (int)(p.id_offset + cbase);
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (v[i] > thr) thr = topk_insert(ls, li, LW, p.k, v[i], id0 + i);
+          }
+        } else {
+          if (m > run_m) {  // rescale the running sum to the new maximum (m is finite here)
+            run_s *= ex2_ftz((run_m - m) * kLog2e);
+            run_m = m;
+          }
+          if (run_m > -INFINITY) {
+            const float mb = run_m * kLog2e;
+            float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              acc0 += ex2_ftz(fmaf(v[i], kLog2e, -mb));
+              acc1 += ex2_ftz(fmaf(v[i + 1], kLog2e, -mb));
+            }
+            run_s += acc0 + acc1;
+          }
+          if (pos_local >= cbase && pos_local < cbase + 32) {
+            const int sel = (int)(pos_local - cbase);
+            float pv = 0.f;
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (i == sel) pv = v[i];
+            p.pos_logit[user] = pv;
+          }
+        }
+      }
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&acc_empty[b]);
+    }
+    if (user < p.n_users) {
+      if (MODE == MODE_TOPK) {
+        float* os = p.part_scores + ((size_t)user * p.splits + split) * p.k;
+        int* oi = p.part_ids + ((size_t)user * p.splits + split) * p.k;
+        for (int j = 0; j < p.k; ++j) {
+          os[j] = ls[j * LW];
+          oi[j] = li[j * LW];
+        }
+      } else {
+        p.part_max[(size_t)user * p.splits + split] = run_m;
+        p.part_sum[(size_t)user * p.splits + split] = run_s;
+      }
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    tc::fence_after_sync();
+    tc::tmem_dealloc(tmem_base, 256 * UB);
+  }
+}
+
+// ----------------------------------------------------------------------------- merges
+// One warp per user: k rounds of "best remaining candidate" by (score desc, id asc) over n_cand candidates staged in
+// shared memory.  Used for the S per-CTA lists of one GPU and for the G per-shard lists of the NCCL merge.
+__global__ void __launch_bounds__(128) topk_merge_kernel(const float* __restrict__ cs, const int* __restrict__ ci,
+                                                         long n_users, int n_cand, int k, float* __restrict__ os,
+                                                         int* __restrict__ oi) {
+  extern __shared__ uint8_t msm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long user = (long)blockIdx.x * 4 + warp;
+  if (user >= n_users) return;
+  float* s = reinterpret_cast<float*>(msm) + (size_t)warp * n_cand;
+  int* id = reinterpret_cast<int*>(msm + (size_t)4 * n_cand * sizeof(float)) + (size_t)warp * n_cand;
+  for (int j = lane; j < n_cand; j += 32) {
+    s[j] = cs[user * n_cand + j];
+    id[j] = ci[user * n_cand + j];
+  }
+  __syncwarp();
+  for (int r = 0; r < k; ++r) {
+    float bs = -INFINITY;
+    int bi = 0x7fffffff, bj = -1;
+    for (int j = lane; j < n_cand; j += 32) {
+      const float x = s[j];
+      const int y = id[j];
+      if (y >= 0 && (x > bs || (x == bs && y < bi))) {
+        bs = x; bi = y; bj = j;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float xs = __shfl_xor_sync(0xffffffffu, bs, o);
+      const int xi = __shfl_xor_sync(0xffffffffu, bi, o);
+      const int xj = __shfl_xor_sync(0xffffffffu, bj, o);
+      if (xj >= 0 && (bj < 0 || xs > bs || (xs == bs && xi < bi))) {
+        bs = xs; bi = xi; bj = xj;
+      }
+    }
+    if (lane == 0) {
+      os[user * k + r] = bj >= 0 ? bs : -INFINITY;
+      oi[user * k + r] = bj >= 0 ? bi : -1;
+      if (bj >= 0) id[bj] = -1;  // taken
+    }
+    __syncwarp();
+  }
+}
+
+// CE: combine the per-split (max, sumexp) pairs of each user.
+__global__ void ce_merge_kernel(const float* __restrict__ pm, const float* __restrict__ ps, long n_users, int splits,
+                                float* __restrict__ row_max, float* __restrict__ row_sum) {
+  const long u = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= n_users) return;
+  float m = -INFINITY;
+  for (int j = 0; j < splits; ++j) m = fmaxf(m, pm[u * splits + j]);
+  float s = 0.f;
+  for (int j = 0; j < splits; ++j) {
+    const float mj = pm[u * splits + j];
+    if (mj > -INFINITY) s += ps[u * splits + j] * expf(mj - m);
+  }
+  row_max[u] = m;
+  row_sum[u] = s;
+}
+
+// ----------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* ptr = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess || !ptr) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  return fn;
+}
+
+// [rows, D] bf16 row-major -> boxes of 128 rows x 64 channels, 128-byte swizzle, zero fill out of bounds.
+static int make_map(CUtensorMap* m, const void* base, long rows, int D) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return BDLRU_ERR_CUDA;
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)D, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)D * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)kTile};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%ld D=%d)", (int)r, rows, D);
+    return BDLRU_ERR_CUDA;
+  }
+  return BDLRU_OK;
+}
+
+static int fs_check(const void* Q, const void* E, long n_users, long n_rows, int D) {
+  BDLRU_REQUIRE(Q && E, "fullsort: null Q/E");
+  BDLRU_REQUIRE(n_users >= 1 && n_rows >= 1, "fullsort: bad sizes n_users=%ld n_rows=%ld", n_users, n_rows);
+  BDLRU_REQUIRE(D % 64 == 0 && D >= 64 && D <= 256, "fullsort: D=%d must be a multiple of 64 in [64, 256]", D);
+  BDLRU_REQUIRE(aligned(Q, 16) && aligned(E, 16), "fullsort: Q/E must be 16-byte aligned");
+  BDLRU_REQUIRE(n_rows < (1L << 31) && n_users < (1L << 31), "fullsort: sizes must fit int32");
+  return BDLRU_OK;
+}
+
+template <int MODE>
+static int fs_launch(const FsPlan& pl, const CUtensorMap& mq, const CUtensorMap& me, const FsParams& p,
+                     cudaStream_t st) {
+  const int grid = pl.n_ug * pl.splits;
+  if (pl.UB == 2) {
+    BDLRU_CUDA(cudaFuncSetAttribute(fullsort_kernel<2, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    fullsort_kernel<2, MODE><<<grid, pl.threads, pl.smem, st>>>(mq, me, p);
+  } else {
+    BDLRU_CUDA(cudaFuncSetAttribute(fullsort_kernel<1, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    fullsort_kernel<1, MODE><<<grid, pl.threads, pl.smem, st>>>(mq, me, p);
+  }
+  BDLRU_LAUNCHED();
+  return BDLRU_OK;
+}
+
+}  // namespace bdlru
 
 using namespace bdlru;
 
-#define UNSUPPORTED(name)                                              \
-  do {                                                                 \
-    set_error(name ": tcgen05 kernel not built into this library yet"); \
-    return BDLRU_ERR_UNSUPPORTED;                                      \
-  } while (0)
+extern "C" BDLRU_API int bdlru_fullsort_available(void) { return 1; }
 
-extern "C" BDLRU_API int bdlru_fullsort_available(void) { return 0; }
-extern "C" BDLRU_API size_t bdlru_fullsort_topk_workspace_bytes(int64_t, int64_t, int, int) { return 0; }
-extern "C" BDLRU_API int bdlru_fullsort_topk(const void*, const void*, int64_t, int64_t, int, int, int64_t, int64_t,
-                                             float*, int32_t*, void*, size_t, void*) {
-  UNSUPPORTED("bdlru_fullsort_topk");
+extern "C" BDLRU_API size_t bdlru_fullsort_topk_workspace_bytes(int64_t n_users, int64_t n_rows, int D, int k) {
+  FsPlan pl;
+  if (D % 64 != 0 || D < 64 || D > 256 || k < 1 || k > 32 || !fs_plan(n_users, n_rows, D, k, &pl)) return 0;
+  return (size_t)n_users * pl.splits * k * 8;
 }
-extern "C" BDLRU_API int bdlru_topk_merge(const float*, const int32_t*, int64_t, int, int, float*, int32_t*, void*) {
-  UNSUPPORTED("bdlru_topk_merge");
+
+extern "C" BDLRU_API int bdlru_fullsort_topk(const void* Q, const void* E, int64_t n_users, int64_t n_rows, int D, int k,
+                                             int64_t id_offset, int64_t mask_id, float* out_scores, int32_t* out_ids,
+                                             void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = fs_check(Q, E, n_users, n_rows, D);
+  if (rc) return rc;
+  BDLRU_REQUIRE(k >= 1 && k <= 32, "fullsort_topk: k=%d not in [1, 32]", k);
+  BDLRU_REQUIRE(out_scores && out_ids, "fullsort_topk: null outputs");
+  BDLRU_REQUIRE(id_offset >= 0 && id_offset + n_rows < (1L << 31), "fullsort_topk: item ids must fit int32");
+  FsPlan pl;
+  BDLRU_REQUIRE(fs_plan(n_users, n_rows, D, k, &pl), "fullsort_topk: no tiling fits shared memory (D=%d k=%d)", D, k);
+  const size_t need = (size_t)n_users * pl.splits * k * 8;
+  BDLRU_REQUIRE(workspace && workspace_bytes >= need, "fullsort_topk: workspace %zu < %zu bytes", workspace_bytes, need);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  CUtensorMap mq, me;
+  if ((rc = make_map(&mq, Q, n_users, D))) return rc;
+  if ((rc = make_map(&me, E, n_rows, D))) return rc;
+  FsParams p = {};
+  p.D = D; p.k = k; p.stages = pl.stages; p.splits = pl.splits; p.n_ug = pl.n_ug;
+  p.n_users = n_users; p.n_rows = n_rows; p.id_offset = id_offset;
+  p.mask_local = (mask_id >= id_offset && mask_id < id_offset + n_rows) ? mask_id - id_offset : -1;
+  p.tiles_total = pl.tiles_total;
+  p.part_scores = reinterpret_cast<float*>(workspace);
+  p.part_ids = reinterpret_cast<int*>(p.part_scores + (size_t)n_users * pl.splits * k);
+  if ((rc = fs_launch<MODE_TOPK>(pl, mq, me, p, st))) return rc;
+  const int n_cand = pl.splits * k;
+  const size_t msmem = (size_t)4 * n_cand * 8;
+  BDLRU_REQUIRE(msmem <= 200 * 1024, "fullsort_topk: merge of %d candidates per user does not fit", n_cand);
+  BDLRU_CUDA(cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
+  topk_merge_kernel<<<(unsigned)((n_users + 3) / 4), 128, msmem, st>>>(p.part_scores, p.part_ids, n_users, n_cand, k,
+                                                                      out_scores, out_ids);
+  BDLRU_LAUNCHED();
+  return BDLRU_OK;
 }
-extern "C" BDLRU_API size_t bdlru_fullsort_ce_workspace_bytes(int64_t, int64_t, int) { return 0; }
-extern "C" BDLRU_API int bdlru_fullsort_ce_fwd(const void*, const void*, const int64_t*, int64_t, int64_t, int, int64_t,
-                                               float*, float*, float*, void*, size_t, void*) {
-  UNSUPPORTED("bdlru_fullsort_ce_fwd");
+
+extern "C" BDLRU_API int bdlru_topk_merge(const float* cand_scores, const int32_t* cand_ids, int64_t n_users,
+                                          int n_lists, int k, float* out_scores, int32_t* out_ids, void* stream) {
+  BDLRU_REQUIRE(cand_scores && cand_ids && out_scores && out_ids, "topk_merge: null pointer");
+  BDLRU_REQUIRE(n_users >= 1 && n_lists >= 1 && k >= 1 && k <= 32, "topk_merge: bad sizes");
+  const int n_cand = n_lists * k;
+  const size_t msmem = (size_t)4 * n_cand * 8;
+  BDLRU_REQUIRE(msmem <= 200 * 1024, "topk_merge: %d candidates per user do not fit", n_cand);
+  BDLRU_CUDA(cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
+  topk_merge_kernel<<<(unsigned)((n_users + 3) / 4), 128, msmem, reinterpret_cast<cudaStream_t>(stream)>>>(
+      cand_scores, cand_ids, n_users, n_cand, k, out_scores, out_ids);
+  BDLRU_LAUNCHED();
+  return BDLRU_OK;
 }
+
+extern "C" BDLRU_API size_t bdlru_fullsort_ce_workspace_bytes(int64_t n_users, int64_t n_rows, int D) {
+  FsPlan pl;
+  if (D % 64 != 0 || D < 64 || D > 256 || !fs_plan(n_users, n_rows, D, 1, &pl)) return 0;
+  return (size_t)n_users * pl.splits * 8;
+}
+
+extern "C" BDLRU_API int bdlru_fullsort_ce_fwd(const void* Q, const void* E, const int64_t* pos, int64_t n_users,
+                                               int64_t n_rows, int D, int64_t id_offset, float* row_max,
+                                               float* row_sumexp, float* pos_logit, void* workspace,
+                                               size_t workspace_bytes, void* stream) {
+  int rc = fs_check(Q, E, n_users, n_rows, D);
+  if (rc) return rc;
+  BDLRU_REQUIRE(pos && row_max && row_sumexp && pos_logit, "fullsort_ce_fwd: null pointer");
+  FsPlan pl;
+  BDLRU_REQUIRE(fs_plan(n_users, n_rows, D, 1, &pl), "fullsort_ce_fwd: no tiling fits shared memory (D=%d)", D);
+  const size_t need = (size_t)n_users * pl.splits * 8;
+  BDLRU_REQUIRE(workspace && workspace_bytes >= need, "fullsort_ce_fwd: workspace %zu < %zu bytes", workspace_bytes, need);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  CUtensorMap mq, me;
+  if ((rc = make_map(&mq, Q, n_users, D))) return rc;
+  if ((rc = make_map(&me, E, n_rows, D))) return rc;
+  FsParams p = {};
+  p.D = D; p.k = 1; p.stages = pl.stages; p.splits = pl.splits; p.n_ug = pl.n_ug;
+  p.n_users = n_users; p.n_rows = n_rows; p.id_offset = id_offset; p.mask_local = -1;
+  p.tiles_total = pl.tiles_total;
+  p.part_max = reinterpret_cast<float*>(workspace);
+  p.part_sum = p.part_max + (size_t)n_users * pl.splits;
+  p.pos = pos;
+  p.pos_logit = pos_logit;
+  if ((rc = fs_launch<MODE_CE>(pl, mq, me, p, st))) return rc;
+  ce_merge_kernel<<<(unsigned)((n_users + 255) / 256), 256, 0, st>>>(p.part_max, p.part_sum, n_users, pl.splits,
+                                                                     row_max, row_sumexp);
+  BDLRU_LAUNCHED();
+  return BDLRU_OK;
+}
+
 extern "C" BDLRU_API int bdlru_fullsort_ce_bwd(const void*, const void*, const int64_t*, const float*, float, int64_t,
                                                int64_t, int, int64_t, float*, float*, void*, size_t, void*) {
-  UNSUPPORTED("bdlru_fullsort_ce_bwd");
+  set_error("bdlru_fullsort_ce_bwd: tcgen05 kernel not built into this library yet");
+  return BDLRU_ERR_UNSUPPORTED;
 }

@@ -247,3 +247,97 @@ def embed_layernorm(ids, table, gamma, beta, eps=1e-12, dropout_p=0.0, seed=0, p
 def fullsort_supported(D):
     """Shapes the tcgen05 full-sort kernels take: bf16 operands, D a multiple of 64 up to 256."""
     return D % 64 == 0 and D <= 256 and bool(L.load().bdlru_fullsort_available())
+
+
+def _bf16_rows(t):
+    """bf16, row-major, 16-byte aligned copy/view of a [rows, D] matrix (the operand format of the tensor cores)."""
+    t = t.detach()
+    if t.dtype != torch.bfloat16:
+        t = t.to(torch.bfloat16)
+    return t.contiguous()
+
+
+def fullsort_topk(q, table, k, mask_id=0, id_offset=0):
+    """Fused full-sort scoring + top-k (RecBLR.py:114-122 + RecBole's `scores[:, 0] = -inf; torch.topk`): returns
+    (scores fp32 [B, k], ids int32 [B, k]) of q @ table^T without forming [B, n_rows].  Operands are rounded to bf16,
+    accumulated in fp32 on the tcgen05 tensor cores; ordering is score descending, LOWEST id first among ties; the row
+    with global id `mask_id` is excluded (-1: none).  Row j of `table` has global id id_offset + j (row shards)."""
+    L.require_cuda(q, table)
+    assert q.dim() == 2 and table.dim() == 2 and q.shape[1] == table.shape[1]
+    B, D = q.shape
+    N = table.shape[0]
+    qb, eb = _bf16_rows(q), _bf16_rows(table)
+    lib = L.load()
+    out_s = torch.empty((B, k), dtype=torch.float32, device=q.device)
+    out_i = torch.empty((B, k), dtype=torch.int32, device=q.device)
+    nws = lib.bdlru_fullsort_topk_workspace_bytes(B, N, D, k)
+    ws = _workspace(q.device, nws)
+    L.check(lib.bdlru_fullsort_topk(L.ptr(qb), L.ptr(eb), B, N, D, k, id_offset, mask_id, L.ptr(out_s), L.ptr(out_i),
+                                    L.ptr(ws), nws, L.stream_ptr(q)))
+    return out_s, out_i
+
+
+def topk_merge(cand_scores, cand_ids, k):
+    """Keeps the k best of [B, n_lists * k] candidates by (score desc, id asc) — the local step of the NCCL merge."""
+    L.require_cuda(cand_scores, cand_ids)
+    B, nc = cand_scores.shape
+    assert nc % k == 0 and cand_ids.shape == (B, nc) and cand_ids.dtype == torch.int32
+    cs, ci = cand_scores.float().contiguous(), cand_ids.contiguous()
+    out_s = torch.empty((B, k), dtype=torch.float32, device=cs.device)
+    out_i = torch.empty((B, k), dtype=torch.int32, device=cs.device)
+    L.check(L.load().bdlru_topk_merge(L.ptr(cs), L.ptr(ci), B, nc // k, k, L.ptr(out_s), L.ptr(out_i), L.stream_ptr(cs)))
+    return out_s, out_i
+
+
+def fullsort_ce_stats(q, table, pos, id_offset=0):
+    """Per-user (row_max, row_sumexp, pos_logit) of the logits q @ table^T over this table (shard), never materialised.
+    pos_logit is written only for users whose positive row lives in this shard (others keep 0)."""
+    L.require_cuda(q, table, pos)
+    B, D = q.shape
+    N = table.shape[0]
+    qb, eb = _bf16_rows(q), _bf16_rows(table)
+    lib = L.load()
+    row_max = torch.empty(B, dtype=torch.float32, device=q.device)
+    row_sum = torch.empty_like(row_max)
+    pos_logit = torch.zeros_like(row_max)
+    nws = lib.bdlru_fullsort_ce_workspace_bytes(B, N, D)
+    ws = _workspace(q.device, nws)
+    L.check(lib.bdlru_fullsort_ce_fwd(L.ptr(qb), L.ptr(eb), L.ptr(pos.contiguous()), B, N, D, id_offset, L.ptr(row_max),
+                                      L.ptr(row_sum), L.ptr(pos_logit), L.ptr(ws), nws, L.stream_ptr(q)))
+    return row_max, row_sum, pos_logit
+
+
+class _FullsortCE(torch.autograd.Function):
+    """mean_b(logsumexp_n(q_b . E_n) - q_b . E_pos_b) over ALL rows of E (RecBLR.py:99-103), logits never stored."""
+
+    @staticmethod
+    def forward(ctx, q, table, pos):
+        qb, eb = _bf16_rows(q), _bf16_rows(table)
+        m, s, pl = fullsort_ce_stats(qb, eb, pos)
+        lse = m + torch.log(s)
+        ctx.save_for_backward(qb, eb, pos, lse)
+        ctx.dtypes = (q.dtype, table.dtype)
+        return (lse - pl).mean()
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        qb, eb, pos, lse = ctx.saved_tensors
+        B, D = qb.shape
+        N = eb.shape[0]
+        lib = L.load()
+        dQ = torch.empty((B, D), dtype=torch.float32, device=qb.device)
+        dE = torch.empty((N, D), dtype=torch.float32, device=qb.device)
+        nws = lib.bdlru_fullsort_ce_workspace_bytes(B, N, D)
+        ws = _workspace(qb.device, nws)
+        # dloss/dlogit = (softmax - onehot) / B, times the upstream scalar (kept on the device: no sync)
+        L.check(lib.bdlru_fullsort_ce_bwd(L.ptr(qb), L.ptr(eb), L.ptr(pos), L.ptr(lse), 1.0 / B, B, N, D, 0, L.ptr(dQ),
+                                          L.ptr(dE), L.ptr(ws), nws, L.stream_ptr(qb)))
+        g = grad_loss.float()
+        return (dQ * g).to(ctx.dtypes[0]), (dE * g).to(ctx.dtypes[1]), None
+
+
+def fullsort_cross_entropy(q, table, pos):
+    """Fused full-softmax cross-entropy over every row of `table` (incl. the pad row 0), mean over the
+    batch: bf16 operands, fp32 accumulation and statistics, [B, n_items] never materialised in forward or backward."""
+    L.require_cuda(q, table, pos)
+    return _FullsortCE.apply(q, table, pos.contiguous())
