@@ -13,11 +13,14 @@
 // Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one lane), warps 2.. = epilogue,
 // one warp per 32 TMEM lanes per user block (a warp may only touch TMEM lanes 32*(warp%4)..+31): thread == user.
 //
-// Top-k epilogue: every thread keeps its user's k best (score, id) sorted in shared memory ([k][users] so lanes hit
-// distinct banks) and the k-th score in a register.  A 32-score chunk is first reduced to its maximum; only if that
-// beats the threshold are the 32 scores inspected one by one (rare after the first few tiles: the expected number of
-// insertions over n items is ~k ln(n/k)).  Items arrive in increasing id order and an item is inserted only if it is
-// STRICTLY better than the k-th, after all entries with an equal score, so ties resolve to the lowest id.
+// Top-k epilogue: every thread keeps its user's K best (score, id) sorted in REGISTERS (K = 10/16/20/32 by template)
+// and the K-th score as threshold.  A 32-score chunk is first reduced to its maximum; only if some lane's maximum beats
+// its threshold does the warp enter insert rounds: each lane with a candidate extracts its chunk maximum (first index
+// among equals), inserts it with a branch-free unrolled shift, knocks it out and recomputes its maximum, until no lane
+// has a candidate left.  Lanes insert together, so a round costs ~100 + 5K issue slots for up to 32 insertions (the
+// expected number of insertions per user over n items is ~K ln(n/K); a one-lane-at-a-time list in shared memory made
+// the epilogue 10x slower than the MMAs).  An item is inserted only if STRICTLY better than the K-th and after all
+// entries with an equal score; chunks arrive in increasing id order, so ties resolve to the lowest id.
 // The grid splits the item range S ways; a second kernel merges the S (or, multi-GPU, G) sorted lists per user by
 // (score desc, id asc).
 #include <cuda.h>
@@ -61,7 +64,8 @@ static bool fs_plan(long n_users, long n_rows, int D, int k, FsPlan* pl) {
   const long tiles = (n_rows + kTile - 1) / kTile;
   for (int UB = 2; UB >= 1; --UB) {
     const size_t q = (size_t)UB * n_slab * kSlab;
-    const size_t lists = (size_t)8 * k * kTile * UB;
+    const size_t lists = 0;  // the per-user lists live in registers
+    (void)k;
     const size_t fixed = 1024 /*align slack*/ + q + lists + 256 /*barriers*/;
     if (fixed >= (size_t)kMaxSmem) continue;
     int stages = (int)(((size_t)kMaxSmem - fixed) / ((size_t)n_slab * kSlab));
@@ -71,10 +75,13 @@ static bool fs_plan(long n_users, long n_rows, int D, int k, FsPlan* pl) {
     pl->UB = UB;
     pl->stages = stages;
     pl->n_ug = (int)((n_users + (long)kTile * UB - 1) / ((long)kTile * UB));
+    // ONE wave of long item streams: the insert work per user grows only with the log of the stream length, so
+    // fewer, longer streams keep the epilogue under the MMA time.  splits = floor(SMs / user groups), at least 4 tiles
+    // per CTA; when there are more user groups than SMs every group gets one CTA (several waves).
     long max_s = tiles / 4 > 0 ? tiles / 4 : 1;
-    long want = ((long)sm_count() * 4 + pl->n_ug - 1) / pl->n_ug;
+    long want = (long)sm_count() / pl->n_ug;
+    if (want < 1) want = 1;
     long s = want < max_s ? want : max_s;
-    if (s < 1) s = 1;
     pl->splits = (int)s;
     pl->threads = 64 + 128 * UB;
     pl->smem = 1024 + q + (size_t)stages * n_slab * kSlab + lists + 256;
@@ -84,20 +91,21 @@ static bool fs_plan(long n_users, long n_rows, int D, int k, FsPlan* pl) {
   return false;
 }
 
-// ----------------------------------------------------------------------------- per-thread sorted list in smem
-// Inserts (v, id) after every entry with score >= v; the caller has checked v > list[k-1].  Returns the new k-th.
-__device__ __noinline__ float topk_insert(float* ls, int* li, int LW, int k, float v, int id) {
-  int j = k - 1;
-  while (j > 0) {
-    const float pv = ls[(j - 1) * LW];
-    if (!(pv < v)) break;
-    ls[j * LW] = pv;
-    li[j * LW] = li[(j - 1) * LW];
-    --j;
+// ----------------------------------------------------------------------------- per-thread sorted list in registers
+// Inserts (v, id) after every entry with score >= v (branch-free, fully unrolled).  Caller has checked v > ls[K-1].
+template <int K>
+__device__ __forceinline__ void topk_insert(float (&ls)[K], int (&li)[K], float v, int id) {
+#pragma unroll
+  for (int j = K - 1; j >= 1; --j) {
+    const bool prev = ls[j - 1] < v;  // entry j-1 moves down to j
+    const bool cur = ls[j] < v;
+    ls[j] = prev ? ls[j - 1] : (cur ? v : ls[j]);
+    li[j] = prev ? li[j - 1] : (cur ? id : li[j]);
   }
-  ls[j * LW] = v;
-  li[j * LW] = id;
-  return ls[(k - 1) * LW];
+  if (ls[0] < v) {
+    ls[0] = v;
+    li[0] = id;
+  }
 }
 
 __device__ __forceinline__ float max32(const float (&v)[32]) {
@@ -107,20 +115,16 @@ __device__ __forceinline__ float max32(const float (&v)[32]) {
   return fmaxf(fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3])), fmaxf(fmaxf(m[4], m[5]), fmaxf(m[6], m[7])));
 }
 
-template <int UB, int MODE>
+template <int UB, int MODE, int K>
 __global__ void __launch_bounds__(64 + 128 * UB, 1)
 fullsort_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmE, const FsParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_slab = p.D >> 6;
-  constexpr int LW = kTile * UB;  // list row width (threads of the epilogue)
-
   uint8_t* sQ = smem;
   uint8_t* sE = sQ + (size_t)UB * n_slab * kSlab;
-  float* lsc = reinterpret_cast<float*>(sE + (size_t)p.stages * n_slab * kSlab);
-  int* lid = reinterpret_cast<int*>(lsc + (size_t)p.k * LW);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(lid + (size_t)p.k * LW);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sE + (size_t)p.stages * n_slab * kSlab);
   uint64_t* q_full = bars;
   uint64_t* e_full = bars + 1;
   uint64_t* e_empty = e_full + kMaxStages;
@@ -216,19 +220,16 @@ fullsort_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int row = q * 32 + lane;          // user row inside the block
     const int col = ub * kTile + row;       // this thread's list column
     const long user = user0 + col;
-    float* ls = lsc + col;
-    int* li = lid + col;
-    float thr = -INFINITY;                  // top-k: current k-th best; CE: unused
+    float ls[K];                            // top-k: K best scores, descending
+    int li[K];                              //        and their global ids
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      ls[j] = -INFINITY;
+      li[j] = -1;
+    }
     float run_m = -INFINITY, run_s = 0.f;   // CE: online max / sum of exp
     long pos_local = -1;
-    if (MODE == MODE_TOPK) {
-      for (int j = 0; j < p.k; ++j) {
-        ls[j * LW] = -INFINITY;
-        li[j * LW] = -1;
-      }
-    } else {
-      if (user < p.n_users) pos_local = p.pos[user] - p.id_offset;
-    }
+    if (MODE == MODE_CE && user < p.n_users) pos_local = p.pos[user] - p.id_offset;
     constexpr float kLog2e = 1.4426950408889634f;
     for (int it = 0; it < n_iter; ++it) {
       const int b = it & 1;
@@ -252,13 +253,19 @@ fullsort_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           for (int i = 0; i < 32; ++i)
             if (cbase + i >= p.n_rows || cbase + i == p.mask_local) v[i] = -INFINITY;
         }
-        const float m = max32(v);
+        float m = max32(v);
         if (MODE == MODE_TOPK) {
-          if (m > thr) {
-            const int id0 = (int)(p.id_offset + cbase);
+          const int id0 = (int)(p.id_offset + cbase);
+          while (__any_sync(0xffffffffu, m > ls[K - 1])) {  // insert rounds: lanes with a candidate act together
+            if (m > ls[K - 1]) {
+              int idx = 31;
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (v[i] > thr) thr = topk_insert(ls, li, LW, p.k, v[i], id0 + i);
+              for (int i = 30; i >= 0; --i) idx = (v[i] == m) ? i : idx;  // first index among equal scores
+              topk_insert<K>(ls, li, m, id0 + idx);
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = (i == idx) ? -INFINITY : v[i];
+              m = max32(v);
+            }
           }
         } else {
           if (m > run_m) {  // rescale the running sum to the new maximum (m is finite here)
@@ -293,10 +300,12 @@ fullsort_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       if (MODE == MODE_TOPK) {
         float* os = p.part_scores + ((size_t)user * p.splits + split) * p.k;
         int* oi = p.part_ids + ((size_t)user * p.splits + split) * p.k;
-        for (int j = 0; j < p.k; ++j) {
-          os[j] = ls[j * LW];
-          oi[j] = li[j * LW];
-        }
+#pragma unroll
+        for (int j = 0; j < K; ++j)
+          if (j < p.k) {
+            os[j] = ls[j];
+            oi[j] = li[j];
+          }
       } else {
         p.part_max[(size_t)user * p.splits + split] = run_m;
         p.part_sum[(size_t)user * p.splits + split] = run_s;
@@ -421,19 +430,29 @@ static int fs_check(const void* Q, const void* E, long n_users, long n_rows, int
   return BDLRU_OK;
 }
 
+template <int UB, int MODE, int K>
+static int fs_launch_one(const FsPlan& pl, const CUtensorMap& mq, const CUtensorMap& me, const FsParams& p,
+                         cudaStream_t st) {
+  BDLRU_CUDA(cudaFuncSetAttribute(fullsort_kernel<UB, MODE, K>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)pl.smem));
+  fullsort_kernel<UB, MODE, K><<<pl.n_ug * pl.splits, pl.threads, pl.smem, st>>>(mq, me, p);
+  BDLRU_LAUNCHED();
+  return BDLRU_OK;
+}
+
 template <int MODE>
 static int fs_launch(const FsPlan& pl, const CUtensorMap& mq, const CUtensorMap& me, const FsParams& p,
                      cudaStream_t st) {
-  const int grid = pl.n_ug * pl.splits;
-  if (pl.UB == 2) {
-    BDLRU_CUDA(cudaFuncSetAttribute(fullsort_kernel<2, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-    fullsort_kernel<2, MODE><<<grid, pl.threads, pl.smem, st>>>(mq, me, p);
-  } else {
-    BDLRU_CUDA(cudaFuncSetAttribute(fullsort_kernel<1, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-    fullsort_kernel<1, MODE><<<grid, pl.threads, pl.smem, st>>>(mq, me, p);
-  }
-  BDLRU_LAUNCHED();
-  return BDLRU_OK;
+  if (MODE == MODE_CE)
+    return pl.UB == 2 ? fs_launch_one<2, MODE_CE, 1>(pl, mq, me, p, st) : fs_launch_one<1, MODE_CE, 1>(pl, mq, me, p, st);
+#define FS_K(KK)                                                                               \
+  if (p.k <= KK)                                                                               \
+    return pl.UB == 2 ? fs_launch_one<2, MODE_TOPK, KK>(pl, mq, me, p, st)                     \
+                      : fs_launch_one<1, MODE_TOPK, KK>(pl, mq, me, p, st);
+  FS_K(10) FS_K(16) FS_K(20) FS_K(32)
+#undef FS_K
+  set_error("fullsort: k=%d > 32", p.k);
+  return BDLRU_ERR_INVALID;
 }
 
 }  // namespace bdlru
