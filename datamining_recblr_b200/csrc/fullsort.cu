@@ -24,6 +24,7 @@
 // The grid splits the item range S ways; a second kernel merges the S (or, multi-GPU, G) sorted lists per user by
 // (score desc, id asc).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "tc05.cuh"
@@ -39,6 +40,7 @@ enum { MODE_TOPK = 0, MODE_CE = 1 };
 
 struct FsParams {
   int D, k, stages, splits, n_ug;
+  int dbg;  // BDLRU_FS_DEBUG (tuning only): 1 = epilogue skips loads+arithmetic, 2 = MMA warp skips the MMAs
   long n_users, n_rows;       // rows of Q, rows of this E shard
   long id_offset, mask_local; // global id of E row 0; LOCAL row to exclude (-1: none)
   long tiles_total;
@@ -196,6 +198,7 @@ fullsort_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tc::fence_after_sync();
 #pragma unroll
         for (int ub = 0; ub < UB; ++ub) {
+          if (p.dbg & 2) break;
           const uint32_t d_tmem = tmem_base + (uint32_t)((b * UB + ub) * kTile);
           for (int sl = 0; sl < n_slab; ++sl) {
             const uint32_t a0 = tc::smem_u32(sQ + (size_t)(ub * n_slab + sl) * kSlab);
@@ -239,62 +242,93 @@ fullsort_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tc::mbar_wait(&acc_full[b], bph);
       tc::fence_after_sync();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((b * UB + ub) * kTile);
+      // The accumulator tile is pulled into registers CH chunks (CH*32 columns) at a time; once the last group has
+      // landed the TMEM buffer is handed back to the MMA warp BEFORE the scores are processed, so the tensor pipe
+      // only ever waits for the loads, not for the top-k / softmax arithmetic.
+      constexpr int CH = (MODE == MODE_TOPK && K > 16) ? 2 : 4;
+      if (p.dbg & 1) {
+        tc::fence_before_sync();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&acc_empty[b]);
+        continue;
+      }
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t raw[32];
-        tc::tmem_ld_32x32(taddr + c * 32, raw);
+      for (int g = 0; g < 4 / CH; ++g) {
+        uint32_t raw[CH][32];
+#pragma unroll
+        for (int c = 0; c < CH; ++c) tc::tmem_ld_32x32(taddr + (g * CH + c) * 32, raw[c]);
         tc::tmem_ld_wait();
-        float v[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
-        const long cbase = base + c * 32;
-        if (special) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (cbase + i >= p.n_rows || cbase + i == p.mask_local) v[i] = -INFINITY;
+        if (g == 4 / CH - 1) {
+          tc::fence_before_sync();
+          __syncwarp();
+          if (lane == 0) tc::mbar_arrive(&acc_empty[b]);
         }
-        float m = max32(v);
+        // all CH chunk maxima first (independent trees: ILP), one vote for the common case "nothing to insert"
+        float v[CH][32];
+        float m[CH];
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[c][i] = __uint_as_float(raw[c][i]);
+          if (special) {
+            const long cb = base + (g * CH + c) * 32;
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (cb + i >= p.n_rows || cb + i == p.mask_local) v[c][i] = -INFINITY;
+          }
+          m[c] = max32(v[c]);
+        }
+        float mt = m[0];
+#pragma unroll
+        for (int c = 1; c < CH; ++c) mt = fmaxf(mt, m[c]);
         if (MODE == MODE_TOPK) {
-          const int id0 = (int)(p.id_offset + cbase);
-          while (__any_sync(0xffffffffu, m > ls[K - 1])) {  // insert rounds: lanes with a candidate act together
-            if (m > ls[K - 1]) {
-              int idx = 31;
+          if (__any_sync(0xffffffffu, mt > ls[K - 1])) {
 #pragma unroll
-              for (int i = 30; i >= 0; --i) idx = (v[i] == m) ? i : idx;  // first index among equal scores
-              topk_insert<K>(ls, li, m, id0 + idx);
+            for (int c = 0; c < CH; ++c) {
+              const int id0 = (int)(p.id_offset + base + (g * CH + c) * 32);
+              while (__any_sync(0xffffffffu, m[c] > ls[K - 1])) {  // insert rounds: lanes with a candidate act together
+                if (m[c] > ls[K - 1]) {
+                  int idx = 31;
 #pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = (i == idx) ? -INFINITY : v[i];
-              m = max32(v);
+                  for (int i = 30; i >= 0; --i) idx = (v[c][i] == m[c]) ? i : idx;  // first index among equal scores
+                  topk_insert<K>(ls, li, m[c], id0 + idx);
+#pragma unroll
+                  for (int i = 0; i < 32; ++i) v[c][i] = (i == idx) ? -INFINITY : v[c][i];
+                  m[c] = max32(v[c]);
+                }
+              }
             }
           }
         } else {
-          if (m > run_m) {  // rescale the running sum to the new maximum (m is finite here)
-            run_s *= ex2_ftz((run_m - m) * kLog2e);
-            run_m = m;
+          if (mt > run_m) {  // rescale the running sum to the new maximum (mt is finite here)
+            run_s *= ex2_ftz((run_m - mt) * kLog2e);
+            run_m = mt;
           }
           if (run_m > -INFINITY) {
             const float mb = run_m * kLog2e;
-            float acc0 = 0.f, acc1 = 0.f;
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              acc0 += ex2_ftz(fmaf(v[i], kLog2e, -mb));
-              acc1 += ex2_ftz(fmaf(v[i + 1], kLog2e, -mb));
-            }
-            run_s += acc0 + acc1;
+            for (int c = 0; c < CH; ++c)
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) acc[u] += ex2_ftz(fmaf(v[c][i + u], kLog2e, -mb));
+              }
+            run_s += (acc[0] + acc[1]) + (acc[2] + acc[3]);
           }
-          if (pos_local >= cbase && pos_local < cbase + 32) {
-            const int sel = (int)(pos_local - cbase);
+          const long gb = base + g * CH * 32;
+          if (pos_local >= gb && pos_local < gb + CH * 32) {
+            const int sel = (int)(pos_local - gb);
             float pv = 0.f;
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (i == sel) pv = v[i];
+            for (int c = 0; c < CH; ++c)
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (c * 32 + i == sel) pv = v[c][i];
             p.pos_logit[user] = pv;
           }
         }
       }
-      tc::fence_before_sync();
-      __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&acc_empty[b]);
     }
     if (user < p.n_users) {
       if (MODE == MODE_TOPK) {
@@ -421,6 +455,15 @@ static int make_map(CUtensorMap* m, const void* base, long rows, int D) {
   return BDLRU_OK;
 }
 
+static int fs_debug() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("BDLRU_FS_DEBUG");
+    v = e ? atoi(e) : 0;
+  }
+  return v;
+}
+
 static int fs_check(const void* Q, const void* E, long n_users, long n_rows, int D) {
   BDLRU_REQUIRE(Q && E, "fullsort: null Q/E");
   BDLRU_REQUIRE(n_users >= 1 && n_rows >= 1, "fullsort: bad sizes n_users=%ld n_rows=%ld", n_users, n_rows);
@@ -485,6 +528,7 @@ extern "C" BDLRU_API int bdlru_fullsort_topk(const void* Q, const void* E, int64
   if ((rc = make_map(&me, E, n_rows, D))) return rc;
   FsParams p = {};
   p.D = D; p.k = k; p.stages = pl.stages; p.splits = pl.splits; p.n_ug = pl.n_ug;
+  p.dbg = fs_debug();
   p.n_users = n_users; p.n_rows = n_rows; p.id_offset = id_offset;
   p.mask_local = (mask_id >= id_offset && mask_id < id_offset + n_rows) ? mask_id - id_offset : -1;
   p.tiles_total = pl.tiles_total;
