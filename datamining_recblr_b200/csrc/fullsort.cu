@@ -32,15 +32,15 @@
 namespace bdlru {
 
 constexpr int kTile = 128;                 // users per block (TMEM lanes) and items per E tile (MMA N)
-constexpr uint32_t kSlab = 128 * 128;      // bytes of one [128 rows x 64 bf16] swizzled slab
 constexpr int kMaxSmem = 227 * 1024;
-constexpr int kMaxStages = 6;
+constexpr int kMaxStages = 8;
 
 enum { MODE_TOPK = 0, MODE_CE = 1 };
 
 struct FsParams {
   int D, k, stages, splits, n_ug;
-  int dbg;  // BDLRU_FS_DEBUG (tuning only): 1 = epilogue skips loads+arithmetic, 2 = MMA warp skips the MMAs
+  int dbg;  // BDLRU_FS_DEBUG (tuning only): 1 = epilogue skips loads+arithmetic, 2 = MMA warp skips the MMAs, 4 = no TMA loads
+  const void* Q;              // [n_users, D] bf16 row-major
   long n_users, n_rows;       // rows of Q, rows of this E shard
   long id_offset, mask_local; // global id of E row 0; LOCAL row to exclude (-1: none)
   long tiles_total;
@@ -55,42 +55,39 @@ struct FsParams {
 };
 
 struct FsPlan {
-  int UB, stages, splits, n_ug, threads;
+  int UB, NT, stages, splits, n_ug, threads;
   size_t smem;
   long tiles_total;
 };
 
-// One plan for (n_users, n_rows, D, k): used by the launch AND by the workspace query, so both agree.
+// One plan for (n_users, n_rows, D): used by the launch AND by the workspace query, so both agree.
+// TMEM budget (512 columns): UB*D/2 for Q + 2*UB*NT for the double-buffered accumulators -> NT = 96 up to D = 128,
+// 64 above.
 static bool fs_plan(long n_users, long n_rows, int D, int k, FsPlan* pl) {
+  (void)k;
   const int n_slab = D / 64;
-  const long tiles = (n_rows + kTile - 1) / kTile;
-  for (int UB = 2; UB >= 1; --UB) {
-    const size_t q = (size_t)UB * n_slab * kSlab;
-    const size_t lists = 0;  // the per-user lists live in registers
-    (void)k;
-    const size_t fixed = 1024 /*align slack*/ + q + lists + 256 /*barriers*/;
-    if (fixed >= (size_t)kMaxSmem) continue;
-    int stages = (int)(((size_t)kMaxSmem - fixed) / ((size_t)n_slab * kSlab));
-    if (stages > kMaxStages) stages = kMaxStages;
-    if (stages < 2 || (UB == 2 && stages < 3 && n_slab > 1)) continue;
-    if (UB == 2 && n_users <= kTile) continue;  // a single user block: do not waste the second one
-    pl->UB = UB;
-    pl->stages = stages;
-    pl->n_ug = (int)((n_users + (long)kTile * UB - 1) / ((long)kTile * UB));
-    // ONE wave of long item streams: the insert work per user grows only with the log of the stream length, so
-    // fewer, longer streams keep the epilogue under the MMA time.  splits = floor(SMs / user groups), at least 4 tiles
-    // per CTA; when there are more user groups than SMs every group gets one CTA (several waves).
-    long max_s = tiles / 4 > 0 ? tiles / 4 : 1;
-    long want = (long)sm_count() / pl->n_ug;
-    if (want < 1) want = 1;
-    long s = want < max_s ? want : max_s;
-    pl->splits = (int)s;
-    pl->threads = 64 + 128 * UB;
-    pl->smem = 1024 + q + (size_t)stages * n_slab * kSlab + lists + 256;
-    pl->tiles_total = tiles;
-    return true;
-  }
-  return false;
+  const int NT = D <= 128 ? 96 : 64;
+  const int UB = n_users > kTile ? 2 : 1;
+  const long tiles = (n_rows + NT - 1) / NT;
+  const size_t stage = (size_t)n_slab * NT * 128;
+  int stages = (int)(((size_t)kMaxSmem - 1024 - 256) / stage);
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages < 2) return false;
+  pl->UB = UB;
+  pl->NT = NT;
+  pl->stages = stages;
+  pl->n_ug = (int)((n_users + (long)kTile * UB - 1) / ((long)kTile * UB));
+  // ONE wave of long item streams: the insert work per user grows only with the log of the stream length, so
+  // fewer, longer streams keep the epilogue under the MMA time.  splits = floor(SMs / user groups), at least 4 tiles
+  // per CTA; when there are more user groups than SMs every group gets one CTA (several waves).
+  long max_s = tiles / 4 > 0 ? tiles / 4 : 1;
+  long want = (long)sm_count() / pl->n_ug;
+  if (want < 1) want = 1;
+  pl->splits = (int)(want < max_s ? want : max_s);
+  pl->threads = 64 + 128 * UB;
+  pl->smem = 1024 + (size_t)stages * stage + 256;
+  pl->tiles_total = tiles;
+  return true;
 }
 
 // ----------------------------------------------------------------------------- per-thread sorted list in registers
@@ -117,16 +114,17 @@ __device__ __forceinline__ float max32(const float (&v)[32]) {
   return fmaxf(fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3])), fmaxf(fmaxf(m[4], m[5]), fmaxf(m[6], m[7])));
 }
 
-template <int UB, int MODE, int K>
+template <int UB, int MODE, int K, int NT>
 __global__ void __launch_bounds__(64 + 128 * UB, 1)
-fullsort_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmE, const FsParams p) {
+fullsort_kernel(const __grid_constant__ CUtensorMap tmE, const FsParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_slab = p.D >> 6;
-  uint8_t* sQ = smem;
-  uint8_t* sE = sQ + (size_t)UB * n_slab * kSlab;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sE + (size_t)p.stages * n_slab * kSlab);
+  constexpr uint32_t kSlabB = NT * 128;    // bytes of one [NT items x 64 channels] swizzled slab
+  constexpr int NCH = NT / 32;             // 32-column chunks per accumulator tile
+  uint8_t* sE = smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sE + (size_t)p.stages * n_slab * kSlabB);
   uint64_t* q_full = bars;
   uint64_t* e_full = bars + 1;
   uint64_t* e_empty = e_full + kMaxStages;
@@ -141,11 +139,13 @@ fullsort_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const long t_end = p.tiles_total * (split + 1) / p.splits;
   const int n_iter = (int)(t_end - t_begin);
   const long user0 = (long)ug * kTile * UB;
+  // TMEM columns: [0, UB*D/2) the user block(s) Q as packed bf16 pairs (A operand), then 2 x UB accumulators of NT
+  const uint32_t q_cols = (uint32_t)(p.D >> 1);
+  const uint32_t acc_col0 = (uint32_t)UB * q_cols;
 
   if (warp == 0 && lane == 0) {
-    tc::prefetch_tensormap(&tmQ);
     tc::prefetch_tensormap(&tmE);
-    tc::mbar_init(q_full, 1);
+    tc::mbar_init(q_full, 4 * UB);
     for (int s = 0; s < p.stages; ++s) {
       tc::mbar_init(&e_full[s], 1);
       tc::mbar_init(&e_empty[s], 1);
@@ -157,7 +157,7 @@ fullsort_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     tc::fence_barrier_init();
   }
   if (warp == 1) {
-    tc::tmem_alloc(tmem_slot, 256 * UB);
+    tc::tmem_alloc(tmem_slot, 512);
     tc::tmem_relinquish();
   }
   tc::fence_before_sync();
@@ -166,54 +166,60 @@ fullsort_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===================================================================== TMA producer
-    if (lane == 0) {
-      tc::mbar_arrive_expect_tx(q_full, (uint32_t)(UB * n_slab) * kSlab);
-      for (int ub = 0; ub < UB; ++ub)
+    // ===================================================================== TMA producer (warp stays converged)
+    for (int it = 0; it < n_iter; ++it) {
+      const int s = it % p.stages;
+      const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+      tc::mbar_wait(&e_empty[s], ph ^ 1u);
+      if (tc::elect_one()) {
+        if (p.dbg & 4) {
+          tc::mbar_arrive(&e_full[s]);
+        } else {
+        tc::mbar_arrive_expect_tx(&e_full[s], (uint32_t)n_slab * kSlabB);
         for (int sl = 0; sl < n_slab; ++sl)
-          tc::tma_load_2d(sQ + (size_t)(ub * n_slab + sl) * kSlab, &tmQ, q_full, sl * 64, (int)(user0 + ub * kTile));
-      for (int it = 0; it < n_iter; ++it) {
-        const int s = it % p.stages;
-        const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
-        tc::mbar_wait(&e_empty[s], ph ^ 1u);
-        tc::mbar_arrive_expect_tx(&e_full[s], (uint32_t)n_slab * kSlab);
-        for (int sl = 0; sl < n_slab; ++sl)
-          tc::tma_load_2d(sE + (size_t)(s * n_slab + sl) * kSlab, &tmE, &e_full[s], sl * 64,
-                          (int)((t_begin + it) * kTile));
+          tc::tma_load_2d(sE + (size_t)(s * n_slab + sl) * kSlabB, &tmE, &e_full[s], sl * 64,
+                          (int)((t_begin + it) * NT));
+        }
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    // ===================================================================== MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = tc::idesc_bf16_f32(kTile, kTile, 0, 0);
-      tc::mbar_wait(q_full, 0);
+    // ===================================================================== MMA issuer (warp stays converged)
+    constexpr uint32_t idesc = tc::idesc_bf16_f32(kTile, NT, 0, 0);
+    tc::mbar_wait(q_full, 0);
+    tc::fence_after_sync();
+    for (int it = 0; it < n_iter; ++it) {
+      const int s = it % p.stages;
+      const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+      const int b = it & 1;
+      const uint32_t bph = (uint32_t)(it >> 1) & 1u;
+      tc::mbar_wait(&acc_empty[b], bph ^ 1u);
+      tc::mbar_wait(&e_full[s], ph);
       tc::fence_after_sync();
-      for (int it = 0; it < n_iter; ++it) {
-        const int s = it % p.stages;
-        const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
-        const int b = it & 1;
-        const uint32_t bph = (uint32_t)(it >> 1) & 1u;
-        tc::mbar_wait(&acc_empty[b], bph ^ 1u);
-        tc::mbar_wait(&e_full[s], ph);
-        tc::fence_after_sync();
+      if (tc::elect_one()) {
+        const uint32_t e0 = tc::smem_u32(sE + (size_t)s * n_slab * kSlabB);
+        // descriptor of (slab 0, k step 0); a K step of 16 channels is +32 bytes (+2 in the >>4 address field) inside
+        // the swizzle atom, a slab is +kSlabB
+        const uint64_t bd0 = tc::smem_desc_sw128(e0, 16, 1024);
 #pragma unroll
         for (int ub = 0; ub < UB; ++ub) {
           if (p.dbg & 2) break;
-          const uint32_t d_tmem = tmem_base + (uint32_t)((b * UB + ub) * kTile);
+          const uint32_t d_tmem = tmem_base + acc_col0 + (uint32_t)((b * UB + ub) * NT);
+          const uint32_t a_tmem = tmem_base + (uint32_t)ub * q_cols;
           for (int sl = 0; sl < n_slab; ++sl) {
-            const uint32_t a0 = tc::smem_u32(sQ + (size_t)(ub * n_slab + sl) * kSlab);
-            const uint32_t b0 = tc::smem_u32(sE + (size_t)(s * n_slab + sl) * kSlab);
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
-              const uint64_t ad = tc::smem_desc_sw128(a0 + kk * 32, 16, 1024);
-              const uint64_t bd = tc::smem_desc_sw128(b0 + kk * 32, 16, 1024);
-              tc::umma_bf16(d_tmem, ad, bd, idesc, (uint32_t)((sl | kk) != 0));
+            for (int k4 = 0; k4 < 4; ++k4) {
+              // A: 16 channels = 8 packed TMEM columns per K step
+              tc::umma_bf16_ts(d_tmem, a_tmem + (uint32_t)(sl * 4 + k4) * 8,
+                               bd0 + (uint64_t)((uint32_t)sl * (kSlabB >> 4) + (uint32_t)k4 * 2), idesc,
+                               (uint32_t)((sl | k4) != 0));
             }
           }
         }
         tc::umma_commit(&e_empty[s]);   // smem stage reusable once these MMAs have read it
         tc::umma_commit(&acc_full[b]);  // accumulators complete
       }
+      __syncwarp();
     }
   } else {
     // ===================================================================== epilogue: thread == user
@@ -221,8 +227,27 @@ fullsort_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int ub = e >> 2;
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;          // user row inside the block
-    const int col = ub * kTile + row;       // this thread's list column
-    const long user = user0 + col;
+    const long user = user0 + ub * kTile + row;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    {
+      // This thread's user row of Q -> TMEM lane `row`, columns ub*D/2 .. : bf16 pairs, channel 2j in the low half.
+      // The A operand of every MMA of this CTA then comes from TMEM, which halves the shared-memory operand traffic
+      // (with both operands in shared memory a 128x128x16 MMA needs 128 B/clk, all the SM has: measured half rate).
+      const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.Q) + user * p.D);
+      for (int j = 0; j < (p.D >> 4); ++j) {
+        uint4 lo = make_uint4(0, 0, 0, 0), hi = lo;
+        if (user < p.n_users) {
+          lo = src[2 * j];
+          hi = src[2 * j + 1];
+        }
+        const uint32_t w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+        tc::tmem_st_32x32_x8(lane_addr + (uint32_t)ub * q_cols + (uint32_t)j * 8, w);
+      }
+      tc::tmem_st_wait();
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(q_full);
+    }
     float ls[K];                            // top-k: K best scores, descending
     int li[K];                              //        and their global ids
 #pragma unroll
@@ -237,15 +262,15 @@ fullsort_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     for (int it = 0; it < n_iter; ++it) {
       const int b = it & 1;
       const uint32_t bph = (uint32_t)(it >> 1) & 1u;
-      const long base = (t_begin + it) * kTile;  // local row index of the tile's first item
-      const bool special = (base + kTile > p.n_rows) || (p.mask_local >= base && p.mask_local < base + kTile);
+      const long base = (t_begin + it) * NT;  // local row index of the tile's first item
+      const bool special = (base + NT > p.n_rows) || (p.mask_local >= base && p.mask_local < base + NT);
       tc::mbar_wait(&acc_full[b], bph);
       tc::fence_after_sync();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((b * UB + ub) * kTile);
+      const uint32_t taddr = lane_addr + acc_col0 + (uint32_t)((b * UB + ub) * NT);
       // The accumulator tile is pulled into registers CH chunks (CH*32 columns) at a time; once the last group has
       // landed the TMEM buffer is handed back to the MMA warp BEFORE the scores are processed, so the tensor pipe
       // only ever waits for the loads, not for the top-k / softmax arithmetic.
-      constexpr int CH = (MODE == MODE_TOPK && K > 16) ? 2 : 4;
+      constexpr int CH = (MODE == MODE_TOPK && K > 16) ? 1 : NCH;
       if (p.dbg & 1) {
         tc::fence_before_sync();
         __syncwarp();
@@ -253,12 +278,12 @@ fullsort_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         continue;
       }
 #pragma unroll 1
-      for (int g = 0; g < 4 / CH; ++g) {
+      for (int g = 0; g < NCH / CH; ++g) {
         uint32_t raw[CH][32];
 #pragma unroll
         for (int c = 0; c < CH; ++c) tc::tmem_ld_32x32(taddr + (g * CH + c) * 32, raw[c]);
         tc::tmem_ld_wait();
-        if (g == 4 / CH - 1) {
+        if (g == NCH / CH - 1) {
           tc::fence_before_sync();
           __syncwarp();
           if (lane == 0) tc::mbar_arrive(&acc_empty[b]);
@@ -350,7 +375,7 @@ fullsort_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   __syncthreads();
   if (warp == 1) {
     tc::fence_after_sync();
-    tc::tmem_dealloc(tmem_base, 256 * UB);
+    tc::tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -434,8 +459,8 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
-// [rows, D] bf16 row-major -> boxes of 128 rows x 64 channels, 128-byte swizzle, zero fill out of bounds.
-static int make_map(CUtensorMap* m, const void* base, long rows, int D) {
+// [rows, D] bf16 row-major -> boxes of box_rows rows x 64 channels, 128-byte swizzle, zero fill out of bounds.
+static int make_map(CUtensorMap* m, const void* base, long rows, int D, int box_rows) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled entry point not available");
@@ -443,7 +468,7 @@ static int make_map(CUtensorMap* m, const void* base, long rows, int D) {
   }
   cuuint64_t dims[2] = {(cuuint64_t)D, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)D * 2};
-  cuuint32_t box[2] = {64, (cuuint32_t)kTile};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -473,29 +498,29 @@ static int fs_check(const void* Q, const void* E, long n_users, long n_rows, int
   return BDLRU_OK;
 }
 
-template <int UB, int MODE, int K>
-static int fs_launch_one(const FsPlan& pl, const CUtensorMap& mq, const CUtensorMap& me, const FsParams& p,
-                         cudaStream_t st) {
-  BDLRU_CUDA(cudaFuncSetAttribute(fullsort_kernel<UB, MODE, K>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+template <int UB, int MODE, int K, int NT>
+static int fs_launch_one(const FsPlan& pl, const CUtensorMap& me, const FsParams& p, cudaStream_t st) {
+  BDLRU_CUDA(cudaFuncSetAttribute(fullsort_kernel<UB, MODE, K, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)pl.smem));
-  fullsort_kernel<UB, MODE, K><<<pl.n_ug * pl.splits, pl.threads, pl.smem, st>>>(mq, me, p);
+  fullsort_kernel<UB, MODE, K, NT><<<pl.n_ug * pl.splits, pl.threads, pl.smem, st>>>(me, p);
   BDLRU_LAUNCHED();
   return BDLRU_OK;
 }
 
+template <int MODE, int K>
+static int fs_launch_k(const FsPlan& pl, const CUtensorMap& me, const FsParams& p, cudaStream_t st) {
+  if (pl.NT == 96)
+    return pl.UB == 2 ? fs_launch_one<2, MODE, K, 96>(pl, me, p, st) : fs_launch_one<1, MODE, K, 96>(pl, me, p, st);
+  return pl.UB == 2 ? fs_launch_one<2, MODE, K, 64>(pl, me, p, st) : fs_launch_one<1, MODE, K, 64>(pl, me, p, st);
+}
+
 template <int MODE>
-static int fs_launch(const FsPlan& pl, const CUtensorMap& mq, const CUtensorMap& me, const FsParams& p,
-                     cudaStream_t st) {
-  if (MODE == MODE_CE)
-    return pl.UB == 2 ? fs_launch_one<2, MODE_CE, 1>(pl, mq, me, p, st) : fs_launch_one<1, MODE_CE, 1>(pl, mq, me, p, st);
-#define FS_K(KK)                                                                               \
-  if (p.k <= KK)                                                                               \
-    return pl.UB == 2 ? fs_launch_one<2, MODE_TOPK, KK>(pl, mq, me, p, st)                     \
-                      : fs_launch_one<1, MODE_TOPK, KK>(pl, mq, me, p, st);
-  FS_K(10) FS_K(16) FS_K(20) FS_K(32)
-#undef FS_K
-  set_error("fullsort: k=%d > 32", p.k);
-  return BDLRU_ERR_INVALID;
+static int fs_launch(const FsPlan& pl, const CUtensorMap& me, const FsParams& p, cudaStream_t st) {
+  if (MODE == MODE_CE) return fs_launch_k<MODE_CE, 1>(pl, me, p, st);
+  if (p.k <= 10) return fs_launch_k<MODE_TOPK, 10>(pl, me, p, st);
+  if (p.k <= 16) return fs_launch_k<MODE_TOPK, 16>(pl, me, p, st);
+  if (p.k <= 20) return fs_launch_k<MODE_TOPK, 20>(pl, me, p, st);
+  return fs_launch_k<MODE_TOPK, 32>(pl, me, p, st);
 }
 
 }  // namespace bdlru
@@ -523,10 +548,10 @@ extern "C" BDLRU_API int bdlru_fullsort_topk(const void* Q, const void* E, int64
   const size_t need = (size_t)n_users * pl.splits * k * 8;
   BDLRU_REQUIRE(workspace && workspace_bytes >= need, "fullsort_topk: workspace %zu < %zu bytes", workspace_bytes, need);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  CUtensorMap mq, me;
-  if ((rc = make_map(&mq, Q, n_users, D))) return rc;
-  if ((rc = make_map(&me, E, n_rows, D))) return rc;
+  CUtensorMap me;
+  if ((rc = make_map(&me, E, n_rows, D, pl.NT))) return rc;
   FsParams p = {};
+  p.Q = Q;
   p.D = D; p.k = k; p.stages = pl.stages; p.splits = pl.splits; p.n_ug = pl.n_ug;
   p.dbg = fs_debug();
   p.n_users = n_users; p.n_rows = n_rows; p.id_offset = id_offset;
@@ -534,7 +559,7 @@ extern "C" BDLRU_API int bdlru_fullsort_topk(const void* Q, const void* E, int64
   p.tiles_total = pl.tiles_total;
   p.part_scores = reinterpret_cast<float*>(workspace);
   p.part_ids = reinterpret_cast<int*>(p.part_scores + (size_t)n_users * pl.splits * k);
-  if ((rc = fs_launch<MODE_TOPK>(pl, mq, me, p, st))) return rc;
+  if ((rc = fs_launch<MODE_TOPK>(pl, me, p, st))) return rc;
   const int n_cand = pl.splits * k;
   const size_t msmem = (size_t)4 * n_cand * 8;
   BDLRU_REQUIRE(msmem <= 200 * 1024, "fullsort_topk: merge of %d candidates per user does not fit", n_cand);
@@ -577,10 +602,11 @@ extern "C" BDLRU_API int bdlru_fullsort_ce_fwd(const void* Q, const void* E, con
   const size_t need = (size_t)n_users * pl.splits * 8;
   BDLRU_REQUIRE(workspace && workspace_bytes >= need, "fullsort_ce_fwd: workspace %zu < %zu bytes", workspace_bytes, need);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  CUtensorMap mq, me;
-  if ((rc = make_map(&mq, Q, n_users, D))) return rc;
-  if ((rc = make_map(&me, E, n_rows, D))) return rc;
+  CUtensorMap me;
+  if ((rc = make_map(&me, E, n_rows, D, pl.NT))) return rc;
   FsParams p = {};
+  p.Q = Q;
+  p.dbg = fs_debug();
   p.D = D; p.k = 1; p.stages = pl.stages; p.splits = pl.splits; p.n_ug = pl.n_ug;
   p.n_users = n_users; p.n_rows = n_rows; p.id_offset = id_offset; p.mask_local = -1;
   p.tiles_total = pl.tiles_total;
@@ -588,7 +614,7 @@ extern "C" BDLRU_API int bdlru_fullsort_ce_fwd(const void* Q, const void* E, con
   p.part_sum = p.part_max + (size_t)n_users * pl.splits;
   p.pos = pos;
   p.pos_logit = pos_logit;
-  if ((rc = fs_launch<MODE_CE>(pl, mq, me, p, st))) return rc;
+  if ((rc = fs_launch<MODE_CE>(pl, me, p, st))) return rc;
   ce_merge_kernel<<<(unsigned)((n_users + 255) / 256), 256, 0, st>>>(p.part_max, p.part_sum, n_users, pl.splits,
                                                                      row_max, row_sumexp);
   BDLRU_LAUNCHED();
