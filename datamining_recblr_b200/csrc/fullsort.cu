@@ -466,6 +466,13 @@ static int make_map(CUtensorMap* m, const void* base, long rows, int D, int box_
     set_error("cuTensorMapEncodeTiled entry point not available");
     return BDLRU_ERR_CUDA;
   }
+  // The driver entry point needs the primary context bound on THIS thread; PyTorch's autograd threads only bind it
+  // lazily through runtime calls (CUDA_ERROR_INVALID_CONTEXT otherwise).  cudaFree(nullptr) binds it and is a no-op.
+  static thread_local bool bound = false;
+  if (!bound) {
+    cudaFree(nullptr);
+    bound = true;
+  }
   cuuint64_t dims[2] = {(cuuint64_t)D, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)D * 2};
   cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
@@ -584,10 +591,14 @@ extern "C" BDLRU_API int bdlru_topk_merge(const float* cand_scores, const int32_
   return BDLRU_OK;
 }
 
+namespace bdlru { size_t ce_bwd_workspace_bytes(long n_users, long n_rows, int D); }
+
 extern "C" BDLRU_API size_t bdlru_fullsort_ce_workspace_bytes(int64_t n_users, int64_t n_rows, int D) {
   FsPlan pl;
   if (D % 64 != 0 || D < 64 || D > 256 || !fs_plan(n_users, n_rows, D, 1, &pl)) return 0;
-  return (size_t)n_users * pl.splits * 8;
+  const size_t fwd = (size_t)n_users * pl.splits * 8;
+  const size_t bwd = ce_bwd_workspace_bytes(n_users, n_rows, D);
+  return fwd > bwd ? fwd : bwd;
 }
 
 extern "C" BDLRU_API int bdlru_fullsort_ce_fwd(const void* Q, const void* E, const int64_t* pos, int64_t n_users,
@@ -619,10 +630,4 @@ extern "C" BDLRU_API int bdlru_fullsort_ce_fwd(const void* Q, const void* E, con
                                                                      row_max, row_sumexp);
   BDLRU_LAUNCHED();
   return BDLRU_OK;
-}
-
-extern "C" BDLRU_API int bdlru_fullsort_ce_bwd(const void*, const void*, const int64_t*, const float*, float, int64_t,
-                                               int64_t, int, int64_t, float*, float*, void*, size_t, void*) {
-  set_error("bdlru_fullsort_ce_bwd: tcgen05 kernel not built into this library yet");
-  return BDLRU_ERR_UNSUPPORTED;
 }

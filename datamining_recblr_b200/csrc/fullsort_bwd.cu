@@ -1,0 +1,461 @@
+// Backward of the full-softmax cross-entropy over all item rows (RecBLR.py:99-103, what autograd does through
+// nn.CrossEntropyLoss + the logits GEMM) WITHOUT materialising the [users, items] logits or probabilities.
+//
+//   P = exp(Q E^T - lse) - onehot(pos),   dQ = scale * P E,   dE = scale * P^T Q.
+//
+// One kernel template serves both gradients:  "X rows against a stream of Y tiles"
+//   dX[128 rows, D] = sum over Y tiles  P_tile[128, NT] * Y_tile[NT, D],   P_tile from S = X Y_tile^T.
+//   dQ: X = Q (rows = users), Y = E (cols = items), softmax statistics per ROW   (TRANSPOSED = false)
+//   dE: X = E (rows = items), Y = Q (cols = users), softmax statistics per COLUMN (TRANSPOSED = true)
+// so each gradient recomputes the logits once on the tensor cores (4 GEMM passes in total instead of the 3 of a
+// materialising implementation; no atomics, deterministic).
+//
+// Per CTA (192 threads): warp 0 streams Y tiles by TMA (128-byte-swizzled slabs), warp 1 issues tcgen05.mma, warps 2-5
+// are the softmax warps (thread == row, TMEM lane quarter == warp % 4).  TMEM columns:
+//   X  (A of GEMM1, packed bf16 pairs, written once per row block with tcgen05.st)        D/2
+//   dX (fp32 accumulator of GEMM2, lives across the whole column loop)                   D
+//   S  x NSTG (GEMM1 accumulator, [128, NT] fp32)                                          NSTG * NT
+//   P  x NSTG (A of GEMM2, packed bf16 pairs written by the softmax warps)                 NSTG * NT/2
+// GEMM1: S = X Y^T       M=128, N=NT, K=D : A from TMEM, B = Y slab as K-major (channels contiguous).
+// GEMM2: dX += P Y       M=128, N=D, K=NT : A from TMEM, B = THE SAME shared-memory bytes described as MN-major
+//                                            (N = channels contiguous inside a swizzled 128-byte row, K = tile rows).
+// The MMA warp runs GEMM1 of tile t+1 before GEMM2 of tile t, so the tensor pipe works while the softmax warps turn
+// S(t) into P(t).
+#include <cuda.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "tc05.cuh"
+
+namespace bdlru {
+
+constexpr int kRows = 128;
+constexpr int kBwdMaxStages = 6;
+constexpr int kBwdSmem = 200 * 1024;
+
+struct BwdParams {
+  const void* X;        // [n_x, D] bf16 rows owned by CTAs
+  long n_x, n_y;        // rows of X, rows of Y (columns of S)
+  int D, stages, splits;
+  long row_blocks, tiles_total;
+  const float* lse;     // [n_users]
+  const int64_t* pos;   // [n_users] global item ids
+  long n_users;
+  long id_offset;       // global id of item row 0 of this shard
+  float scale;
+  float* out;           // [splits][n_x][D] fp32 (splits == 1: the final gradient)
+};
+
+template <bool TRANSPOSED, int NT, int NSTG>
+__global__ void __launch_bounds__(192, 1)
+ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const BwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_slab = p.D >> 6;
+  constexpr uint32_t kSlabB = NT * 128;
+  constexpr int NCH = NT / 32;
+  uint8_t* sY = smem;
+  float* col_lse = reinterpret_cast<float*>(sY + (size_t)p.stages * n_slab * kSlabB);  // [4 warps][NT]
+  int* col_pos = reinterpret_cast<int*>(col_lse + 4 * NT);                              // [4 warps][NT]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(col_pos + 4 * NT);
+  uint64_t* y_full = bars;
+  uint64_t* y_empty = y_full + kBwdMaxStages;
+  uint64_t* s_full = y_empty + kBwdMaxStages;
+  uint64_t* s_empty = s_full + NSTG;
+  uint64_t* p_full = s_empty + NSTG;
+  uint64_t* p_empty = p_full + NSTG;
+  uint64_t* x_full = p_empty + NSTG;
+  uint64_t* dx_full = x_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dx_full + 1);
+
+  const uint32_t x_cols = (uint32_t)(p.D >> 1);
+  const uint32_t dx_col = x_cols;
+  const uint32_t s_col = dx_col + (uint32_t)p.D;
+  const uint32_t p_col = s_col + NSTG * NT;
+
+  if (warp == 0 && lane == 0) {
+    tc::prefetch_tensormap(&tmY);
+    for (int s = 0; s < p.stages; ++s) {
+      tc::mbar_init(&y_full[s], 1);
+      tc::mbar_init(&y_empty[s], 1);
+    }
+    for (int b = 0; b < NSTG; ++b) {
+      tc::mbar_init(&s_full[b], 1);
+      tc::mbar_init(&s_empty[b], 4);
+      tc::mbar_init(&p_full[b], 4);
+      tc::mbar_init(&p_empty[b], 1);
+    }
+    tc::mbar_init(x_full, 4);
+    tc::mbar_init(dx_full, 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) {
+    tc::tmem_alloc(tmem_slot, 512);
+    tc::tmem_relinquish();
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const long n_work = p.row_blocks * p.splits;
+  // every role walks the same (work item, tile) sequence; g counts tiles globally for ring / stage parities
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    long g = 0;
+    for (long w = blockIdx.x; w < n_work; w += gridDim.x) {
+      const int split = (int)(w / p.row_blocks);
+      const long t0 = p.tiles_total * split / p.splits, t1 = p.tiles_total * (split + 1) / p.splits;
+      for (long t = t0; t < t1; ++t, ++g) {
+        const int s = (int)(g % p.stages);
+        const uint32_t ph = (uint32_t)(g / p.stages) & 1u;
+        tc::mbar_wait(&y_empty[s], ph ^ 1u);
+        if (tc::elect_one()) {
+          tc::mbar_arrive_expect_tx(&y_full[s], (uint32_t)n_slab * kSlabB);
+          for (int sl = 0; sl < n_slab; ++sl)
+            tc::tma_load_2d(sY + (size_t)(s * n_slab + sl) * kSlabB, &tmY, &y_full[s], sl * 64, (int)(t * NT));
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    constexpr uint32_t idesc1 = tc::idesc_bf16_f32(kRows, NT, 0, 0);
+    const uint32_t idesc2 = tc::idesc_bf16_f32(kRows, p.D, 0, 1);  // B is MN-major in GEMM2
+    long g = 0;
+    uint32_t wi = 0;
+    for (long w = blockIdx.x; w < n_work; w += gridDim.x, ++wi) {
+      const int split = (int)(w / p.row_blocks);
+      const long t0 = p.tiles_total * split / p.splits, t1 = p.tiles_total * (split + 1) / p.splits;
+      const long n_t = t1 - t0;
+      tc::mbar_wait(x_full, wi & 1u);
+      tc::fence_after_sync();
+      auto gemm1 = [&](long gg) {
+        const int s = (int)(gg % p.stages);
+        const uint32_t ph = (uint32_t)(gg / p.stages) & 1u;
+        const int b = (int)(gg % NSTG);
+        const uint32_t bph = (uint32_t)(gg / NSTG) & 1u;
+        tc::mbar_wait(&y_full[s], ph);
+        tc::mbar_wait(&s_empty[b], bph ^ 1u);
+        tc::fence_after_sync();
+        if (tc::elect_one()) {
+          const uint64_t bd0 = tc::smem_desc_sw128(tc::smem_u32(sY + (size_t)s * n_slab * kSlabB), 16, 1024);
+          const uint32_t d_tmem = tmem_base + s_col + (uint32_t)b * NT;
+          for (int sl = 0; sl < n_slab; ++sl) {
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4)
+              tc::umma_bf16_ts(d_tmem, tmem_base + (uint32_t)(sl * 4 + k4) * 8,
+                               bd0 + (uint64_t)((uint32_t)sl * (kSlabB >> 4) + (uint32_t)k4 * 2), idesc1,
+                               (uint32_t)((sl | k4) != 0));
+          }
+          tc::umma_commit(&s_full[b]);
+        }
+        __syncwarp();
+      };
+      if (n_t > 0) gemm1(g);
+      for (long t = 0; t < n_t; ++t, ++g) {
+        if (t + 1 < n_t) gemm1(g + 1);
+        const int s = (int)(g % p.stages);
+        const int b = (int)(g % NSTG);
+        const uint32_t bph = (uint32_t)(g / NSTG) & 1u;
+        tc::mbar_wait(&p_full[b], bph);
+        tc::fence_after_sync();
+        if (tc::elect_one()) {
+          // Y tile as the MN-major B operand: leading (MN) stride = one 64-channel slab, K groups of 8 rows are
+          // 1024 bytes apart; one MMA consumes 16 rows = 2048 bytes
+          const uint64_t bd0 = tc::smem_desc_sw128(tc::smem_u32(sY + (size_t)s * n_slab * kSlabB), kSlabB, 1024);
+          const uint32_t a0 = tmem_base + p_col + (uint32_t)b * (NT / 2);
+#pragma unroll
+          for (int kk = 0; kk < NT / 16; ++kk)
+            tc::umma_bf16_ts(tmem_base + dx_col, a0 + (uint32_t)kk * 8, bd0 + (uint64_t)(kk * (2048 >> 4)), idesc2,
+                             (uint32_t)((t | kk) != 0));
+          tc::umma_commit(&y_empty[s]);
+          tc::umma_commit(&p_empty[b]);
+          if (t + 1 == n_t) tc::umma_commit(dx_full);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===================================================================== softmax warps: thread == row
+    const int q = warp & 3;
+    const int ew = warp - 2;                 // private scratch index
+    const int row = q * 32 + lane;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    float* my_lse = col_lse + ew * NT;
+    int* my_pos = col_pos + ew * NT;
+    constexpr float kLog2e = 1.4426950408889634f;
+    long g = 0;
+    uint32_t wi = 0;
+    for (long w = blockIdx.x; w < n_work; w += gridDim.x, ++wi) {
+      const long rb = w % p.row_blocks;
+      const int split = (int)(w / p.row_blocks);
+      const long t0 = p.tiles_total * split / p.splits, t1 = p.tiles_total * (split + 1) / p.splits;
+      const long xrow = rb * kRows + row;
+      {  // this thread's row of X -> TMEM (packed bf16 pairs, channel 2j in the low half)
+        const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.X) + xrow * p.D);
+        for (int j = 0; j < (p.D >> 4); ++j) {
+          uint4 lo = make_uint4(0, 0, 0, 0), hi = lo;
+          if (xrow < p.n_x) {
+            lo = src[2 * j];
+            hi = src[2 * j + 1];
+          }
+          const uint32_t wv[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+          tc::tmem_st_32x32_x8(lane_addr + (uint32_t)j * 8, wv);
+        }
+        tc::tmem_st_wait();
+        tc::fence_before_sync();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(x_full);
+      }
+      // row statistics (dQ) / row identity (dE)
+      float row_lse2 = 0.f;
+      long row_pos = -1;   // dQ: local column of the positive item;  dE: this row's local item index
+      if (!TRANSPOSED) {
+        if (xrow < p.n_x) {
+          row_lse2 = p.lse[xrow] * kLog2e;
+          row_pos = p.pos[xrow] - p.id_offset;
+        }
+      } else {
+        row_pos = xrow;
+      }
+      for (long t = t0; t < t1; ++t, ++g) {
+        const int b = (int)(g % NSTG);
+        const uint32_t bph = (uint32_t)(g / NSTG) & 1u;
+        const long cbase = t * NT;
+        if (TRANSPOSED) {  // column statistics of this tile -> per-warp scratch (lse*log2e, local positive row)
+          __syncwarp();
+          for (int i = lane; i < NT; i += 32) {
+            const long u = cbase + i;
+            const bool ok = u < p.n_users;
+            my_lse[i] = ok ? p.lse[u] * kLog2e : INFINITY;
+            my_pos[i] = ok ? (int)(p.pos[u] - p.id_offset) : -1;
+          }
+          __syncwarp();
+        }
+        tc::mbar_wait(&s_full[b], bph);
+        tc::fence_after_sync();
+        uint32_t raw[NCH][32];
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) tc::tmem_ld_32x32(lane_addr + s_col + (uint32_t)b * NT + c * 32, raw[c]);
+        tc::tmem_ld_wait();
+        tc::fence_before_sync();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&s_empty[b]);
+        uint32_t packed[NT / 2];
+        const bool special = !TRANSPOSED && ((cbase + NT > p.n_y) || (row_pos >= cbase && row_pos < cbase + NT));
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            float pr[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const int col = c * 32 + i + u;
+              const float sv = __uint_as_float(raw[c][i + u]);
+              if (TRANSPOSED) {
+                pr[u] = ex2_ftz(fmaf(sv, kLog2e, -my_lse[col])) - (my_pos[col] == (int)row_pos ? 1.f : 0.f);
+              } else {
+                pr[u] = ex2_ftz(fmaf(sv, kLog2e, -row_lse2));
+                if (special) {
+                  if (cbase + col == row_pos) pr[u] -= 1.f;
+                  if (cbase + col >= p.n_y) pr[u] = 0.f;
+                }
+              }
+            }
+            const __nv_bfloat162 h = __floats2bfloat162_rn(pr[0], pr[1]);
+            packed[(c * 32 + i) >> 1] = *reinterpret_cast<const uint32_t*>(&h);
+          }
+        }
+        tc::mbar_wait(&p_empty[b], bph ^ 1u);   // GEMM2 of the tile that used this P stage has completed
+        tc::fence_after_sync();
+#pragma unroll
+        for (int j = 0; j < NT / 16; ++j) {
+          const uint32_t wv[8] = {packed[8 * j], packed[8 * j + 1], packed[8 * j + 2], packed[8 * j + 3],
+                                  packed[8 * j + 4], packed[8 * j + 5], packed[8 * j + 6], packed[8 * j + 7]};
+          tc::tmem_st_32x32_x8(lane_addr + p_col + (uint32_t)b * (NT / 2) + (uint32_t)j * 8, wv);
+        }
+        tc::tmem_st_wait();
+        tc::fence_before_sync();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&p_full[b]);
+      }
+      // row block finished: dX accumulator -> global (scaled)
+      tc::mbar_wait(dx_full, wi & 1u);
+      tc::fence_after_sync();
+      float* orow = p.out + ((size_t)split * p.n_x + xrow) * p.D;
+      for (int c = 0; c < (p.D >> 5); ++c) {
+        uint32_t acc[32];
+        tc::tmem_ld_32x32(lane_addr + dx_col + (uint32_t)c * 32, acc);
+        tc::tmem_ld_wait();
+        if (xrow < p.n_x) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 4)
+            *reinterpret_cast<float4*>(orow + c * 32 + i) =
+                make_float4(__uint_as_float(acc[i]) * p.scale, __uint_as_float(acc[i + 1]) * p.scale,
+                            __uint_as_float(acc[i + 2]) * p.scale, __uint_as_float(acc[i + 3]) * p.scale);
+        }
+      }
+      tc::fence_before_sync();
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    tc::fence_after_sync();
+    tc::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// out[r][d] = sum_s part[s][r][d]
+__global__ void sum_partials_kernel(const float4* __restrict__ part, long n4, int splits, float4* __restrict__ out) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  float4 a = part[i];
+  for (int s = 1; s < splits; ++s) {
+    const float4 b = part[(size_t)s * n4 + i];
+    a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+  }
+  out[i] = a;
+}
+
+// ----------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int bwd_make_map(CUtensorMap* m, const void* base, long rows, int D, int box_rows) {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess || !ptr) {
+      cudaGetLastError();
+      set_error("cuTensorMapEncodeTiled entry point not available");
+      return BDLRU_ERR_CUDA;
+    }
+    fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  // The driver entry point needs the primary context bound on THIS thread; PyTorch's autograd threads only bind it
+  // lazily through runtime calls (CUDA_ERROR_INVALID_CONTEXT otherwise).  cudaFree(nullptr) binds it and is a no-op.
+  static thread_local bool bound = false;
+  if (!bound) {
+    cudaFree(nullptr);
+    bound = true;
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)D, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)D * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%ld D=%d)", (int)r, rows, D);
+    return BDLRU_ERR_CUDA;
+  }
+  return BDLRU_OK;
+}
+
+struct BwdPlan {
+  int NT, NSTG, stages, splits, grid;
+  long row_blocks, tiles;
+  size_t smem;
+};
+
+static void bwd_plan(long n_x, long n_y, int D, BwdPlan* pl) {
+  pl->NT = D <= 128 ? 96 : 64;
+  pl->NSTG = D <= 192 ? 2 : 1;
+  pl->row_blocks = (n_x + kRows - 1) / kRows;
+  pl->tiles = (n_y + pl->NT - 1) / pl->NT;
+  const size_t stage = (size_t)(D / 64) * pl->NT * 128;
+  int stages = (int)(((size_t)kBwdSmem - 1024 - 8 * pl->NT * 4 - 512) / stage);
+  pl->stages = stages > kBwdMaxStages ? kBwdMaxStages : stages;
+  long splits = (long)sm_count() / pl->row_blocks;
+  if (splits < 1) splits = 1;
+  const long max_s = pl->tiles / 4 > 0 ? pl->tiles / 4 : 1;
+  if (splits > max_s) splits = max_s;
+  pl->splits = (int)splits;
+  const long n_work = pl->row_blocks * splits;
+  pl->grid = (int)(n_work < sm_count() ? n_work : sm_count());
+  pl->smem = 1024 + (size_t)pl->stages * stage + 8 * pl->NT * 4 + 512;
+}
+
+template <bool TR>
+static int bwd_launch(const BwdPlan& pl, const CUtensorMap& my, const BwdParams& p, cudaStream_t st) {
+#define BWD_CASE(NTv, NSv)                                                                                      \
+  if (pl.NT == NTv && pl.NSTG == NSv) {                                                                         \
+    BDLRU_CUDA(cudaFuncSetAttribute(ce_bwd_kernel<TR, NTv, NSv>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                    (int)pl.smem));                                                             \
+    ce_bwd_kernel<TR, NTv, NSv><<<pl.grid, 192, pl.smem, st>>>(my, p);                                          \
+    BDLRU_LAUNCHED();                                                                                           \
+    return BDLRU_OK;                                                                                            \
+  }
+  BWD_CASE(96, 2) BWD_CASE(64, 2) BWD_CASE(64, 1)
+#undef BWD_CASE
+  set_error("fullsort_ce_bwd: no kernel for NT=%d NSTG=%d", pl.NT, pl.NSTG);
+  return BDLRU_ERR_UNSUPPORTED;
+}
+
+// one gradient: X rows against Y columns; result (scaled) in `grad` [n_x, D]
+template <bool TR>
+static int bwd_one(const void* X, long n_x, const void* Y, long n_y, int D, const float* lse, const int64_t* pos,
+                   long n_users, long id_offset, float scale, float* grad, float* scratch, cudaStream_t st) {
+  BwdPlan pl;
+  bwd_plan(n_x, n_y, D, &pl);
+  CUtensorMap my;
+  int rc = bwd_make_map(&my, Y, n_y, D, pl.NT);
+  if (rc) return rc;
+  BwdParams p = {};
+  p.X = X; p.n_x = n_x; p.n_y = n_y; p.D = D; p.stages = pl.stages; p.splits = pl.splits;
+  p.row_blocks = pl.row_blocks; p.tiles_total = pl.tiles;
+  p.lse = lse; p.pos = pos; p.n_users = n_users; p.id_offset = id_offset; p.scale = scale;
+  p.out = pl.splits > 1 ? scratch : grad;
+  if ((rc = bwd_launch<TR>(pl, my, p, st))) return rc;
+  if (pl.splits > 1) {
+    const long n4 = n_x * D / 4;
+    sum_partials_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float4*>(scratch), n4,
+                                                                      pl.splits, reinterpret_cast<float4*>(grad));
+    BDLRU_LAUNCHED();
+  }
+  return BDLRU_OK;
+}
+
+size_t ce_bwd_workspace_bytes(long n_users, long n_rows, int D) {
+  BwdPlan a, b;
+  bwd_plan(n_users, n_rows, D, &a);
+  bwd_plan(n_rows, n_users, D, &b);
+  const size_t wa = a.splits > 1 ? (size_t)a.splits * n_users * D * 4 : 0;
+  const size_t wb = b.splits > 1 ? (size_t)b.splits * n_rows * D * 4 : 0;
+  return wa > wb ? wa : wb;
+}
+
+}  // namespace bdlru
+
+using namespace bdlru;
+
+extern "C" BDLRU_API int bdlru_fullsort_ce_bwd(const void* Q, const void* E, const int64_t* pos, const float* lse,
+                                               float scale, int64_t n_users, int64_t n_rows, int D, int64_t id_offset,
+                                               float* dQ, float* dE, void* workspace, size_t workspace_bytes,
+                                               void* stream) {
+  BDLRU_REQUIRE(Q && E && pos && lse, "fullsort_ce_bwd: null input");
+  BDLRU_REQUIRE(dQ || dE, "fullsort_ce_bwd: both gradients null");
+  BDLRU_REQUIRE(n_users >= 1 && n_rows >= 1, "fullsort_ce_bwd: bad sizes n_users=%ld n_rows=%ld", (long)n_users, (long)n_rows);
+  BDLRU_REQUIRE(D % 64 == 0 && D >= 64 && D <= 256, "fullsort_ce_bwd: D=%d must be a multiple of 64 in [64, 256]", D);
+  BDLRU_REQUIRE(aligned(Q, 16) && aligned(E, 16) && aligned(dQ, 16) && aligned(dE, 16),
+                "fullsort_ce_bwd: Q/E/dQ/dE must be 16-byte aligned");
+  const size_t need = ce_bwd_workspace_bytes(n_users, n_rows, D);
+  BDLRU_REQUIRE(need == 0 || (workspace && workspace_bytes >= need), "fullsort_ce_bwd: workspace %zu < %zu bytes",
+                workspace_bytes, need);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int rc;
+  if (dQ && (rc = bwd_one<false>(Q, n_users, E, n_rows, D, lse, pos, n_users, id_offset, scale, dQ,
+                                 reinterpret_cast<float*>(workspace), st)))
+    return rc;
+  if (dE && (rc = bwd_one<true>(E, n_rows, Q, n_users, D, lse, pos, n_users, id_offset, scale, dE,
+                                reinterpret_cast<float*>(workspace), st)))
+    return rc;
+  return BDLRU_OK;
+}

@@ -87,7 +87,7 @@ class RecBLR(SequentialRecommender):
         if self.bd_lru_only:  # RecBLR.py:33-35
             self.disable_conv1d = True
             self.disable_ffn = True
-        self.ce_impl = _cfg(config, "ce_impl", "dense")
+        self.ce_impl = _cfg(config, "ce_impl", "fused")
         self.fused_front = bool(_cfg(config, "fused_front", True))
 
         self.item_embedding = nn.Embedding(self.n_items, self.hidden_size, padding_idx=0)
