@@ -17,7 +17,7 @@ import torch
 def run_score(args):
     import torch.distributed as dist
     from bench import SCORE_WORKLOADS, ClockSampler, cpu_score_baseline, dist_env, peaks
-    from datamining_recblr_b200 import _lib, ops
+    from datamining_recblr_b200 import _lib, ops, sharded
     from datamining_recblr_b200.timing import flush_l2
 
     rank, world, local = dist_env()
@@ -38,14 +38,7 @@ def run_score(args):
     out_h = (torch.empty(B, k, dtype=torch.float32).pin_memory(), torch.empty(B, k, dtype=torch.int32).pin_memory())
 
     def step(q):
-        s, i = ops.fullsort_topk(q, E, k, mask_id=0, id_offset=lo)
-        if world > 1:
-            cs = torch.empty(world, B, k, dtype=torch.float32, device=dev)
-            ci = torch.empty(world, B, k, dtype=torch.int32, device=dev)
-            dist.all_gather_into_tensor(cs, s)
-            dist.all_gather_into_tensor(ci, i)
-            s, i = ops.topk_merge(cs.permute(1, 0, 2).reshape(B, world * k), ci.permute(1, 0, 2).reshape(B, world * k), k)
-        return s, i
+        return sharded.sharded_topk(q, E, k, id_offset=lo, mask_id=0)
 
     for it in range(max(args.warmup, 3)):
         step(Qd[it % n_q])

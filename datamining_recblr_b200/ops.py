@@ -307,6 +307,22 @@ def fullsort_ce_stats(q, table, pos, id_offset=0):
     return row_max, row_sum, pos_logit
 
 
+def fullsort_ce_grads(qb, eb, pos, lse, scale, id_offset=0):
+    """(dQ [B, D], dE [rows, D]) fp32 of scale * sum_b(lse_b - logit_{b,pos_b}) for bf16 qb, eb and the GLOBAL lse;
+    the logits are recomputed tile by tile on the tensor cores and never stored."""
+    L.require_cuda(qb, eb, pos, lse)
+    B, D = qb.shape
+    N = eb.shape[0]
+    lib = L.load()
+    dQ = torch.empty((B, D), dtype=torch.float32, device=qb.device)
+    dE = torch.empty((N, D), dtype=torch.float32, device=qb.device)
+    nws = lib.bdlru_fullsort_ce_workspace_bytes(B, N, D)
+    ws = _workspace(qb.device, nws)
+    L.check(lib.bdlru_fullsort_ce_bwd(L.ptr(qb), L.ptr(eb), L.ptr(pos), L.ptr(lse.float().contiguous()), float(scale), B,
+                                      N, D, id_offset, L.ptr(dQ), L.ptr(dE), L.ptr(ws), nws, L.stream_ptr(qb)))
+    return dQ, dE
+
+
 class _FullsortCE(torch.autograd.Function):
     """mean_b(logsumexp_n(q_b . E_n) - q_b . E_pos_b) over ALL rows of E (RecBLR.py:99-103), logits never stored."""
 
@@ -322,16 +338,8 @@ class _FullsortCE(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_loss):
         qb, eb, pos, lse = ctx.saved_tensors
-        B, D = qb.shape
-        N = eb.shape[0]
-        lib = L.load()
-        dQ = torch.empty((B, D), dtype=torch.float32, device=qb.device)
-        dE = torch.empty((N, D), dtype=torch.float32, device=qb.device)
-        nws = lib.bdlru_fullsort_ce_workspace_bytes(B, N, D)
-        ws = _workspace(qb.device, nws)
         # dloss/dlogit = (softmax - onehot) / B, times the upstream scalar (kept on the device: no sync)
-        L.check(lib.bdlru_fullsort_ce_bwd(L.ptr(qb), L.ptr(eb), L.ptr(pos), L.ptr(lse), 1.0 / B, B, N, D, 0, L.ptr(dQ),
-                                          L.ptr(dE), L.ptr(ws), nws, L.stream_ptr(qb)))
+        dQ, dE = fullsort_ce_grads(qb, eb, pos, lse, 1.0 / qb.shape[0])
         g = grad_loss.float()
         return (dQ * g).to(ctx.dtypes[0]), (dE * g).to(ctx.dtypes[1]), None
 

@@ -1,0 +1,83 @@
+"""Multi-GPU forms of the full-sort scoring and full-softmax CE: the item table is ROW-SHARDED over the ranks of a
+`torch.distributed` process group (rank g owns global item ids [bounds[g], bounds[g+1]); the pad row 0 lives on rank 0).
+New functionality — the reference is single-GPU — whose oracle is the single-table result.
+
+Only small tensors cross NVLink: queries are replicated by the caller (data parallel eval gathers them first),
+per-shard top-k lists [B, k] are all-gathered and merged by (score desc, id asc); CE statistics are combined with one
+MAX and two SUM all-reduces of [B] vectors; dE stays shard-local, dQ partials are all-reduced.
+
+The per-shard arithmetic runs in the CUDA kernels (`ops`); the exchange logic below is backend-agnostic so that the
+world_size-2 `gloo` tests can drive it on CPU with the oracle standing in for the kernels (`local_*` hooks).
+"""
+import torch
+import torch.distributed as dist
+
+from . import ops
+
+
+def shard_bounds(n_items, world):
+    """Row ranges of the item table: rank g owns [b[g], b[g+1])."""
+    return [n_items * g // world for g in range(world + 1)]
+
+
+def _world(group):
+    return dist.get_world_size(group) if dist.is_initialized() else 1
+
+
+def sharded_topk(q, table_shard, k, id_offset, mask_id=0, group=None, local_topk=None, local_merge=None):
+    """Top-k of q @ table^T over the whole (sharded) table.  q [B, D] must be identical on every rank.
+    Returns (scores [B, k] fp32, ids [B, k] int32), identical on every rank and to the single-table result."""
+    local_topk = local_topk or ops.fullsort_topk
+    local_merge = local_merge or ops.topk_merge
+    s, i = local_topk(q, table_shard, k, mask_id=mask_id, id_offset=id_offset)
+    world = _world(group)
+    if world == 1:
+        return s, i
+    B = q.shape[0]
+    cs = torch.empty((world * B, k), dtype=torch.float32, device=s.device)   # rank-major concatenation
+    ci = torch.empty((world * B, k), dtype=torch.int32, device=s.device)
+    dist.all_gather_into_tensor(cs, s.contiguous(), group=group)
+    dist.all_gather_into_tensor(ci, i.contiguous(), group=group)
+    cs = cs.view(world, B, k).permute(1, 0, 2).reshape(B, world * k).contiguous()
+    ci = ci.view(world, B, k).permute(1, 0, 2).reshape(B, world * k).contiguous()
+    return local_merge(cs, ci, k)
+
+
+def combine_ce_stats(row_max, row_sum, pos_logit, group=None):
+    """Global logsumexp and positive logit from per-shard (max, sum exp(. - max), pos_logit-or-0):
+        m = max_g m_g;  s = sum_g s_g * exp(m_g - m);  lse = m + log s;  pos = sum_g pos_g."""
+    if _world(group) == 1:
+        return row_max + torch.log(row_sum), pos_logit
+    m = row_max.clone()
+    dist.all_reduce(m, op=dist.ReduceOp.MAX, group=group)
+    s = row_sum * torch.exp(row_max - m)
+    packed = torch.stack([s, pos_logit])
+    dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
+    return m + torch.log(packed[0]), packed[1]
+
+
+class _ShardedCE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q, table_shard, pos, id_offset, group):
+        qb, eb = ops._bf16_rows(q), ops._bf16_rows(table_shard)
+        m, s, pl = ops.fullsort_ce_stats(qb, eb, pos, id_offset=id_offset)
+        lse, pl = combine_ce_stats(m, s, pl, group)
+        ctx.save_for_backward(qb, eb, pos, lse)
+        ctx.meta = (id_offset, group, q.dtype, table_shard.dtype)
+        return (lse - pl).mean()
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        qb, eb, pos, lse = ctx.saved_tensors
+        id_offset, group, qd, ed = ctx.meta
+        dQ, dE = ops.fullsort_ce_grads(qb, eb, pos, lse, 1.0 / qb.shape[0], id_offset=id_offset)
+        if _world(group) > 1:  # every shard contributes P_shard E_shard to dQ; dE is shard-local
+            dist.all_reduce(dQ, op=dist.ReduceOp.SUM, group=group)
+        g = grad_loss.float()
+        return (dQ * g).to(qd), (dE * g).to(ed), None, None, None
+
+
+def sharded_cross_entropy(q, table_shard, pos, id_offset, group=None):
+    """Mean full-softmax CE over the whole sharded table; q [B, D] and pos [B] (GLOBAL ids) identical on every rank.
+    Gradients: dq is the full gradient on every rank, dtable_shard is this rank's rows."""
+    return _ShardedCE.apply(q, table_shard, pos.contiguous(), int(id_offset), group)

@@ -134,3 +134,17 @@ def test_fused_ce_forward_backward_match_oracle(B, N, D):
     assert np.abs(gq - dQ).max() <= 1e-2 * np.abs(dQ).max()
     assert np.abs(ge - dE).max() <= 1e-2 * np.abs(dE).max()
     assert np.abs(ge[0]).max() > 0   # the pad row receives gradient as a never/rarely-positive class (quirk 2)
+
+
+def test_sharded_paths_on_two_gpus():
+    """Launches tests/dist_check.py on 2 GPUs of this node (NCCL); skipped on a 1-GPU box."""
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29631", os.path.join(root, "tests", "dist_check.py")],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "dist_check ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
