@@ -224,7 +224,7 @@ def run_train(args):
     B, L, D = w["B"], w["L"], w["D"]
     torch.manual_seed(2020)
     model = RecBLR(make_config(w, dev), _DS(w["n_items"])).to(dev)
-    opt = torch.optim.Adam(model.parameters(), lr=1e-3, fused=True)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, fused=True, capturable=True)
     params = [p for p in model.parameters()]
     amp = args.dtype == "bf16"
 
@@ -234,21 +234,43 @@ def run_train(args):
     host = [tuple(t.pin_memory() for t in b) for b in host]
     devb = [tuple(t.to(dev) for t in b) for b in host]
 
-    def step(batch):
+    def allreduce_grads(ps):  # data-parallel gradient all-reduce (mean), one flat NCCL call
+        flat = torch.cat([p.grad.reshape(-1) for p in ps])
+        dist.all_reduce(flat, op=dist.ReduceOp.AVG)
+        off = 0
+        for p in ps:
+            p.grad.copy_(flat[off:off + p.numel()].view_as(p))
+            off += p.numel()
+
+    def eager_step(batch):
         inter = {"item_id_list": batch[0], "item_length": batch[1], "item_id": batch[2]}
         opt.zero_grad(set_to_none=True)
         with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
             loss = model.calculate_loss(inter)
         loss.backward()
-        if world > 1:  # data-parallel gradient all-reduce (mean), one flat NCCL call
-            flat = torch.cat([p.grad.reshape(-1) for p in params])
-            dist.all_reduce(flat, op=dist.ReduceOp.AVG)
-            off = 0
-            for p in params:
-                p.grad.copy_(flat[off:off + p.numel()].view_as(p))
-                off += p.numel()
+        if world > 1:
+            allreduce_grads(params)
         opt.step()
-        return loss
+        return loss.detach()
+
+    model.train()
+    graphed = None
+    if not args.no_graph:
+        from datamining_recblr_b200.train_step import GraphedTrainStep
+        ex = {"item_id_list": devb[0][0], "item_length": devb[0][1], "item_id": devb[0][2]}
+        graphed = GraphedTrainStep(model, opt, ex, autocast_dtype=torch.bfloat16 if amp else None,
+                                   grad_hook=allreduce_grads if world > 1 else None)
+
+    graphed_launches = 0
+    if graphed is not None:  # launches of libbdlru kernels in one step (same code path as the captured graph)
+        c0 = _lib.launch_count()
+        eager_step(devb[0])
+        graphed_launches = _lib.launch_count() - c0
+
+    def step(batch):
+        if graphed is None:
+            return eager_step(batch)
+        return graphed({"item_id_list": batch[0], "item_length": batch[1], "item_id": batch[2]})
 
     model.train()
     for i in range(max(args.warmup, 3)):
@@ -264,8 +286,23 @@ def run_train(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    # per-kernel launch durations: event pairs around the C-ABI calls.  Events cannot be recorded inside a graph
+    # replay, so with the graphed step they are taken from eager steps of the same work right before the timed region.
+    ktimes = None
+    if graphed is not None:
+        _lib.kernel_timer(timed)
+        for i in range(3):
+            flush_l2(dev)
+            eager_step(devb[i % n_batches])
+        ktimes = _lib.kernel_timer_stop()
+        eager_steps = 3
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
     n0 = _lib.launch_count()
-    _lib.kernel_timer(timed)
+    if graphed is None:
+        _lib.kernel_timer(timed)
+        eager_steps = args.steps
     evs = []
     for i in range(args.steps):
         flush_l2(dev)
@@ -275,8 +312,11 @@ def run_train(args):
         e.record()
         evs.append((s, e))
     torch.cuda.synchronize()
-    ktimes = _lib.kernel_timer_stop()
+    if graphed is None:
+        ktimes = _lib.kernel_timer_stop()
     launches = _lib.launch_count() - n0
+    if graphed is not None:  # replays do not pass through the host launch counter: count what the graph contains
+        launches = graphed_launches * args.steps
     if world > 1:
         dist.barrier()
     total_ms = sum(s.elapsed_time(e) for s, e in evs)
@@ -295,7 +335,7 @@ def run_train(args):
     for i in range(args.steps):
         hb = host[i % n_batches]
         db = tuple(t.to(dev, non_blocking=True) for t in hb)
-        float(step(db))
+        step(db).item()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     te = torch.tensor([e2e_s], device=dev)
@@ -355,8 +395,8 @@ def run_train(args):
     per_kernel = {}
     for name, ts in ktimes.items():
         if ts:
-            per_kernel[name] = dict(calls_per_step=len(ts) / args.steps, avg_ms=sum(ts) / len(ts),
-                                    share_of_step=sum(ts) / total_ms if world == 1 else None,
+            per_kernel[name] = dict(calls_per_step=len(ts) / eager_steps, avg_ms=sum(ts) / len(ts),
+                                    share_of_step=(sum(ts) / eager_steps) / ms_per_step if world == 1 else None,
                                     gbs=(alg[name] / (sum(ts) / len(ts)) / 1e6) if name in alg else None)
     dom = max((n for n in per_kernel if n in alg), key=lambda n: per_kernel[n]["avg_ms"] * per_kernel[n]["calls_per_step"])
     roofline = dict(bound="hbm", kernel=dom, achieved=per_kernel[dom]["gbs"], peak=P["hbm"], unit="GB/s",
@@ -374,7 +414,8 @@ def run_train(args):
                                      f"(CE over all items) + backward + Adam",
                             l2="flushed between steps (256 MB write); per-step working set < L2",
                             parallelism=f"dp{world}" if world > 1 else "single",
-                            ce_impl=model.ce_impl, scan_state="fp32"),
+                            ce_impl=model.ce_impl, scan_state="fp32",
+                            launch="CUDA graph replay of the whole step" if graphed is not None else "eager"),
                 e2e=dict(value=world * B * L * args.steps / e2e_s, unit="seq-tokens/s", h2d_bytes_per_step=h2d,
                          d2h_bytes_per_step=4, ms_per_step=e2e_s / args.steps * 1e3),
                 gpu_launches=launches, clocks=clocks, roofline=roofline, kernels=per_kernel, fullsort=fullsort,
@@ -394,6 +435,7 @@ def main():
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
     ap.add_argument("--cpu-sample", type=int, default=0, help="sequences (train) / users (scoring) per CPU step")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-graph", action="store_true", help="run the training step eagerly instead of as a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -30,6 +30,6 @@ int sm_count() {
 
 }  // namespace bdlru
 
-extern "C" BDLRU_API int bdlru_version(void) { return 1; }
+extern "C" BDLRU_API int bdlru_version(void) { return 2; }
 extern "C" BDLRU_API const char* bdlru_last_error(void) { return bdlru::g_err; }
 extern "C" BDLRU_API uint64_t bdlru_launch_count(void) { return bdlru::g_launches.load(); }

@@ -50,7 +50,8 @@ __global__ void __launch_bounds__(256) embed_ln_fwd_kernel(const int64_t* __rest
                                                            const float* __restrict__ beta, T* __restrict__ out,
                                                            float* __restrict__ mean_out, float* __restrict__ rstd_out,
                                                            long n_tokens, long n_items, int D, float eps, float p,
-                                                           uint64_t seed) {
+                                                           uint64_t seed, const uint64_t* __restrict__ seed_dev) {
+  if (seed_dev) seed += *seed_dev;  // device-side step counter: lets a captured CUDA graph draw a new mask per replay
   const int lane = threadIdx.x & 31;
   const long gw = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long nw = ((long)gridDim.x * blockDim.x) >> 5;
@@ -115,7 +116,9 @@ __global__ void __launch_bounds__(256) embed_ln_bwd_kernel(const int64_t* __rest
                                                            const float* __restrict__ mean_in,
                                                            const float* __restrict__ rstd_in, float* __restrict__ dtable,
                                                            float* __restrict__ part /* [grid][2][D] */, long n_tokens,
-                                                           long n_items, int D, float p, uint64_t seed, long padding_idx) {
+                                                           long n_items, int D, float p, uint64_t seed, const uint64_t* __restrict__ seed_dev,
+                                                           long padding_idx) {
+  if (seed_dev) seed += *seed_dev;
   extern __shared__ float red[];  // [warps][2][D]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   const long gw = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -232,7 +235,7 @@ using namespace bdlru;
 extern "C" BDLRU_API int bdlru_embed_ln_fwd(const int64_t* ids, const void* table, const float* gamma,
                                             const float* beta, void* out, float* mean, float* rstd, int64_t n_tokens,
                                             int64_t n_items, int D, float eps, float dropout_p, uint64_t seed,
-                                            int dtype, void* stream) {
+                                            const uint64_t* seed_device, int dtype, void* stream) {
   int rc = embed_check(n_tokens, n_items, D, dtype, dropout_p);
   if (rc) return rc;
   BDLRU_REQUIRE(ids && table && gamma && beta && out && mean && rstd, "embed_ln_fwd: null pointer");
@@ -242,11 +245,11 @@ extern "C" BDLRU_API int bdlru_embed_ln_fwd(const int64_t* ids, const void* tabl
   const int grid = embed_grid(n_tokens);
   if (dtype == BDLRU_F32)
     embed_ln_fwd_kernel<float><<<grid, 256, 0, st>>>(ids, (const float*)table, gamma, beta, (float*)out, mean, rstd,
-                                                     n_tokens, n_items, D, eps, dropout_p, seed);
+                                                     n_tokens, n_items, D, eps, dropout_p, seed, seed_device);
   else
     embed_ln_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(ids, (const __nv_bfloat16*)table, gamma, beta,
                                                              (__nv_bfloat16*)out, mean, rstd, n_tokens, n_items, D,
-                                                             eps, dropout_p, seed);
+                                                             eps, dropout_p, seed, seed_device);
   BDLRU_LAUNCHED();
   return BDLRU_OK;
 }
@@ -260,7 +263,7 @@ extern "C" BDLRU_API int bdlru_embed_ln_bwd(const int64_t* ids, const void* tabl
                                             const void* grad_out, const float* mean, const float* rstd, float* dtable,
                                             float* dgamma, float* dbeta, void* workspace, size_t workspace_bytes,
                                             int64_t n_tokens, int64_t n_items, int D, float dropout_p, uint64_t seed,
-                                            int64_t padding_idx, int dtype, void* stream) {
+                                            const uint64_t* seed_device, int64_t padding_idx, int dtype, void* stream) {
   int rc = embed_check(n_tokens, n_items, D, dtype, dropout_p);
   if (rc) return rc;
   BDLRU_REQUIRE(ids && table && gamma && grad_out && mean && rstd && dtable && dgamma && dbeta,
@@ -277,12 +280,12 @@ extern "C" BDLRU_API int bdlru_embed_ln_bwd(const int64_t* ids, const void* tabl
   if (dtype == BDLRU_F32)
     embed_ln_bwd_kernel<float><<<grid, 256, smem, st>>>(ids, (const float*)table, gamma, (const float*)grad_out, mean,
                                                         rstd, dtable, part, n_tokens, n_items, D, dropout_p, seed,
-                                                        padding_idx);
+                                                        seed_device, padding_idx);
   else
     embed_ln_bwd_kernel<__nv_bfloat16><<<grid, 256, smem, st>>>(ids, (const __nv_bfloat16*)table, gamma,
                                                                 (const __nv_bfloat16*)grad_out, mean, rstd, dtable,
                                                                 part, n_tokens, n_items, D, dropout_p, seed,
-                                                                padding_idx);
+                                                                seed_device, padding_idx);
   BDLRU_LAUNCHED();
   embed_ln_reduce<<<(2 * D + 127) / 128, 128, 0, st>>>(part, grid, D, dgamma, dbeta);
   BDLRU_LAUNCHED();

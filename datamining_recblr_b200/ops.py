@@ -200,7 +200,7 @@ def causal_conv1d_channel_last(x, weight, bias=None, silu=True):
 
 class _EmbedLN(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, ids, table, gamma, beta, eps, p, seed, padding_idx):
+    def forward(ctx, ids, table, gamma, beta, eps, p, seed, padding_idx, seed_dev):
         L.require_cuda(ids, table, gamma, beta)
         assert ids.dtype == torch.int64 and table.dim() == 2
         n_items, D = table.shape
@@ -213,8 +213,9 @@ class _EmbedLN(torch.autograd.Function):
         rstd = torch.empty_like(mean)
         L.check(L.load().bdlru_embed_ln_fwd(L.ptr(ids_c), L.ptr(tab), L.ptr(gf), L.ptr(bf), L.ptr(out), L.ptr(mean),
                                             L.ptr(rstd), n, n_items, D, float(eps), float(p), int(seed),
-                                            L.dtype_tag(tab), L.stream_ptr(tab)))
+                                            L.ptr(seed_dev), L.dtype_tag(tab), L.stream_ptr(tab)))
         ctx.save_for_backward(ids_c, tab, gf, mean, rstd)
+        ctx.seed_dev = seed_dev
         ctx.args = (float(p), int(seed), int(padding_idx), gamma.dtype, beta.dtype)
         return out
 
@@ -233,14 +234,16 @@ class _EmbedLN(torch.autograd.Function):
         ws = _workspace(tab.device, nws)
         L.check(lib.bdlru_embed_ln_bwd(L.ptr(ids_c), L.ptr(tab), L.ptr(gf), L.ptr(grad_out), L.ptr(mean), L.ptr(rstd),
                                        L.ptr(dtable), L.ptr(dgamma), L.ptr(dbeta), L.ptr(ws), nws, n, n_items, D, p,
-                                       seed, padding_idx, L.dtype_tag(tab), L.stream_ptr(tab)))
-        return None, dtable.to(tab.dtype), dgamma.to(g_dtype), dbeta.to(b_dtype), None, None, None, None
+                                       seed, L.ptr(ctx.seed_dev), padding_idx, L.dtype_tag(tab), L.stream_ptr(tab)))
+        return None, dtable.to(tab.dtype), dgamma.to(g_dtype), dbeta.to(b_dtype), None, None, None, None, None
 
 
-def embed_layernorm(ids, table, gamma, beta, eps=1e-12, dropout_p=0.0, seed=0, padding_idx=-1):
+def embed_layernorm(ids, table, gamma, beta, eps=1e-12, dropout_p=0.0, seed=0, padding_idx=-1, seed_dev=None):
     """LayerNorm(dropout(table[ids])) in one kernel (RecBLR.py:76-78).  ids int64 [...]; returns [..., D] in
-    table.dtype.  Rows equal to padding_idx receive no gather gradient (nn.Embedding(padding_idx=0) semantics)."""
-    return _EmbedLN.apply(ids, table, gamma, beta, eps, dropout_p, seed, padding_idx)
+    table.dtype.  Rows equal to padding_idx receive no gather gradient (nn.Embedding(padding_idx=0) semantics).
+    seed_dev: optional int64[1] CUDA tensor added to `seed` on the device (the mask must NOT change between this
+    call's forward and backward: bump it once per step, before the forward)."""
+    return _EmbedLN.apply(ids, table, gamma, beta, eps, dropout_p, seed, padding_idx, seed_dev)
 
 
 # ----------------------------------------------------------------------------- full-sort scoring / CE (tcgen05)

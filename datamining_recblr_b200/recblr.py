@@ -106,7 +106,9 @@ class RecBLR(SequentialRecommender):
         else:
             raise NotImplementedError("Make sure 'loss_type' in ['BPR', 'CE']!")
         self.apply(self._init_weights)
-        self._step = 0  # advances the dropout counter stream of the fused front end
+        # step counter of the fused front end's dropout stream, ON THE DEVICE so that a training step captured in a
+        # CUDA graph draws a new mask at every replay (not a parameter, not saved in checkpoints)
+        self.register_buffer("_dropout_step", torch.zeros(1, dtype=torch.int64), persistent=False)
 
     def _init_weights(self, module):  # RecBLR.py:66-73 (the pad row 0 is re-randomised too: SURVEY quirk 2)
         if isinstance(module, (nn.Linear, nn.Embedding)):
@@ -122,11 +124,14 @@ class RecBLR(SequentialRecommender):
         p = self.dropout_prob if self.training else 0.0
         D = self.hidden_size
         if self.fused_front and D % 4 == 0 and D <= 512:
-            self._step += 1
-            seed = (torch.initial_seed() * 0x9E3779B97F4A7C15 + self._step) & 0xFFFFFFFFFFFFFFFF
+            seed_dev = None
+            if p > 0.0:
+                self._dropout_step.add_(1)
+                seed_dev = self._dropout_step
+            seed = (torch.initial_seed() * 0x9E3779B97F4A7C15) & 0x7FFFFFFFFFFFFFFF
             return ops.embed_layernorm(item_seq, self.item_embedding.weight, self.layer_norm.weight,
                                        self.layer_norm.bias, eps=self.layer_norm.eps, dropout_p=p, seed=seed,
-                                       padding_idx=0)
+                                       padding_idx=0, seed_dev=seed_dev)
         return self.layer_norm(self.dropout(self.item_embedding(item_seq)))
 
     def forward(self, item_seq, item_seq_len):
