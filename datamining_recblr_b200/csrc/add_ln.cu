@@ -1,0 +1,278 @@
+// Residual epilogue of RecurrentLayer.forward / FeedForward.forward (RecBLR.py:142, 221-225):
+//     out = LayerNorm(dropout(x) + residual) * gamma + beta          eps = 1e-12, fp32 statistics
+// as ONE kernel (the reference runs dropout, add and an ATen LayerNorm that spends ~150 us on a [102400, 64] tensor).
+// One warp per row, lanes hold 4-channel vectors (128-bit I/O), mean/variance by warp shuffles; dropout uses the same
+// Philox counter stream as the front end (embed_ln.cu), keyed by (seed [+ device counter], row, vector) and
+// regenerated in the backward.  Backward: LayerNorm backward per row -> d(sum) written as dresidual and, masked, as dx;
+// dgamma/dbeta accumulated in registers over a grid-stride loop, block-reduced, finished by a deterministic second pass.
+#include "common.cuh"
+
+namespace bdlru {
+
+constexpr int kAV = 4;  // vectors per lane: D <= 512
+
+__device__ __forceinline__ void philox_a(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                                         uint32_t (&out)[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+__device__ __forceinline__ void keep_scale4(uint64_t seed, long row, int vec, float p, float (&m)[4]) {
+  uint32_t r[4];
+  philox_a((uint32_t)row, (uint32_t)((uint64_t)row >> 32), (uint32_t)vec, 0x2545F491u, (uint32_t)seed,
+           (uint32_t)(seed >> 32), r);
+  const float inv = 1.0f / (1.0f - p);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) m[e] = ((float)(r[e] >> 8) * (1.0f / 16777216.0f)) >= p ? inv : 0.f;
+}
+
+__device__ __forceinline__ float wsum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) add_ln_fwd_kernel(const T* __restrict__ x, const T* __restrict__ res,
+                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                         T* __restrict__ out, float* __restrict__ mean_out,
+                                                         float* __restrict__ rstd_out, long n_rows, int D, float eps,
+                                                         float p, uint64_t seed, const uint64_t* __restrict__ seed_dev) {
+  if (seed_dev) seed += *seed_dev;
+  const int lane = threadIdx.x & 31;
+  const long gw = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long nw = ((long)gridDim.x * blockDim.x) >> 5;
+  const int nvec = D / 4;
+  for (long n = gw; n < n_rows; n += nw) {
+    float v[kAV][4];
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < kAV; ++k) {
+      const int vec = lane + 32 * k;
+      if (vec < nvec) {
+        float a[4], r[4];
+        IO<T>::load(x + n * D + vec * 4, a);
+        IO<T>::load(res + n * D + vec * 4, r);
+        if (p > 0.f) {
+          float m[4];
+          keep_scale4(seed, n, vec, p, m);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) a[e] *= m[e];
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[k][e] = a[e] + r[e];
+        s += (v[k][0] + v[k][1]) + (v[k][2] + v[k][3]);
+      }
+    }
+    const float mean = wsum(s) / (float)D;
+    float q = 0.f;
+#pragma unroll
+    for (int k = 0; k < kAV; ++k)
+      if (lane + 32 * k < nvec) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float d = v[k][e] - mean;
+          q = fmaf(d, d, q);
+        }
+      }
+    const float rstd = rsqrtf(wsum(q) / (float)D + eps);
+#pragma unroll
+    for (int k = 0; k < kAV; ++k) {
+      const int vec = lane + 32 * k;
+      if (vec < nvec) {
+        const float4 g4 = *reinterpret_cast<const float4*>(gamma + vec * 4);
+        const float4 b4 = *reinterpret_cast<const float4*>(beta + vec * 4);
+        float o[4];
+        o[0] = fmaf((v[k][0] - mean) * rstd, g4.x, b4.x);
+        o[1] = fmaf((v[k][1] - mean) * rstd, g4.y, b4.y);
+        o[2] = fmaf((v[k][2] - mean) * rstd, g4.z, b4.z);
+        o[3] = fmaf((v[k][3] - mean) * rstd, g4.w, b4.w);
+        IO<T>::store(out + n * D + vec * 4, o);
+      }
+    }
+    if (lane == 0) {
+      mean_out[n] = mean;
+      rstd_out[n] = rstd;
+    }
+  }
+}
+
+// Backward reads x, res (to rebuild the normalised row), dy; writes dres (= d sum) and dx (= dres * mask).
+template <typename T>
+__global__ void __launch_bounds__(256) add_ln_bwd_kernel(const T* __restrict__ x, const T* __restrict__ res,
+                                                         const float* __restrict__ gamma, const T* __restrict__ dy,
+                                                         const float* __restrict__ mean_in,
+                                                         const float* __restrict__ rstd_in, T* __restrict__ dx,
+                                                         T* __restrict__ dres, float* __restrict__ part, long n_rows,
+                                                         int D, float p, uint64_t seed,
+                                                         const uint64_t* __restrict__ seed_dev) {
+  extern __shared__ float red[];  // [warps][2][D]
+  if (seed_dev) seed += *seed_dev;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const long gw = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long nw = ((long)gridDim.x * blockDim.x) >> 5;
+  const int nvec = D / 4;
+  float dg[kAV][4], db[kAV][4];
+#pragma unroll
+  for (int k = 0; k < kAV; ++k)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) dg[k][e] = db[k][e] = 0.f;
+  for (long n = gw; n < n_rows; n += nw) {
+    const float mean = mean_in[n], rstd = rstd_in[n];
+    float xh[kAV][4], dxh[kAV][4], msk[kAV][4];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < kAV; ++k) {
+      const int vec = lane + 32 * k;
+      if (vec < nvec) {
+        float a[4], r[4], g[4];
+        IO<T>::load(x + n * D + vec * 4, a);
+        IO<T>::load(res + n * D + vec * 4, r);
+        IO<T>::load(dy + n * D + vec * 4, g);
+        if (p > 0.f) {
+          keep_scale4(seed, n, vec, p, msk[k]);
+        } else {
+          msk[k][0] = msk[k][1] = msk[k][2] = msk[k][3] = 1.f;
+        }
+        const float4 g4 = *reinterpret_cast<const float4*>(gamma + vec * 4);
+        const float gm[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          xh[k][e] = (fmaf(a[e], msk[k][e], r[e]) - mean) * rstd;
+          dxh[k][e] = g[e] * gm[e];
+          dg[k][e] = fmaf(g[e], xh[k][e], dg[k][e]);
+          db[k][e] += g[e];
+          s1 += dxh[k][e];
+          s2 = fmaf(dxh[k][e], xh[k][e], s2);
+        }
+      }
+    }
+    s1 = wsum(s1) / (float)D;
+    s2 = wsum(s2) / (float)D;
+#pragma unroll
+    for (int k = 0; k < kAV; ++k) {
+      const int vec = lane + 32 * k;
+      if (vec < nvec) {
+        float ds[4], dxx[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          ds[e] = rstd * (dxh[k][e] - s1 - xh[k][e] * s2);
+          dxx[e] = ds[e] * msk[k][e];
+        }
+        IO<T>::store(dres + n * D + vec * 4, ds);
+        if (dx != dres) IO<T>::store(dx + n * D + vec * 4, dxx);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < kAV; ++k) {
+    const int vec = lane + 32 * k;
+    if (vec < nvec) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        red[((size_t)warp * 2 + 0) * D + vec * 4 + e] = dg[k][e];
+        red[((size_t)warp * 2 + 1) * D + vec * 4 + e] = db[k][e];
+      }
+    }
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < 2 * D; idx += blockDim.x) {
+    float s = 0.f;
+    for (int w = 0; w < nwarp; ++w) s += red[(size_t)w * 2 * D + idx];
+    part[(size_t)blockIdx.x * 2 * D + idx] = s;
+  }
+}
+
+__global__ void add_ln_reduce(const float* __restrict__ part, int grid, int D, float* __restrict__ dgamma,
+                              float* __restrict__ dbeta) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 2 * D) return;
+  float s = 0.f;
+  for (int g = 0; g < grid; ++g) s += part[(size_t)g * 2 * D + idx];
+  if (idx < D) dgamma[idx] = s;
+  else dbeta[idx - D] = s;
+}
+
+static int add_ln_grid(long n_rows) {
+  long blocks = (n_rows + 7) / 8;
+  const long cap = (long)sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  return (int)(blocks < 1 ? 1 : blocks);
+}
+
+static int add_ln_check(long n_rows, int D, int dtype, float p) {
+  BDLRU_REQUIRE(n_rows >= 1, "add_ln: n_rows=%ld", n_rows);
+  BDLRU_REQUIRE(D >= 4 && D % 4 == 0 && D <= 128 * kAV, "add_ln: D=%d must be a multiple of 4 and <= %d", D, 128 * kAV);
+  BDLRU_REQUIRE(dtype == BDLRU_F32 || dtype == BDLRU_BF16, "add_ln: bad dtype %d", dtype);
+  BDLRU_REQUIRE(p >= 0.f && p < 1.f, "add_ln: dropout_p=%f not in [0, 1)", p);
+  return BDLRU_OK;
+}
+
+}  // namespace bdlru
+
+using namespace bdlru;
+
+extern "C" BDLRU_API int bdlru_add_ln_fwd(const void* x, const void* residual, const float* gamma, const float* beta,
+                                          void* out, float* mean, float* rstd, int64_t n_rows, int D, float eps,
+                                          float dropout_p, uint64_t seed, const uint64_t* seed_device, int dtype,
+                                          void* stream) {
+  int rc = add_ln_check(n_rows, D, dtype, dropout_p);
+  if (rc) return rc;
+  BDLRU_REQUIRE(x && residual && gamma && beta && out && mean && rstd, "add_ln_fwd: null pointer");
+  BDLRU_REQUIRE(aligned(x, 8) && aligned(residual, 8) && aligned(out, 8) && aligned(gamma, 16) && aligned(beta, 16),
+                "add_ln_fwd: misaligned pointer");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int grid = add_ln_grid(n_rows);
+  if (dtype == BDLRU_F32) {
+    BDLRU_REQUIRE(aligned(x, 16) && aligned(residual, 16) && aligned(out, 16), "add_ln_fwd: misaligned fp32 pointer");
+    add_ln_fwd_kernel<float><<<grid, 256, 0, st>>>((const float*)x, (const float*)residual, gamma, beta, (float*)out,
+                                                   mean, rstd, n_rows, D, eps, dropout_p, seed, seed_device);
+  } else {
+    add_ln_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)residual,
+                                                           gamma, beta, (__nv_bfloat16*)out, mean, rstd, n_rows, D, eps,
+                                                           dropout_p, seed, seed_device);
+  }
+  BDLRU_LAUNCHED();
+  return BDLRU_OK;
+}
+
+extern "C" BDLRU_API size_t bdlru_add_ln_bwd_workspace_bytes(int64_t n_rows, int D) {
+  (void)n_rows;
+  return (size_t)sm_count() * 8 * 2 * (size_t)D * sizeof(float);
+}
+
+extern "C" BDLRU_API int bdlru_add_ln_bwd(const void* x, const void* residual, const float* gamma, const void* grad_out,
+                                          const float* mean, const float* rstd, void* dx, void* dresidual, float* dgamma,
+                                          float* dbeta, void* workspace, size_t workspace_bytes, int64_t n_rows, int D,
+                                          float dropout_p, uint64_t seed, const uint64_t* seed_device, int dtype,
+                                          void* stream) {
+  int rc = add_ln_check(n_rows, D, dtype, dropout_p);
+  if (rc) return rc;
+  BDLRU_REQUIRE(x && residual && gamma && grad_out && mean && rstd && dx && dresidual && dgamma && dbeta,
+                "add_ln_bwd: null pointer");
+  const int grid = add_ln_grid(n_rows);
+  const size_t need = (size_t)grid * 2 * D * sizeof(float);
+  BDLRU_REQUIRE(workspace && workspace_bytes >= need, "add_ln_bwd: workspace too small (%zu < %zu)", workspace_bytes, need);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  float* part = reinterpret_cast<float*>(workspace);
+  const size_t smem = (size_t)8 * 2 * D * sizeof(float);
+  if (dtype == BDLRU_F32)
+    add_ln_bwd_kernel<float><<<grid, 256, smem, st>>>((const float*)x, (const float*)residual, gamma,
+                                                      (const float*)grad_out, mean, rstd, (float*)dx, (float*)dresidual,
+                                                      part, n_rows, D, dropout_p, seed, seed_device);
+  else
+    add_ln_bwd_kernel<__nv_bfloat16><<<grid, 256, smem, st>>>(
+        (const __nv_bfloat16*)x, (const __nv_bfloat16*)residual, gamma, (const __nv_bfloat16*)grad_out, mean, rstd,
+        (__nv_bfloat16*)dx, (__nv_bfloat16*)dresidual, part, n_rows, D, dropout_p, seed, seed_device);
+  BDLRU_LAUNCHED();
+  add_ln_reduce<<<(2 * D + 127) / 128, 128, 0, st>>>(part, grid, D, dgamma, dbeta);
+  BDLRU_LAUNCHED();
+  return BDLRU_OK;
+}

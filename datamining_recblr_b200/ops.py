@@ -246,6 +246,53 @@ def embed_layernorm(ids, table, gamma, beta, eps=1e-12, dropout_p=0.0, seed=0, p
     return _EmbedLN.apply(ids, table, gamma, beta, eps, dropout_p, seed, padding_idx, seed_dev)
 
 
+class _AddLN(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, res, gamma, beta, eps, p, seed, seed_dev):
+        L.require_cuda(x, res, gamma, beta)
+        assert x.shape == res.shape
+        D = x.shape[-1]
+        dt = x.dtype
+        xc, rc = x.contiguous(), res.to(dt).contiguous()
+        gf, bf = gamma.detach().float().contiguous(), beta.detach().float().contiguous()
+        n = xc.numel() // D
+        out = torch.empty_like(xc)
+        mean = torch.empty(n, dtype=torch.float32, device=x.device)
+        rstd = torch.empty_like(mean)
+        L.check(L.load().bdlru_add_ln_fwd(L.ptr(xc), L.ptr(rc), L.ptr(gf), L.ptr(bf), L.ptr(out), L.ptr(mean), L.ptr(rstd),
+                                          n, D, float(eps), float(p), int(seed), L.ptr(seed_dev), L.dtype_tag(xc),
+                                          L.stream_ptr(xc)))
+        ctx.save_for_backward(xc, rc, gf, mean, rstd)
+        ctx.seed_dev = seed_dev
+        ctx.args = (float(p), int(seed), res.dtype, gamma.dtype, beta.dtype)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        xc, rc, gf, mean, rstd = ctx.saved_tensors
+        p, seed, res_dtype, g_dtype, b_dtype = ctx.args
+        D = xc.shape[-1]
+        n = xc.numel() // D
+        grad_out = grad_out.to(xc.dtype).contiguous()
+        dres = torch.empty_like(xc)
+        dx = torch.empty_like(xc) if p > 0.0 else dres
+        dgamma = torch.empty(D, dtype=torch.float32, device=xc.device)
+        dbeta = torch.empty_like(dgamma)
+        lib = L.load()
+        nws = lib.bdlru_add_ln_bwd_workspace_bytes(n, D)
+        ws = _workspace(xc.device, nws)
+        L.check(lib.bdlru_add_ln_bwd(L.ptr(xc), L.ptr(rc), L.ptr(gf), L.ptr(grad_out), L.ptr(mean), L.ptr(rstd), L.ptr(dx),
+                                     L.ptr(dres), L.ptr(dgamma), L.ptr(dbeta), L.ptr(ws), nws, n, D, p, seed,
+                                     L.ptr(ctx.seed_dev), L.dtype_tag(xc), L.stream_ptr(xc)))
+        return dx, dres.to(res_dtype), dgamma.to(g_dtype), dbeta.to(b_dtype), None, None, None, None
+
+
+def add_dropout_layernorm(x, residual, gamma, beta, eps=1e-12, dropout_p=0.0, seed=0, seed_dev=None):
+    """LayerNorm(dropout(x) + residual) in one kernel (RecBLR.py:142, 221-225); output in x.dtype (the residual is
+    read in that dtype too), fp32 statistics.  D % 4 == 0, D <= 512."""
+    return _AddLN.apply(x, residual, gamma, beta, eps, dropout_p, seed, seed_dev)
+
+
 # ----------------------------------------------------------------------------- full-sort scoring / CE (tcgen05)
 def fullsort_supported(D):
     """Shapes the tcgen05 full-sort kernels take: bf16 operands, D a multiple of 64 up to 256."""

@@ -128,7 +128,7 @@ class RecBLR(SequentialRecommender):
             if p > 0.0:
                 self._dropout_step.add_(1)
                 seed_dev = self._dropout_step
-            seed = (torch.initial_seed() * 0x9E3779B97F4A7C15) & 0x7FFFFFFFFFFFFFFF
+            seed = self._seed_base()
             return ops.embed_layernorm(item_seq, self.item_embedding.weight, self.layer_norm.weight,
                                        self.layer_norm.bias, eps=self.layer_norm.eps, dropout_p=p, seed=seed,
                                        padding_idx=0, seed_dev=seed_dev)
@@ -136,9 +136,14 @@ class RecBLR(SequentialRecommender):
 
     def forward(self, item_seq, item_seq_len):
         item_emb = self._front(item_seq)
-        for layer in self.recurrent_layers:
-            item_emb = layer(item_emb)
+        ctx = (self._seed_base(), self._dropout_step if self.training and self.dropout_prob > 0 else None)
+        for i, layer in enumerate(self.recurrent_layers):
+            item_emb = layer(item_emb, dropout_ctx=(ctx[0] + 7919 * (i + 1), ctx[1]))
         return self.gather_indexes(item_emb, item_seq_len - 1)
+
+    @staticmethod
+    def _seed_base():
+        return (torch.initial_seed() * 0x9E3779B97F4A7C15) & 0x3FFFFFFFFFFFFFFF
 
     # ------------------------------------------------------------------ RecBLR.py:86-103
     def calculate_loss(self, interaction):
@@ -178,6 +183,23 @@ class RecBLR(SequentialRecommender):
         return scores, ids.long()
 
 
+def _residual_ln(owner, norm, dropout, x, residual, dropout_ctx, site):
+    """LayerNorm(dropout(x) + residual) (RecBLR.py:142 / 221-225) through the fused kernel."""
+    D = x.shape[-1]
+    p = dropout.p if owner.training else 0.0
+    if not x.is_cuda or D % 4 != 0 or D > 512:
+        return norm(dropout(x) + residual)
+    seed, seed_dev = 0, None
+    if p > 0.0:
+        if dropout_ctx is not None and dropout_ctx[1] is not None:
+            seed, seed_dev = dropout_ctx[0] + 104729 * site, dropout_ctx[1]
+        else:  # standalone layer: advance a host-side step count
+            owner._host_step = getattr(owner, "_host_step", 0) + 1
+            seed = (RecBLR._seed_base() + 104729 * site + owner._host_step) & 0x3FFFFFFFFFFFFFFF
+    return ops.add_dropout_layernorm(x, residual, norm.weight, norm.bias, eps=norm.eps, dropout_p=p, seed=seed,
+                                     seed_dev=seed_dev)
+
+
 class RecurrentLayer(nn.Module):
     """RecBLR.py:124-145."""
 
@@ -191,11 +213,13 @@ class RecurrentLayer(nn.Module):
         self.layer_norm = nn.LayerNorm(d_model, eps=1e-12)
         self.ffn = FeedForward(d_model=d_model, inner_size=d_model * 4, dropout=dropout)
 
-    def forward(self, input_tensor):
+    def forward(self, input_tensor, dropout_ctx=None):
+        """dropout_ctx = (seed, device step counter or None): the counter stream shared by the model's fused dropouts
+        (RecBLR.forward supplies it; standalone use falls back to a host-side step count)."""
         hidden_states = self.behavior_modeling(input_tensor)
-        hidden_states = self.layer_norm(self.dropout(hidden_states) + input_tensor)
+        hidden_states = _residual_ln(self, self.layer_norm, self.dropout, hidden_states, input_tensor, dropout_ctx, 1)
         if not self.disable_ffn:
-            hidden_states = self.ffn(hidden_states)
+            hidden_states = self.ffn(hidden_states, dropout_ctx)
         return hidden_states
 
 
@@ -254,7 +278,7 @@ class FeedForward(nn.Module):
         self.dropout = nn.Dropout(dropout)
         self.layer_norm = nn.LayerNorm(d_model, eps=1e-12)
 
-    def forward(self, input_tensor):
+    def forward(self, input_tensor, dropout_ctx=None):
         hidden_states = self.dropout(F.silu(self.w_1(input_tensor)))
-        hidden_states = self.dropout(self.w_2(hidden_states))
-        return self.layer_norm(hidden_states + input_tensor)
+        hidden_states = self.w_2(hidden_states)
+        return _residual_ln(self, self.layer_norm, self.dropout, hidden_states, input_tensor, dropout_ctx, 2)

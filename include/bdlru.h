@@ -15,6 +15,7 @@
  *                                    and the left-pad of RecBLR.py:177-179,203-204 (as h0 / dh0)
  *   bdlru_conv1d_fwd / _bwd          causal_conv1d_fn call site RecBLR.py:188-193 (fallback line 185)
  *   bdlru_embed_ln_fwd / _bwd        RecBLR.py:76-78 (embedding gather -> dropout -> LayerNorm)
+ *   bdlru_add_ln_fwd / _bwd          RecBLR.py:142, 221-225 (dropout -> + residual -> LayerNorm)
  *   bdlru_fullsort_topk              RecBLR.py:114-122 + RecBole mask/top-k ([upstream])
  *   bdlru_fullsort_ce_fwd / _bwd     RecBLR.py:99-103 (logits GEMM + nn.CrossEntropyLoss, mean)
  */
@@ -130,6 +131,22 @@ int bdlru_embed_ln_bwd(const int64_t* ids, const void* table, const float* gamma
                        void* workspace, size_t workspace_bytes, int64_t n_tokens, int64_t n_items, int D,
                        float dropout_p, uint64_t seed, const uint64_t* seed_device, int64_t padding_idx, int dtype,
                        void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Residual epilogue: out[n,:] = LayerNorm(dropout(x[n,:]) + residual[n,:]) * gamma + beta
+ * (RecurrentLayer.forward RecBLR.py:142 and FeedForward.forward RecBLR.py:221-225).  x, residual, out, grad_out, dx,
+ * dresidual are contiguous [n_rows, D] in `dtype`; gamma/beta/dgamma/dbeta/mean/rstd fp32.  Same dropout generator and
+ * seed_device convention as bdlru_embed_ln_*.  bwd: dresidual = d(sum), dx = dresidual * mask; dx may alias
+ * dresidual when dropout_p == 0.
+ * ------------------------------------------------------------------------------------------- */
+int bdlru_add_ln_fwd(const void* x, const void* residual, const float* gamma, const float* beta, void* out,
+                     float* mean, float* rstd, int64_t n_rows, int D, float eps, float dropout_p, uint64_t seed,
+                     const uint64_t* seed_device, int dtype, void* stream);
+size_t bdlru_add_ln_bwd_workspace_bytes(int64_t n_rows, int D);
+int bdlru_add_ln_bwd(const void* x, const void* residual, const float* gamma, const void* grad_out, const float* mean,
+                     const float* rstd, void* dx, void* dresidual, float* dgamma, float* dbeta, void* workspace,
+                     size_t workspace_bytes, int64_t n_rows, int D, float dropout_p, uint64_t seed,
+                     const uint64_t* seed_device, int dtype, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Full-sort scoring with fused streaming top-k (RecBLR.py:114-122 + RecBole's scores[:,0] = -inf and
