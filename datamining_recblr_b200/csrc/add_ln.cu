@@ -39,24 +39,37 @@ __device__ __forceinline__ float wsum(float v) {
   return v;
 }
 
-template <typename T>
+// LPR lanes cooperate on one row (32 / LPR rows per warp, so D = 64 keeps all lanes busy with two rows per warp);
+// each lane holds VPL 4-channel vectors: D <= 4 * LPR * VPL.
+template <int LPR>
+__device__ __forceinline__ float gsum(float v) {
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <typename T, int LPR, int VPL>
 __global__ void __launch_bounds__(256) add_ln_fwd_kernel(const T* __restrict__ x, const T* __restrict__ res,
                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
                                                          T* __restrict__ out, float* __restrict__ mean_out,
                                                          float* __restrict__ rstd_out, long n_rows, int D, float eps,
                                                          float p, uint64_t seed, const uint64_t* __restrict__ seed_dev) {
   if (seed_dev) seed += *seed_dev;
-  const int lane = threadIdx.x & 31;
+  constexpr int RPW = 32 / LPR;
+  const int lane = threadIdx.x & 31, sub = lane / LPR, sl = lane % LPR;
   const long gw = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long nw = ((long)gridDim.x * blockDim.x) >> 5;
   const int nvec = D / 4;
-  for (long n = gw; n < n_rows; n += nw) {
-    float v[kAV][4];
+  for (long n0 = gw * RPW; n0 < n_rows; n0 += nw * RPW) {
+    const long n = n0 + sub;
+    const bool live = n < n_rows;
+    float v[VPL][4];
     float s = 0.f;
 #pragma unroll
-    for (int k = 0; k < kAV; ++k) {
-      const int vec = lane + 32 * k;
-      if (vec < nvec) {
+    for (int k = 0; k < VPL; ++k) {
+      const int vec = sl + LPR * k;
+      v[k][0] = v[k][1] = v[k][2] = v[k][3] = 0.f;
+      if (live && vec < nvec) {
         float a[4], r[4];
         IO<T>::load(x + n * D + vec * 4, a);
         IO<T>::load(res + n * D + vec * 4, r);
@@ -71,22 +84,22 @@ __global__ void __launch_bounds__(256) add_ln_fwd_kernel(const T* __restrict__ x
         s += (v[k][0] + v[k][1]) + (v[k][2] + v[k][3]);
       }
     }
-    const float mean = wsum(s) / (float)D;
+    const float mean = gsum<LPR>(s) / (float)D;
     float q = 0.f;
 #pragma unroll
-    for (int k = 0; k < kAV; ++k)
-      if (lane + 32 * k < nvec) {
+    for (int k = 0; k < VPL; ++k)
+      if (sl + LPR * k < nvec) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const float d = v[k][e] - mean;
           q = fmaf(d, d, q);
         }
       }
-    const float rstd = rsqrtf(wsum(q) / (float)D + eps);
+    const float rstd = rsqrtf(gsum<LPR>(q) / (float)D + eps);
 #pragma unroll
-    for (int k = 0; k < kAV; ++k) {
-      const int vec = lane + 32 * k;
-      if (vec < nvec) {
+    for (int k = 0; k < VPL; ++k) {
+      const int vec = sl + LPR * k;
+      if (live && vec < nvec) {
         const float4 g4 = *reinterpret_cast<const float4*>(gamma + vec * 4);
         const float4 b4 = *reinterpret_cast<const float4*>(beta + vec * 4);
         float o[4];
@@ -97,7 +110,7 @@ __global__ void __launch_bounds__(256) add_ln_fwd_kernel(const T* __restrict__ x
         IO<T>::store(out + n * D + vec * 4, o);
       }
     }
-    if (lane == 0) {
+    if (live && sl == 0) {
       mean_out[n] = mean;
       rstd_out[n] = rstd;
     }
@@ -105,7 +118,7 @@ __global__ void __launch_bounds__(256) add_ln_fwd_kernel(const T* __restrict__ x
 }
 
 // Backward reads x, res (to rebuild the normalised row), dy; writes dres (= d sum) and dx (= dres * mask).
-template <typename T>
+template <typename T, int LPR, int VPL>
 __global__ void __launch_bounds__(256) add_ln_bwd_kernel(const T* __restrict__ x, const T* __restrict__ res,
                                                          const float* __restrict__ gamma, const T* __restrict__ dy,
                                                          const float* __restrict__ mean_in,
@@ -113,34 +126,36 @@ __global__ void __launch_bounds__(256) add_ln_bwd_kernel(const T* __restrict__ x
                                                          T* __restrict__ dres, float* __restrict__ part, long n_rows,
                                                          int D, float p, uint64_t seed,
                                                          const uint64_t* __restrict__ seed_dev) {
-  extern __shared__ float red[];  // [warps][2][D]
+  extern __shared__ float red[];  // [warps * RPW][2][D]
   if (seed_dev) seed += *seed_dev;
+  constexpr int RPW = 32 / LPR;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const int sub = lane / LPR, sl = lane % LPR;
   const long gw = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long nw = ((long)gridDim.x * blockDim.x) >> 5;
   const int nvec = D / 4;
-  float dg[kAV][4], db[kAV][4];
+  float dg[VPL][4], db[VPL][4];
 #pragma unroll
-  for (int k = 0; k < kAV; ++k)
+  for (int k = 0; k < VPL; ++k)
 #pragma unroll
     for (int e = 0; e < 4; ++e) dg[k][e] = db[k][e] = 0.f;
-  for (long n = gw; n < n_rows; n += nw) {
-    const float mean = mean_in[n], rstd = rstd_in[n];
-    float xh[kAV][4], dxh[kAV][4], msk[kAV][4];
+  for (long n0 = gw * RPW; n0 < n_rows; n0 += nw * RPW) {
+    const long n = n0 + sub;
+    const bool live = n < n_rows;
+    const float mean = live ? mean_in[n] : 0.f, rstd = live ? rstd_in[n] : 0.f;
+    float xh[VPL][4], dxh[VPL][4], msk[VPL][4];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int k = 0; k < kAV; ++k) {
-      const int vec = lane + 32 * k;
-      if (vec < nvec) {
+    for (int k = 0; k < VPL; ++k) {
+      const int vec = sl + LPR * k;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) xh[k][e] = dxh[k][e] = 0.f, msk[k][e] = 1.f;
+      if (live && vec < nvec) {
         float a[4], r[4], g[4];
         IO<T>::load(x + n * D + vec * 4, a);
         IO<T>::load(res + n * D + vec * 4, r);
         IO<T>::load(dy + n * D + vec * 4, g);
-        if (p > 0.f) {
-          keep_scale4(seed, n, vec, p, msk[k]);
-        } else {
-          msk[k][0] = msk[k][1] = msk[k][2] = msk[k][3] = 1.f;
-        }
+        if (p > 0.f) keep_scale4(seed, n, vec, p, msk[k]);
         const float4 g4 = *reinterpret_cast<const float4*>(gamma + vec * 4);
         const float gm[4] = {g4.x, g4.y, g4.z, g4.w};
 #pragma unroll
@@ -154,12 +169,12 @@ __global__ void __launch_bounds__(256) add_ln_bwd_kernel(const T* __restrict__ x
         }
       }
     }
-    s1 = wsum(s1) / (float)D;
-    s2 = wsum(s2) / (float)D;
+    s1 = gsum<LPR>(s1) / (float)D;
+    s2 = gsum<LPR>(s2) / (float)D;
 #pragma unroll
-    for (int k = 0; k < kAV; ++k) {
-      const int vec = lane + 32 * k;
-      if (vec < nvec) {
+    for (int k = 0; k < VPL; ++k) {
+      const int vec = sl + LPR * k;
+      if (live && vec < nvec) {
         float ds[4], dxx[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
@@ -172,36 +187,40 @@ __global__ void __launch_bounds__(256) add_ln_bwd_kernel(const T* __restrict__ x
     }
   }
 #pragma unroll
-  for (int k = 0; k < kAV; ++k) {
-    const int vec = lane + 32 * k;
+  for (int k = 0; k < VPL; ++k) {
+    const int vec = sl + LPR * k;
     if (vec < nvec) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        red[((size_t)warp * 2 + 0) * D + vec * 4 + e] = dg[k][e];
-        red[((size_t)warp * 2 + 1) * D + vec * 4 + e] = db[k][e];
+        red[((size_t)(warp * RPW + sub) * 2 + 0) * D + vec * 4 + e] = dg[k][e];
+        red[((size_t)(warp * RPW + sub) * 2 + 1) * D + vec * 4 + e] = db[k][e];
       }
     }
   }
   __syncthreads();
   for (int idx = threadIdx.x; idx < 2 * D; idx += blockDim.x) {
     float s = 0.f;
-    for (int w = 0; w < nwarp; ++w) s += red[(size_t)w * 2 * D + idx];
+    for (int w = 0; w < nwarp * RPW; ++w) s += red[(size_t)w * 2 * D + idx];
     part[(size_t)blockIdx.x * 2 * D + idx] = s;
   }
 }
 
-__global__ void add_ln_reduce(const float* __restrict__ part, int grid, int D, float* __restrict__ dgamma,
-                              float* __restrict__ dbeta) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= 2 * D) return;
-  float s = 0.f;
-  for (int g = 0; g < grid; ++g) s += part[(size_t)g * 2 * D + idx];
-  if (idx < D) dgamma[idx] = s;
-  else dbeta[idx - D] = s;
-}
+// (LPR, VPL) for a row of D channels
+#define ADD_LN_DISPATCH(D, CALL)                         \
+  do {                                                   \
+    const int nv_ = (D) / 4;                             \
+    if (nv_ <= 8) { CALL(8, 1); }                        \
+    else if (nv_ <= 16) { CALL(16, 1); }                 \
+    else if (nv_ <= 32) { CALL(32, 1); }                 \
+    else if (nv_ <= 64) { CALL(32, 2); }                 \
+    else { CALL(32, 4); }                                \
+  } while (0)
 
-static int add_ln_grid(long n_rows) {
-  long blocks = (n_rows + 7) / 8;
+static int add_ln_rpw(int D) { const int nv = D / 4; return nv <= 8 ? 4 : (nv <= 16 ? 2 : 1); }
+
+static int add_ln_grid(long n_rows, int D) {
+  const int rpb = 8 * add_ln_rpw(D);
+  long blocks = (n_rows + rpb - 1) / rpb;
   const long cap = (long)sm_count() * 8;
   if (blocks > cap) blocks = cap;
   return (int)(blocks < 1 ? 1 : blocks);
@@ -229,15 +248,22 @@ extern "C" BDLRU_API int bdlru_add_ln_fwd(const void* x, const void* residual, c
   BDLRU_REQUIRE(aligned(x, 8) && aligned(residual, 8) && aligned(out, 8) && aligned(gamma, 16) && aligned(beta, 16),
                 "add_ln_fwd: misaligned pointer");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const int grid = add_ln_grid(n_rows);
+  const int grid = add_ln_grid(n_rows, D);
   if (dtype == BDLRU_F32) {
     BDLRU_REQUIRE(aligned(x, 16) && aligned(residual, 16) && aligned(out, 16), "add_ln_fwd: misaligned fp32 pointer");
-    add_ln_fwd_kernel<float><<<grid, 256, 0, st>>>((const float*)x, (const float*)residual, gamma, beta, (float*)out,
-                                                   mean, rstd, n_rows, D, eps, dropout_p, seed, seed_device);
+#define FWD_F32(LPR, VPL)                                                                                          \
+  add_ln_fwd_kernel<float, LPR, VPL><<<grid, 256, 0, st>>>((const float*)x, (const float*)residual, gamma, beta,   \
+                                                           (float*)out, mean, rstd, n_rows, D, eps, dropout_p, seed, \
+                                                           seed_device)
+    ADD_LN_DISPATCH(D, FWD_F32);
+#undef FWD_F32
   } else {
-    add_ln_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)residual,
-                                                           gamma, beta, (__nv_bfloat16*)out, mean, rstd, n_rows, D, eps,
-                                                           dropout_p, seed, seed_device);
+#define FWD_BF16(LPR, VPL)                                                                                       \
+  add_ln_fwd_kernel<__nv_bfloat16, LPR, VPL><<<grid, 256, 0, st>>>(                                                \
+      (const __nv_bfloat16*)x, (const __nv_bfloat16*)residual, gamma, beta, (__nv_bfloat16*)out, mean, rstd, n_rows, \
+      D, eps, dropout_p, seed, seed_device)
+    ADD_LN_DISPATCH(D, FWD_BF16);
+#undef FWD_BF16
   }
   BDLRU_LAUNCHED();
   return BDLRU_OK;
@@ -257,22 +283,28 @@ extern "C" BDLRU_API int bdlru_add_ln_bwd(const void* x, const void* residual, c
   if (rc) return rc;
   BDLRU_REQUIRE(x && residual && gamma && grad_out && mean && rstd && dx && dresidual && dgamma && dbeta,
                 "add_ln_bwd: null pointer");
-  const int grid = add_ln_grid(n_rows);
+  const int grid = add_ln_grid(n_rows, D);
   const size_t need = (size_t)grid * 2 * D * sizeof(float);
   BDLRU_REQUIRE(workspace && workspace_bytes >= need, "add_ln_bwd: workspace too small (%zu < %zu)", workspace_bytes, need);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   float* part = reinterpret_cast<float*>(workspace);
-  const size_t smem = (size_t)8 * 2 * D * sizeof(float);
-  if (dtype == BDLRU_F32)
-    add_ln_bwd_kernel<float><<<grid, 256, smem, st>>>((const float*)x, (const float*)residual, gamma,
-                                                      (const float*)grad_out, mean, rstd, (float*)dx, (float*)dresidual,
-                                                      part, n_rows, D, dropout_p, seed, seed_device);
-  else
-    add_ln_bwd_kernel<__nv_bfloat16><<<grid, 256, smem, st>>>(
-        (const __nv_bfloat16*)x, (const __nv_bfloat16*)residual, gamma, (const __nv_bfloat16*)grad_out, mean, rstd,
-        (__nv_bfloat16*)dx, (__nv_bfloat16*)dresidual, part, n_rows, D, dropout_p, seed, seed_device);
+  const size_t smem = (size_t)8 * add_ln_rpw(D) * 2 * D * sizeof(float);
+#define BWD_F32(LPR, VPL)                                                                                            \
+  add_ln_bwd_kernel<float, LPR, VPL><<<grid, 256, smem, st>>>((const float*)x, (const float*)residual, gamma,        \
+                                                              (const float*)grad_out, mean, rstd, (float*)dx,        \
+                                                              (float*)dresidual, part, n_rows, D, dropout_p, seed,   \
+                                                              seed_device)
+#define BWD_BF16(LPR, VPL)                                                                                           \
+  add_ln_bwd_kernel<__nv_bfloat16, LPR, VPL><<<grid, 256, smem, st>>>(                                               \
+      (const __nv_bfloat16*)x, (const __nv_bfloat16*)residual, gamma, (const __nv_bfloat16*)grad_out, mean, rstd,    \
+      (__nv_bfloat16*)dx, (__nv_bfloat16*)dresidual, part, n_rows, D, dropout_p, seed, seed_device)
+  if (dtype == BDLRU_F32) {
+    ADD_LN_DISPATCH(D, BWD_F32);
+  } else {
+    ADD_LN_DISPATCH(D, BWD_BF16);
+  }
+#undef BWD_F32
+#undef BWD_BF16
   BDLRU_LAUNCHED();
-  add_ln_reduce<<<(2 * D + 127) / 128, 128, 0, st>>>(part, grid, D, dgamma, dbeta);
-  BDLRU_LAUNCHED();
-  return BDLRU_OK;
+  return launch_colsum(part, grid, 2 * D, 2 * D, COLSUM_SPLIT, dgamma, dbeta, D, nullptr, st);
 }

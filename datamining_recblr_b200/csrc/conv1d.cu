@@ -204,19 +204,6 @@ __global__ void __launch_bounds__(256, 2) conv_bwd_kernel(const ConvParams p) {
   }
 }
 
-__global__ void conv_reduce_partials(const float* __restrict__ part, int GY, int C, int W, float* __restrict__ dweight,
-                                     float* __restrict__ dbias) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // over C*(W+1)
-  if (idx >= C * (W + 1)) return;
-  float s = 0.f;
-  for (int g = 0; g < GY; ++g) s += part[(size_t)g * C * (W + 1) + idx];
-  const int c = idx / (W + 1), j = idx % (W + 1);
-  if (j < W)
-    dweight[c * W + j] = s;
-  else if (dbias)
-    dbias[c] = s;
-}
-
 constexpr int kConvS = 8;     // steps per thread, forward
 constexpr int kConvSB = 4;    // steps per chunk, backward
 constexpr int kConvRun = 32;  // time steps per backward work item (walked chunk by chunk with carried halos)
@@ -280,9 +267,7 @@ static int conv_bwd_launch(ConvParams& p, bool silu, float* dweight, float* dbia
     conv_bwd_kernel<T, W, kConvSB, kConvRun, false><<<grid, block, smem, st>>>(p);
   BDLRU_LAUNCHED();
   const int n = p.C * (W + 1);
-  conv_reduce_partials<<<(n + 127) / 128, 128, 0, st>>>(p.part, t.gy, p.C, W, dweight, dbias);
-  BDLRU_LAUNCHED();
-  return BDLRU_OK;
+  return launch_colsum(p.part, t.gy, n, n, COLSUM_CONV, dweight, dbias, W, nullptr, st);
 }
 
 }  // namespace bdlru

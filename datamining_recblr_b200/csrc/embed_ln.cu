@@ -44,7 +44,16 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-template <typename T>
+// LPR lanes cooperate on one token (32 / LPR tokens per warp: D = 64 keeps every lane busy with two tokens per warp);
+// each lane holds VPL 4-channel vectors: D <= 4 * LPR * VPL.
+template <int LPR>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <typename T, int LPR, int VPL>
 __global__ void __launch_bounds__(256) embed_ln_fwd_kernel(const int64_t* __restrict__ ids, const T* __restrict__ table,
                                                            const float* __restrict__ gamma,
                                                            const float* __restrict__ beta, T* __restrict__ out,
@@ -52,20 +61,24 @@ __global__ void __launch_bounds__(256) embed_ln_fwd_kernel(const int64_t* __rest
                                                            long n_tokens, long n_items, int D, float eps, float p,
                                                            uint64_t seed, const uint64_t* __restrict__ seed_dev) {
   if (seed_dev) seed += *seed_dev;  // device-side step counter: lets a captured CUDA graph draw a new mask per replay
-  const int lane = threadIdx.x & 31;
+  constexpr int RPW = 32 / LPR;
+  const int lane = threadIdx.x & 31, sub = lane / LPR, sl = lane % LPR;
   const long gw = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long nw = ((long)gridDim.x * blockDim.x) >> 5;
   const int nvec = D / 4;
-  for (long n = gw; n < n_tokens; n += nw) {
-    long id = ids[n];
+  for (long n0 = gw * RPW; n0 < n_tokens; n0 += nw * RPW) {
+    const long n = n0 + sub;
+    const bool live = n < n_tokens;
+    long id = live ? ids[n] : 0;
     id = id < 0 ? 0 : (id >= n_items ? n_items - 1 : id);
     const T* row = table + id * D;
-    float x[kMaxV][4];
+    float x[VPL][4];
     float s = 0.f;
 #pragma unroll
-    for (int v = 0; v < kMaxV; ++v) {
-      const int vec = lane + 32 * v;
-      if (vec < nvec) {
+    for (int v = 0; v < VPL; ++v) {
+      const int vec = sl + LPR * v;
+      x[v][0] = x[v][1] = x[v][2] = x[v][3] = 0.f;
+      if (live && vec < nvec) {
         IO<T>::load(row + vec * 4, x[v]);
         if (p > 0.f) {
           float m[4];
@@ -76,11 +89,11 @@ __global__ void __launch_bounds__(256) embed_ln_fwd_kernel(const int64_t* __rest
         s += (x[v][0] + x[v][1]) + (x[v][2] + x[v][3]);
       }
     }
-    const float mean = warp_sum(s) / (float)D;
+    const float mean = group_sum<LPR>(s) / (float)D;
     float q = 0.f;
 #pragma unroll
-    for (int v = 0; v < kMaxV; ++v) {
-      if (lane + 32 * v < nvec) {
+    for (int v = 0; v < VPL; ++v) {
+      if (sl + LPR * v < nvec) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const float d = x[v][e] - mean;
@@ -88,11 +101,11 @@ __global__ void __launch_bounds__(256) embed_ln_fwd_kernel(const int64_t* __rest
         }
       }
     }
-    const float rstd = rsqrtf(warp_sum(q) / (float)D + eps);
+    const float rstd = rsqrtf(group_sum<LPR>(q) / (float)D + eps);
 #pragma unroll
-    for (int v = 0; v < kMaxV; ++v) {
-      const int vec = lane + 32 * v;
-      if (vec < nvec) {
+    for (int v = 0; v < VPL; ++v) {
+      const int vec = sl + LPR * v;
+      if (live && vec < nvec) {
         const float4 g4 = *reinterpret_cast<const float4*>(gamma + vec * 4);
         const float4 b4 = *reinterpret_cast<const float4*>(beta + vec * 4);
         float o[4];
@@ -103,52 +116,54 @@ __global__ void __launch_bounds__(256) embed_ln_fwd_kernel(const int64_t* __rest
         IO<T>::store(out + n * D + vec * 4, o);
       }
     }
-    if (lane == 0) {
+    if (live && sl == 0) {
       mean_out[n] = mean;
       rstd_out[n] = rstd;
     }
   }
 }
 
-template <typename T>
+template <typename T, int LPR, int VPL>
 __global__ void __launch_bounds__(256) embed_ln_bwd_kernel(const int64_t* __restrict__ ids, const T* __restrict__ table,
                                                            const float* __restrict__ gamma, const T* __restrict__ dy,
                                                            const float* __restrict__ mean_in,
                                                            const float* __restrict__ rstd_in, float* __restrict__ dtable,
                                                            float* __restrict__ part /* [grid][2][D] */, long n_tokens,
-                                                           long n_items, int D, float p, uint64_t seed, const uint64_t* __restrict__ seed_dev,
-                                                           long padding_idx) {
+                                                           long n_items, int D, float p, uint64_t seed,
+                                                           const uint64_t* __restrict__ seed_dev, long padding_idx) {
+  extern __shared__ float red[];  // [warps * RPW][2][D]
   if (seed_dev) seed += *seed_dev;
-  extern __shared__ float red[];  // [warps][2][D]
+  constexpr int RPW = 32 / LPR;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const int sub = lane / LPR, sl = lane % LPR;
   const long gw = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long nw = ((long)gridDim.x * blockDim.x) >> 5;
   const int nvec = D / 4;
-  float dg[kMaxV][4], db[kMaxV][4];
+  float dg[VPL][4], db[VPL][4];
 #pragma unroll
-  for (int v = 0; v < kMaxV; ++v)
+  for (int v = 0; v < VPL; ++v)
 #pragma unroll
     for (int e = 0; e < 4; ++e) dg[v][e] = db[v][e] = 0.f;
 
-  for (long n = gw; n < n_tokens; n += nw) {
-    long id = ids[n];
+  for (long n0 = gw * RPW; n0 < n_tokens; n0 += nw * RPW) {
+    const long n = n0 + sub;
+    const bool live = n < n_tokens;
+    long id = live ? ids[n] : 0;
     id = id < 0 ? 0 : (id >= n_items ? n_items - 1 : id);
     const T* row = table + id * D;
-    const float mean = mean_in[n], rstd = rstd_in[n];
-    float xh[kMaxV][4], dxh[kMaxV][4], msk[kMaxV][4];
+    const float mean = live ? mean_in[n] : 0.f, rstd = live ? rstd_in[n] : 0.f;
+    float xh[VPL][4], dxh[VPL][4], msk[VPL][4];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int v = 0; v < kMaxV; ++v) {
-      const int vec = lane + 32 * v;
-      if (vec < nvec) {
+    for (int v = 0; v < VPL; ++v) {
+      const int vec = sl + LPR * v;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) xh[v][e] = dxh[v][e] = 0.f, msk[v][e] = 1.f;
+      if (live && vec < nvec) {
         float x[4], g[4];
         IO<T>::load(row + vec * 4, x);
         IO<T>::load(dy + n * D + vec * 4, g);
-        if (p > 0.f) {
-          dropout_scale4(seed, n, vec, p, msk[v]);
-        } else {
-          msk[v][0] = msk[v][1] = msk[v][2] = msk[v][3] = 1.f;
-        }
+        if (p > 0.f) dropout_scale4(seed, n, vec, p, msk[v]);
         const float4 g4 = *reinterpret_cast<const float4*>(gamma + vec * 4);
         const float gm[4] = {g4.x, g4.y, g4.z, g4.w};
 #pragma unroll
@@ -162,12 +177,12 @@ __global__ void __launch_bounds__(256) embed_ln_bwd_kernel(const int64_t* __rest
         }
       }
     }
-    s1 = warp_sum(s1) / (float)D;
-    s2 = warp_sum(s2) / (float)D;
-    if (id != padding_idx) {
+    s1 = group_sum<LPR>(s1) / (float)D;
+    s2 = group_sum<LPR>(s2) / (float)D;
+    if (live && id != padding_idx) {
 #pragma unroll
-      for (int v = 0; v < kMaxV; ++v) {
-        const int vec = lane + 32 * v;
+      for (int v = 0; v < VPL; ++v) {
+        const int vec = sl + LPR * v;
         if (vec < nvec) {
           float4 d;
           d.x = rstd * (dxh[v][0] - s1 - xh[v][0] * s2) * msk[v][0];
@@ -179,40 +194,41 @@ __global__ void __launch_bounds__(256) embed_ln_bwd_kernel(const int64_t* __rest
       }
     }
   }
-  // block reduce dgamma / dbeta over warps -> one partial row per CTA
+  // block reduce dgamma / dbeta over warps and row groups -> one partial row per CTA
 #pragma unroll
-  for (int v = 0; v < kMaxV; ++v) {
-    const int vec = lane + 32 * v;
+  for (int v = 0; v < VPL; ++v) {
+    const int vec = sl + LPR * v;
     if (vec < nvec) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        red[((size_t)warp * 2 + 0) * D + vec * 4 + e] = dg[v][e];
-        red[((size_t)warp * 2 + 1) * D + vec * 4 + e] = db[v][e];
+        red[((size_t)(warp * RPW + sub) * 2 + 0) * D + vec * 4 + e] = dg[v][e];
+        red[((size_t)(warp * RPW + sub) * 2 + 1) * D + vec * 4 + e] = db[v][e];
       }
     }
   }
   __syncthreads();
   for (int idx = threadIdx.x; idx < 2 * D; idx += blockDim.x) {
     float s = 0.f;
-    for (int w = 0; w < nwarp; ++w) s += red[(size_t)w * 2 * D + idx];
+    for (int w = 0; w < nwarp * RPW; ++w) s += red[(size_t)w * 2 * D + idx];
     part[(size_t)blockIdx.x * 2 * D + idx] = s;
   }
 }
 
-__global__ void embed_ln_reduce(const float* __restrict__ part, int grid, int D, float* __restrict__ dgamma,
-                                float* __restrict__ dbeta) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= 2 * D) return;
-  float s = 0.f;
-  for (int g = 0; g < grid; ++g) s += part[(size_t)g * 2 * D + idx];
-  if (idx < D)
-    dgamma[idx] = s;
-  else
-    dbeta[idx - D] = s;
-}
+#define EMBED_DISPATCH(D, CALL)                          \
+  do {                                                   \
+    const int nv_ = (D) / 4;                             \
+    if (nv_ <= 8) { CALL(8, 1); }                        \
+    else if (nv_ <= 16) { CALL(16, 1); }                 \
+    else if (nv_ <= 32) { CALL(32, 1); }                 \
+    else if (nv_ <= 64) { CALL(32, 2); }                 \
+    else { CALL(32, 4); }                                \
+  } while (0)
 
-static int embed_grid(long n_tokens) {
-  long blocks = (n_tokens + 7) / 8;
+static int embed_rpw(int D) { const int nv = D / 4; return nv <= 8 ? 4 : (nv <= 16 ? 2 : 1); }
+
+static int embed_grid(long n_tokens, int D) {
+  const int rpb = 8 * embed_rpw(D);
+  long blocks = (n_tokens + rpb - 1) / rpb;
   const long cap = (long)sm_count() * 8;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
@@ -242,14 +258,22 @@ extern "C" BDLRU_API int bdlru_embed_ln_fwd(const int64_t* ids, const void* tabl
   BDLRU_REQUIRE(aligned(table, 16) && aligned(out, 16) && aligned(gamma, 16) && aligned(beta, 16),
                 "embed_ln_fwd: pointers must be 16-byte aligned");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const int grid = embed_grid(n_tokens);
-  if (dtype == BDLRU_F32)
-    embed_ln_fwd_kernel<float><<<grid, 256, 0, st>>>(ids, (const float*)table, gamma, beta, (float*)out, mean, rstd,
-                                                     n_tokens, n_items, D, eps, dropout_p, seed, seed_device);
-  else
-    embed_ln_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(ids, (const __nv_bfloat16*)table, gamma, beta,
-                                                             (__nv_bfloat16*)out, mean, rstd, n_tokens, n_items, D,
-                                                             eps, dropout_p, seed, seed_device);
+  const int grid = embed_grid(n_tokens, D);
+#define EFWD_F32(LPR, VPL)                                                                                       \
+  embed_ln_fwd_kernel<float, LPR, VPL><<<grid, 256, 0, st>>>(ids, (const float*)table, gamma, beta, (float*)out,   \
+                                                             mean, rstd, n_tokens, n_items, D, eps, dropout_p, seed, \
+                                                             seed_device)
+#define EFWD_BF16(LPR, VPL)                                                                                      \
+  embed_ln_fwd_kernel<__nv_bfloat16, LPR, VPL><<<grid, 256, 0, st>>>(                                              \
+      ids, (const __nv_bfloat16*)table, gamma, beta, (__nv_bfloat16*)out, mean, rstd, n_tokens, n_items, D, eps,   \
+      dropout_p, seed, seed_device)
+  if (dtype == BDLRU_F32) {
+    EMBED_DISPATCH(D, EFWD_F32);
+  } else {
+    EMBED_DISPATCH(D, EFWD_BF16);
+  }
+#undef EFWD_F32
+#undef EFWD_BF16
   BDLRU_LAUNCHED();
   return BDLRU_OK;
 }
@@ -270,24 +294,29 @@ extern "C" BDLRU_API int bdlru_embed_ln_bwd(const int64_t* ids, const void* tabl
                 "embed_ln_bwd: null pointer");
   BDLRU_REQUIRE(aligned(table, 16) && aligned(grad_out, 16) && aligned(dtable, 16) && aligned(gamma, 16),
                 "embed_ln_bwd: pointers must be 16-byte aligned");
-  const int grid = embed_grid(n_tokens);
+  const int grid = embed_grid(n_tokens, D);
   const size_t need = (size_t)grid * 2 * D * sizeof(float);
   BDLRU_REQUIRE(workspace && workspace_bytes >= need, "embed_ln_bwd: workspace too small (%zu < %zu)", workspace_bytes,
                 need);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   float* part = reinterpret_cast<float*>(workspace);
-  const size_t smem = (size_t)8 * 2 * D * sizeof(float);
-  if (dtype == BDLRU_F32)
-    embed_ln_bwd_kernel<float><<<grid, 256, smem, st>>>(ids, (const float*)table, gamma, (const float*)grad_out, mean,
-                                                        rstd, dtable, part, n_tokens, n_items, D, dropout_p, seed,
-                                                        seed_device, padding_idx);
-  else
-    embed_ln_bwd_kernel<__nv_bfloat16><<<grid, 256, smem, st>>>(ids, (const __nv_bfloat16*)table, gamma,
-                                                                (const __nv_bfloat16*)grad_out, mean, rstd, dtable,
-                                                                part, n_tokens, n_items, D, dropout_p, seed,
-                                                                seed_device, padding_idx);
+  const size_t smem = (size_t)8 * embed_rpw(D) * 2 * D * sizeof(float);
+#define EBWD_F32(LPR, VPL)                                                                                         \
+  embed_ln_bwd_kernel<float, LPR, VPL><<<grid, 256, smem, st>>>(ids, (const float*)table, gamma,                     \
+                                                                (const float*)grad_out, mean, rstd, dtable, part,    \
+                                                                n_tokens, n_items, D, dropout_p, seed, seed_device,  \
+                                                                padding_idx)
+#define EBWD_BF16(LPR, VPL)                                                                                        \
+  embed_ln_bwd_kernel<__nv_bfloat16, LPR, VPL><<<grid, 256, smem, st>>>(                                             \
+      ids, (const __nv_bfloat16*)table, gamma, (const __nv_bfloat16*)grad_out, mean, rstd, dtable, part, n_tokens,   \
+      n_items, D, dropout_p, seed, seed_device, padding_idx)
+  if (dtype == BDLRU_F32) {
+    EMBED_DISPATCH(D, EBWD_F32);
+  } else {
+    EMBED_DISPATCH(D, EBWD_BF16);
+  }
+#undef EBWD_F32
+#undef EBWD_BF16
   BDLRU_LAUNCHED();
-  embed_ln_reduce<<<(2 * D + 127) / 128, 128, 0, st>>>(part, grid, D, dgamma, dbeta);
-  BDLRU_LAUNCHED();
-  return BDLRU_OK;
+  return launch_colsum(part, grid, 2 * D, 2 * D, COLSUM_SPLIT, dgamma, dbeta, D, nullptr, st);
 }

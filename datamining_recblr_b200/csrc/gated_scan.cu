@@ -429,18 +429,6 @@ __global__ void __launch_bounds__(256) gscan_bwd_kernel(const GScanParams p) {
   }
 }
 
-// out[c] = scale(c) * sum over CTAs that own channel tile (c / ct_width)
-__global__ void gscan_reduce_partials(const float* __restrict__ part, int grid, int n_ctile, int ctw, int C,
-                                      const float* __restrict__ lambda, float* __restrict__ out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  const int ct = c / ctw, cc = c % ctw;
-  float s = 0.f;
-  for (int blk = ct; blk < grid; blk += n_ctile) s += part[(size_t)blk * ctw + cc];
-  if (lambda) s *= 1.0f / (1.0f + expf(-lambda[c]));  // d softplus(L)/dL = sigmoid(L)
-  out[c] = s;
-}
-
 // ------------------------------------------------------------------------------------------ host side
 struct Tiling {
   int tcn, NS, NT, n_ctile, n_iter, n_units, grid;
@@ -525,14 +513,14 @@ static int launch_bwd(GScanParams& p, float* dLambda, float* dh0_out, void* ws, 
   p.dh0 = (dh0_out && !bcast_h0) ? dh0_out : nullptr;
   kern<<<grid, t.NT, smem, st>>>(p);
   BDLRU_LAUNCHED();
-  const int thr = 128, blocks = (p.C + thr - 1) / thr;
+  // partial row blk holds channel tile blk % n_ctile: viewed as [grid / n_ctile][C] it is a plain column sum
   if (GATED) {
-    gscan_reduce_partials<<<blocks, thr, 0, st>>>(p.part_dc, grid, t.n_ctile, ctw, p.C, p.lambda, dLambda);
-    BDLRU_LAUNCHED();
+    int rc = launch_colsum(p.part_dc, grid / t.n_ctile, p.C, p.C, COLSUM_SIGMOID, dLambda, nullptr, 0, p.lambda, st);
+    if (rc) return rc;
   }
   if (bcast_h0) {
-    gscan_reduce_partials<<<blocks, thr, 0, st>>>(p.part_dh0, grid, t.n_ctile, ctw, p.C, nullptr, dh0_out);
-    BDLRU_LAUNCHED();
+    int rc = launch_colsum(p.part_dh0, grid / t.n_ctile, p.C, p.C, COLSUM_SPLIT, dh0_out, nullptr, p.C, nullptr, st);
+    if (rc) return rc;
   }
   return BDLRU_OK;
 }

@@ -246,6 +246,60 @@ def embed_layernorm(ids, table, gamma, beta, eps=1e-12, dropout_p=0.0, seed=0, p
     return _EmbedLN.apply(ids, table, gamma, beta, eps, dropout_p, seed, padding_idx, seed_dev)
 
 
+def colsum(x2d):
+    """fp32 column sums of a row-major [rows, cols] fp32/bf16 matrix (one streaming pass + deterministic reduce)."""
+    L.require_cuda(x2d)
+    assert x2d.dim() == 2 and x2d.stride(1) == 1
+    rows, cols = x2d.shape
+    out = torch.empty(cols, dtype=torch.float32, device=x2d.device)
+    lib = L.load()
+    nws = lib.bdlru_colsum_workspace_bytes(rows, cols)
+    ws = _workspace(x2d.device, nws)
+    L.check(lib.bdlru_colsum(L.ptr(x2d), rows, cols, x2d.stride(0), L.dtype_tag(x2d), L.ptr(out), L.ptr(ws), nws,
+                             L.stream_ptr(x2d)))
+    return out
+
+
+class _LinearBias(torch.autograd.Function):
+    """y = x W^T + b with the reference's nn.Linear semantics; GEMMs stay cuBLAS, only the bias gradient (a column sum
+    ATen computes with a slow generic reduction) goes through bdlru_colsum."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=None)
+    def forward(ctx, x, weight, bias):
+        if torch.is_autocast_enabled("cuda"):
+            dt = torch.get_autocast_dtype("cuda")
+            x, weight, bias_c = x.to(dt), weight.to(dt), bias.to(dt)
+        else:
+            bias_c = bias
+        ctx.save_for_backward(x, weight)
+        ctx.bias_dtype = bias.dtype
+        with torch.autocast("cuda", enabled=False):
+            return torch.nn.functional.linear(x, weight, bias_c)
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        dy2 = dy.reshape(-1, dy.shape[-1])
+        if not dy2.is_contiguous():
+            dy2 = dy2.contiguous()
+        x2 = x.reshape(-1, x.shape[-1])
+        dx = (dy2 @ weight).view_as(x)
+        dw = dy2.t() @ x2
+        vw = 4 if dy2.dtype == torch.float32 else 8
+        if dy2.shape[1] % vw == 0 and dy2.shape[1] // vw <= 256 and dy2.dtype in (torch.float32, torch.bfloat16):
+            db = colsum(dy2)
+        else:
+            db = dy2.float().sum(0)
+        return dx, dw, db.to(ctx.bias_dtype)
+
+
+def linear_bias(x, weight, bias):
+    """Drop-in for nn.Linear(...)(x) when the layer has a bias (autocast aware)."""
+    return _LinearBias.apply(x, weight, bias)
+
+
 class _AddLN(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, res, gamma, beta, eps, p, seed, seed_dev):

@@ -183,6 +183,13 @@ class RecBLR(SequentialRecommender):
         return scores, ids.long()
 
 
+def _linear(layer, x):
+    """nn.Linear with bias evaluated through ops.linear_bias (same math; fast bias gradient) on CUDA tensors."""
+    if x.is_cuda and layer.bias is not None:
+        return ops.linear_bias(x, layer.weight, layer.bias)
+    return layer(x)
+
+
 def _residual_ln(owner, norm, dropout, x, residual, dropout_ctx, site):
     """LayerNorm(dropout(x) + residual) (RecBLR.py:142 / 221-225) through the fused kernel."""
     D = x.shape[-1]
@@ -263,7 +270,7 @@ class GatedRecurrentLayer(nn.Module):
         x, z = xz.chunk(2, dim=-1)  # strided channel-last views, consumed in place by the kernels
         if not self.disable_conv1d:
             x = ops.causal_conv1d_channel_last(x, self.conv1d.weight.squeeze(1), self.conv1d.bias, silu=True)
-        recurrence, inp = self.gates(x).chunk(2, dim=-1)
+        recurrence, inp = _linear(self.gates, x).chunk(2, dim=-1)
         y = ops.gated_scan(x, recurrence, inp, self.Lambda, h0=self.phantom_state(seq_len), z=z)
         return self.output(y)
 
@@ -279,6 +286,6 @@ class FeedForward(nn.Module):
         self.layer_norm = nn.LayerNorm(d_model, eps=1e-12)
 
     def forward(self, input_tensor, dropout_ctx=None):
-        hidden_states = self.dropout(F.silu(self.w_1(input_tensor)))
-        hidden_states = self.w_2(hidden_states)
+        hidden_states = self.dropout(F.silu(_linear(self.w_1, input_tensor)))
+        hidden_states = _linear(self.w_2, hidden_states)
         return _residual_ln(self, self.layer_norm, self.dropout, hidden_states, input_tensor, dropout_ctx, 2)

@@ -148,6 +148,13 @@ int bdlru_add_ln_bwd(const void* x, const void* residual, const float* gamma, co
                      size_t workspace_bytes, int64_t n_rows, int D, float dropout_p, uint64_t seed,
                      const uint64_t* seed_device, int dtype, void* stream);
 
+/* Column sums of a row-major [n_rows, n_cols] matrix (rows `row_stride` elements apart) -> fp32 out[n_cols]: the bias
+ * gradient of the nn.Linear layers with bias (gates RecBLR.py:165; FFN RecBLR.py:213-214).  n_cols % 4 (fp32) / 8
+ * (bf16) == 0. */
+size_t bdlru_colsum_workspace_bytes(int64_t n_rows, int n_cols);
+int bdlru_colsum(const void* x, int64_t n_rows, int n_cols, int64_t row_stride, int dtype, float* out,
+                 void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Full-sort scoring with fused streaming top-k (RecBLR.py:114-122 + RecBole's scores[:,0] = -inf and
  * torch.topk).  Q [n_users, D] and E [n_rows, D] are bf16 row-major (D % 64 == 0,
