@@ -115,6 +115,73 @@ def gated_scan(xp, r, i, Lambda, h0=None, z=None):
     return out[0] if z is not None else out
 
 
+class _GatedScanPacked(torch.autograd.Function):
+    """Same kernels as _GatedScan with r and i given as the two halves of ONE [B, T, 2C] tensor (the output of the
+    `gates` Linear, RecBLR.py:196): the gradient comes back as one [B, T, 2C] tensor written in place by the kernel, so
+    autograd does not have to concatenate dr and di."""
+
+    @staticmethod
+    def forward(ctx, xp, ri, Lambda, h0, z):
+        L.require_cuda(xp, ri, Lambda, h0, z)
+        B, T, C = xp.shape
+        assert ri.shape == (B, T, 2 * C) and Lambda.shape == (C,) and ri.dtype == xp.dtype
+        dt = L.dtype_tag(xp)
+        xp, ri = L.as_cl(xp), L.as_cl(ri)
+        r, i = ri[..., :C], ri[..., C:]
+        if not (L.cl_ok(r) and L.cl_ok(i)):
+            ri = ri.contiguous()
+            r, i = ri[..., :C], ri[..., C:]
+        Lf = Lambda.detach().float().contiguous()
+        h0f, h0_bs = None, 0
+        if h0 is not None:
+            h0f = h0.detach().float().contiguous()
+            assert h0f.shape in ((C,), (B, C))
+            h0_bs = C if h0f.dim() == 2 else 0
+        h = torch.empty((B, T, C), dtype=xp.dtype, device=xp.device)
+        y = None
+        if z is not None:
+            assert z.shape == (B, T, C) and z.dtype == xp.dtype
+            z = L.as_cl(z)
+            y = torch.empty_like(h)
+        L.check(L.load().bdlru_gated_scan_fwd(L.view3(xp), L.view3(r), L.view3(i), L.ptr(Lf), L.ptr(h0f), h0_bs,
+                                              L.view3(z), L.view3(h), L.view3(y), B, T, C, dt, L.stream_ptr(xp)))
+        ctx.save_for_backward(xp, ri, Lf, h0f, z, h)
+        ctx.h0_bs = h0_bs
+        ctx.lambda_dtype = Lambda.dtype
+        ctx.h0_dtype = h0.dtype if h0 is not None else None
+        if z is not None:
+            ctx.mark_non_differentiable(h)
+            return y, h
+        return h
+
+    @staticmethod
+    def backward(ctx, grad, *unused):
+        xp, ri, Lf, h0f, z, h = ctx.saved_tensors
+        B, T, C = xp.shape
+        dt = L.dtype_tag(xp)
+        r, i = ri[..., :C], ri[..., C:]
+        grad = L.as_cl(grad.to(xp.dtype))
+        dxp = torch.empty_like(h)
+        dri = torch.empty((B, T, 2 * C), dtype=xp.dtype, device=xp.device)
+        dz = torch.empty_like(h) if z is not None else None
+        dLambda = torch.empty(C, dtype=torch.float32, device=xp.device)
+        dh0 = torch.empty_like(h0f) if h0f is not None else None
+        lib = L.load()
+        nws = lib.bdlru_gated_scan_bwd_workspace_bytes(B, T, C)
+        ws = _workspace(xp.device, nws)
+        L.check(lib.bdlru_gated_scan_bwd(L.view3(xp), L.view3(r), L.view3(i), L.ptr(Lf), L.ptr(h0f), ctx.h0_bs,
+                                         L.view3(z), L.view3(h), L.view3(grad), L.view3(dxp), L.view3(dri[..., :C]),
+                                         L.view3(dri[..., C:]), L.view3(dz), L.ptr(dLambda), L.ptr(dh0), L.ptr(ws), nws,
+                                         B, T, C, dt, L.stream_ptr(xp)))
+        return (dxp, dri, dLambda.to(ctx.lambda_dtype), dh0.to(ctx.h0_dtype) if dh0 is not None else None, dz)
+
+
+def gated_scan_packed(xp, ri, Lambda, h0=None, z=None):
+    """gated_scan with (r, i) = ri.chunk(2, -1) passed as one tensor (see _GatedScanPacked)."""
+    out = _GatedScanPacked.apply(xp, ri, Lambda, h0, z)
+    return out[0] if z is not None else out
+
+
 class _ScanCL(torch.autograd.Function):
     @staticmethod
     def forward(ctx, a, b, h0):

@@ -270,8 +270,8 @@ class GatedRecurrentLayer(nn.Module):
         x, z = xz.chunk(2, dim=-1)  # strided channel-last views, consumed in place by the kernels
         if not self.disable_conv1d:
             x = ops.causal_conv1d_channel_last(x, self.conv1d.weight.squeeze(1), self.conv1d.bias, silu=True)
-        recurrence, inp = _linear(self.gates, x).chunk(2, dim=-1)
-        y = ops.gated_scan(x, recurrence, inp, self.Lambda, h0=self.phantom_state(seq_len), z=z)
+        gates = _linear(self.gates, x)  # [B, T, 2C] = (recurrence | input) halves, consumed in place
+        y = ops.gated_scan_packed(x, gates, self.Lambda, h0=self.phantom_state(seq_len), z=z)
         return self.output(y)
 
 

@@ -195,3 +195,24 @@ def test_causal_conv1d_fn_dropin_signature():
                                                 b.astype(np.float32).astype(np.float64))) <= TOL
     with pytest.raises(NotImplementedError):
         causal_conv1d_fn(x=tx.mT, weight=cuda(w), bias=cuda(b), activation="relu")
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_gated_scan_packed_equals_unpacked(dtype):
+    """gated_scan_packed(x, ri) == gated_scan(x, *ri.chunk(2)) bit for bit, forward and every gradient."""
+    rng = np.random.default_rng(3)
+    B, T, C = 3, 77, 128
+    xp, ri, lam, h0, _, z, g = _gated_inputs(rng, B, T, C, dtype)
+    outs = []
+    for packed in (False, True):
+        txp, tri, tz = cuda(xp, dtype, True), cuda(ri, dtype, True), cuda(z, dtype, True)
+        tlam, th0 = cuda(lam, torch.float32, True), cuda(h0, torch.float32, True)
+        if packed:
+            y = _ops().gated_scan_packed(txp, tri, tlam, th0, z=tz)
+        else:
+            r_t, i_t = tri.chunk(2, dim=-1)
+            y = _ops().gated_scan(txp, r_t, i_t, tlam, th0, z=tz)
+        y.backward(cuda(g, dtype))
+        outs.append((y.detach(), txp.grad, tri.grad, tz.grad, tlam.grad, th0.grad))
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
