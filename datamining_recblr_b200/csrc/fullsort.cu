@@ -10,7 +10,8 @@
 // tile t overlaps the MMAs of tile t+1.  Using both user blocks against each E tile halves the L2->SM operand
 // traffic per flop (at D=128 one user block alone would need ~10 TB/s of L2 bandwidth to keep the tensor pipe fed).
 //
-// Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one lane), warps 2.. = epilogue,
+// Warp roles: warps 0-1 = MMA issuers (alternate tiles; warp 0 also owns the TMEM allocation), warp 2 = TMA producer,
+// warps 3.. = epilogue,
 // one warp per 32 TMEM lanes per user block (a warp may only touch TMEM lanes 32*(warp%4)..+31): thread == user.
 //
 // Top-k epilogue: every thread keeps its user's K best (score, id) sorted in REGISTERS (K = 10/16/20/32 by template)
@@ -55,7 +56,7 @@ struct FsParams {
 };
 
 struct FsPlan {
-  int UB, NT, stages, splits, n_ug, threads;
+  int UB, NT, NSTG, stages, splits, n_ug, threads;
   size_t smem;
   long tiles_total;
 };
@@ -66,8 +67,14 @@ struct FsPlan {
 static bool fs_plan(long n_users, long n_rows, int D, int k, FsPlan* pl) {
   (void)k;
   const int n_slab = D / 64;
-  const int NT = D <= 128 ? 96 : 64;
   const int UB = n_users > kTile ? 2 : 1;
+  // BDLRU_FS_NT=64 (tuning): 64-item tiles with 3 accumulator stages instead of 96-item tiles with 2
+  static const int force_nt = getenv("BDLRU_FS_NT") ? atoi(getenv("BDLRU_FS_NT")) : 0;
+  int NT = D <= 128 ? 96 : 64;
+  if (force_nt == 64) NT = 64;
+  int NSTG = 2;
+  if (NT == 64 && UB * (D / 2) + 3 * UB * 64 <= 512) NSTG = 3;
+  pl->NSTG = NSTG;
   const long tiles = (n_rows + NT - 1) / NT;
   const size_t stage = (size_t)n_slab * NT * 128;
   int stages = (int)(((size_t)kMaxSmem - 1024 - 256) / stage);
@@ -84,7 +91,7 @@ static bool fs_plan(long n_users, long n_rows, int D, int k, FsPlan* pl) {
   long want = (long)sm_count() / pl->n_ug;
   if (want < 1) want = 1;
   pl->splits = (int)(want < max_s ? want : max_s);
-  pl->threads = 64 + 128 * UB;
+  pl->threads = 96 + 128 * UB;
   pl->smem = 1024 + (size_t)stages * stage + 256;
   pl->tiles_total = tiles;
   return true;
@@ -107,15 +114,23 @@ __device__ __forceinline__ void topk_insert(float (&ls)[K], int (&li)[K], float 
   }
 }
 
+// 3-input max (FMNMX3 on sm_100): 32 values in 16 instructions instead of 31 — the epilogue's threshold filter is
+// bound by the issue rate of these min/max instructions (measured ~185 cycles per 32-column chunk before).
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
 __device__ __forceinline__ float max32(const float (&v)[32]) {
-  float m[8];
+  float m[10];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) m[i] = fmaxf(fmaxf(v[4 * i], v[4 * i + 1]), fmaxf(v[4 * i + 2], v[4 * i + 3]));
-  return fmaxf(fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3])), fmaxf(fmaxf(m[4], m[5]), fmaxf(m[6], m[7])));
+  for (int i = 0; i < 10; ++i) m[i] = max3(v[3 * i], v[3 * i + 1], v[3 * i + 2]);
+  const float a = max3(m[0], m[1], m[2]), b = max3(m[3], m[4], m[5]), c = max3(m[6], m[7], m[8]);
+  return max3(max3(a, b, c), max3(m[9], v[30], v[31]), -INFINITY);
 }
 
-template <int UB, int MODE, int K, int NT>
-__global__ void __launch_bounds__(64 + 128 * UB, 1)
+template <int UB, int MODE, int K, int NT, int NSTG>
+__global__ void __launch_bounds__(96 + 128 * UB, 1)
 fullsort_kernel(const __grid_constant__ CUtensorMap tmE, const FsParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -129,8 +144,8 @@ fullsort_kernel(const __grid_constant__ CUtensorMap tmE, const FsParams p) {
   uint64_t* e_full = bars + 1;
   uint64_t* e_empty = e_full + kMaxStages;
   uint64_t* acc_full = e_empty + kMaxStages;
-  uint64_t* acc_empty = acc_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint64_t* acc_empty = acc_full + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 4);
 
   // work assignment: consecutive CTAs share an item range and differ in user group -> E tiles hit in L2
   const int ug = blockIdx.x % p.n_ug;
@@ -139,24 +154,24 @@ fullsort_kernel(const __grid_constant__ CUtensorMap tmE, const FsParams p) {
   const long t_end = p.tiles_total * (split + 1) / p.splits;
   const int n_iter = (int)(t_end - t_begin);
   const long user0 = (long)ug * kTile * UB;
-  // TMEM columns: [0, UB*D/2) the user block(s) Q as packed bf16 pairs (A operand), then 2 x UB accumulators of NT
+  // TMEM columns: [0, UB*D/2) the user block(s) Q as packed bf16 pairs (A operand), then NSTG x UB accumulators of NT
   const uint32_t q_cols = (uint32_t)(p.D >> 1);
   const uint32_t acc_col0 = (uint32_t)UB * q_cols;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 2 && lane == 0) {
     tc::prefetch_tensormap(&tmE);
     tc::mbar_init(q_full, 4 * UB);
     for (int s = 0; s < p.stages; ++s) {
       tc::mbar_init(&e_full[s], 1);
       tc::mbar_init(&e_empty[s], 1);
     }
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < NSTG; ++b) {
       tc::mbar_init(&acc_full[b], 1);
       tc::mbar_init(&acc_empty[b], 4 * UB);
     }
     tc::fence_barrier_init();
   }
-  if (warp == 1) {
+  if (warp == 0) {
     tc::tmem_alloc(tmem_slot, 512);
     tc::tmem_relinquish();
   }
@@ -165,7 +180,7 @@ fullsort_kernel(const __grid_constant__ CUtensorMap tmE, const FsParams p) {
   tc::fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
+  if (warp == 2) {
     // ===================================================================== TMA producer (warp stays converged)
     for (int it = 0; it < n_iter; ++it) {
       const int s = it % p.stages;
@@ -183,18 +198,26 @@ fullsort_kernel(const __grid_constant__ CUtensorMap tmE, const FsParams p) {
       }
       __syncwarp();
     }
-  } else if (warp == 1) {
-    // ===================================================================== MMA issuer (warp stays converged)
+  } else if (warp < 2) {
+    // ===================================================================== MMA issuers (warps stay converged)
+    // TWO issuing warps, tile it handled by warp it % 2.  A tcgen05.mma blocks its issuing thread for about the MMA's
+    // execution time and each mbarrier wait costs ~300 cycles even when already satisfied (measured with clock64:
+    // 409 + 328 cycles of waits against 870 of issue per tile), so a single issuer leaves the tensor pipe idle half the
+    // time; with two, one warp's waits overlap the other's MMAs.
     constexpr uint32_t idesc = tc::idesc_bf16_f32(kTile, NT, 0, 0);
     tc::mbar_wait(q_full, 0);
     tc::fence_after_sync();
-    for (int it = 0; it < n_iter; ++it) {
+    long long t_acc = 0, t_ring = 0, t_issue = 0;
+    for (int it = warp; it < n_iter; it += 2) {
       const int s = it % p.stages;
       const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
-      const int b = it & 1;
-      const uint32_t bph = (uint32_t)(it >> 1) & 1u;
+      const int b = it % NSTG;
+      const uint32_t bph = (uint32_t)(it / NSTG) & 1u;
+      const long long c0 = clock64();
       tc::mbar_wait(&acc_empty[b], bph ^ 1u);
+      const long long c1 = clock64();
       tc::mbar_wait(&e_full[s], ph);
+      const long long c2 = clock64();
       tc::fence_after_sync();
       if (tc::elect_one()) {
         const uint32_t e0 = tc::smem_u32(sE + (size_t)s * n_slab * kSlabB);
@@ -220,10 +243,15 @@ fullsort_kernel(const __grid_constant__ CUtensorMap tmE, const FsParams p) {
         tc::umma_commit(&acc_full[b]);  // accumulators complete
       }
       __syncwarp();
+      const long long c3 = clock64();
+      t_acc += c1 - c0; t_ring += c2 - c1; t_issue += c3 - c2;
     }
+    if ((p.dbg & 8) && lane == 0 && blockIdx.x == 0 && n_iter > 1)
+      printf("[fs mma warp %d] tiles %d: wait acc_empty %lld, wait e_full %lld, issue %lld cycles/tile\n", warp, n_iter,
+             t_acc / (n_iter / 2), t_ring / (n_iter / 2), t_issue / (n_iter / 2));
   } else {
     // ===================================================================== epilogue: thread == user
-    const int e = warp - 2;
+    const int e = warp - 3;
     const int ub = e >> 2;
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;          // user row inside the block
@@ -259,12 +287,17 @@ fullsort_kernel(const __grid_constant__ CUtensorMap tmE, const FsParams p) {
     long pos_local = -1;
     if (MODE == MODE_CE && user < p.n_users) pos_local = p.pos[user] - p.id_offset;
     constexpr float kLog2e = 1.4426950408889634f;
+    long long te_wait = 0, te_ld = 0;
+    const long long te_begin = clock64();
     for (int it = 0; it < n_iter; ++it) {
-      const int b = it & 1;
-      const uint32_t bph = (uint32_t)(it >> 1) & 1u;
+      const int b = it % NSTG;
+      const uint32_t bph = (uint32_t)(it / NSTG) & 1u;
       const long base = (t_begin + it) * NT;  // local row index of the tile's first item
       const bool special = (base + NT > p.n_rows) || (p.mask_local >= base && p.mask_local < base + NT);
+      const long long e0c = clock64();
       tc::mbar_wait(&acc_full[b], bph);
+      const long long e1c = clock64();
+      te_wait += e1c - e0c;
       tc::fence_after_sync();
       const uint32_t taddr = lane_addr + acc_col0 + (uint32_t)((b * UB + ub) * NT);
       // The accumulator tile is pulled into registers CH chunks (CH*32 columns) at a time; once the last group has
@@ -287,6 +320,7 @@ fullsort_kernel(const __grid_constant__ CUtensorMap tmE, const FsParams p) {
           tc::fence_before_sync();
           __syncwarp();
           if (lane == 0) tc::mbar_arrive(&acc_empty[b]);
+          te_ld += clock64() - e1c;
         }
         // all CH chunk maxima first (independent trees: ILP), one vote for the common case "nothing to insert"
         float v[CH][32];
@@ -355,6 +389,9 @@ fullsort_kernel(const __grid_constant__ CUtensorMap tmE, const FsParams p) {
         }
       }
     }
+    if ((p.dbg & 8) && lane == 0 && blockIdx.x == 0 && warp == 3 && n_iter > 0)
+      printf("[fs epilogue warp] per tile: total %lld, wait acc_full %lld, ld+release %lld cycles\n",
+             (clock64() - te_begin) / n_iter, te_wait / n_iter, te_ld / n_iter);
     if (user < p.n_users) {
       if (MODE == MODE_TOPK) {
         float* os = p.part_scores + ((size_t)user * p.splits + split) * p.k;
@@ -373,7 +410,7 @@ fullsort_kernel(const __grid_constant__ CUtensorMap tmE, const FsParams p) {
   }
   tc::fence_before_sync();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == 0) {
     tc::fence_after_sync();
     tc::tmem_dealloc(tmem_base, 512);
   }
@@ -505,11 +542,11 @@ static int fs_check(const void* Q, const void* E, long n_users, long n_rows, int
   return BDLRU_OK;
 }
 
-template <int UB, int MODE, int K, int NT>
+template <int UB, int MODE, int K, int NT, int NSTG>
 static int fs_launch_one(const FsPlan& pl, const CUtensorMap& me, const FsParams& p, cudaStream_t st) {
-  BDLRU_CUDA(cudaFuncSetAttribute(fullsort_kernel<UB, MODE, K, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  BDLRU_CUDA(cudaFuncSetAttribute(fullsort_kernel<UB, MODE, K, NT, NSTG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)pl.smem));
-  fullsort_kernel<UB, MODE, K, NT><<<pl.n_ug * pl.splits, pl.threads, pl.smem, st>>>(me, p);
+  fullsort_kernel<UB, MODE, K, NT, NSTG><<<pl.n_ug * pl.splits, pl.threads, pl.smem, st>>>(me, p);
   BDLRU_LAUNCHED();
   return BDLRU_OK;
 }
@@ -517,8 +554,10 @@ static int fs_launch_one(const FsPlan& pl, const CUtensorMap& me, const FsParams
 template <int MODE, int K>
 static int fs_launch_k(const FsPlan& pl, const CUtensorMap& me, const FsParams& p, cudaStream_t st) {
   if (pl.NT == 96)
-    return pl.UB == 2 ? fs_launch_one<2, MODE, K, 96>(pl, me, p, st) : fs_launch_one<1, MODE, K, 96>(pl, me, p, st);
-  return pl.UB == 2 ? fs_launch_one<2, MODE, K, 64>(pl, me, p, st) : fs_launch_one<1, MODE, K, 64>(pl, me, p, st);
+    return pl.UB == 2 ? fs_launch_one<2, MODE, K, 96, 2>(pl, me, p, st) : fs_launch_one<1, MODE, K, 96, 2>(pl, me, p, st);
+  if (pl.NSTG == 3)
+    return pl.UB == 2 ? fs_launch_one<2, MODE, K, 64, 3>(pl, me, p, st) : fs_launch_one<1, MODE, K, 64, 3>(pl, me, p, st);
+  return pl.UB == 2 ? fs_launch_one<2, MODE, K, 64, 2>(pl, me, p, st) : fs_launch_one<1, MODE, K, 64, 2>(pl, me, p, st);
 }
 
 template <int MODE>
