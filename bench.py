@@ -190,7 +190,7 @@ def run_reference(args):
         return
     if args.workload in WORKLOADS:
         w = WORKLOADS[args.workload]
-        base, t = cpu_train_baseline(w, args.steps, max(1, min(args.warmup, 2)), sample_B=args.cpu_sample or 256)
+        base, t = cpu_train_baseline(w, args.steps, max(1, min(args.warmup, 2)), sample_B=args.cpu_sample or 1024)
         line = dict(metric="bdlru_fwd_bwd_seq_tokens_per_s", value=base["value"], unit="seq-tokens/s",
                     config=dict(workload=f"{args.workload}: n_items={w['n_items']} L={w['L']} D={w['D']} "
                                          f"layers={w['layers']} train step (CE over all items + Adam)"),
@@ -279,7 +279,8 @@ def run_train(args):
 
     # ---- timed region: K steps, inputs resident in HBM, CUDA events per step, L2 flushed between steps
     timed = ["bdlru_gated_scan_fwd", "bdlru_gated_scan_bwd", "bdlru_conv1d_fwd", "bdlru_conv1d_bwd",
-             "bdlru_embed_ln_fwd", "bdlru_embed_ln_bwd", "bdlru_fullsort_ce_fwd", "bdlru_fullsort_ce_bwd"]
+             "bdlru_embed_ln_fwd", "bdlru_embed_ln_bwd", "bdlru_fullsort_ce_fwd", "bdlru_fullsort_ce_bwd",
+             "bdlru_add_ln_fwd", "bdlru_add_ln_bwd", "bdlru_colsum"]
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -391,7 +392,8 @@ def run_train(args):
     # bwd reads x', r, i, z, h, g and writes dx', dr, di, dz
     alg = {"bdlru_gated_scan_fwd": 6 * E_l * es, "bdlru_gated_scan_bwd": 10 * E_l * es,
            "bdlru_conv1d_fwd": 2 * E_l * es, "bdlru_conv1d_bwd": 4 * E_l * es,
-           "bdlru_embed_ln_fwd": B * L * (8 + 2 * D * 4), "bdlru_embed_ln_bwd": B * L * (8 + 3 * D * 4)}
+           "bdlru_embed_ln_fwd": B * L * (8 + 2 * D * 4), "bdlru_embed_ln_bwd": B * L * (8 + 3 * D * 4),
+           "bdlru_add_ln_fwd": 3 * B * L * D * es, "bdlru_add_ln_bwd": 5 * B * L * D * es}
     per_kernel = {}
     for name, ts in ktimes.items():
         if ts:
@@ -405,7 +407,7 @@ def run_train(args):
                     note="events bracket the C-ABI call on the launching stream (includes its dLambda/dh0 reduction "
                          "launch); working set is L2-resident at this shape, see DESIGN.md")
 
-    base, _ = cpu_train_baseline(w, steps=3, warmup=1, sample_B=args.cpu_sample or 256) if not args.no_cpu else (None, 0)
+    base, _ = cpu_train_baseline(w, steps=6, warmup=1, sample_B=args.cpu_sample or 1024) if not args.no_cpu else (None, 0)
     line = dict(metric="bdlru_fwd_bwd_seq_tokens_per_s", value=value, unit="seq-tokens/s", n_gpus=world,
                 steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=ms_per_step, higher_is_better=True,
                 scaling="weak", vs_baseline=None, dtype="bf16" if amp else "f32", data="synthetic",
@@ -428,8 +430,8 @@ def run_train(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=0, help="timed steps (default: 200 training / 50 scoring)")
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="beauty", choices=list(WORKLOADS) + list(SCORE_WORKLOADS))
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
@@ -437,6 +439,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-graph", action="store_true", help="run the training step eagerly instead of as a CUDA graph")
     args = ap.parse_args()
+    if args.steps <= 0:
+        args.steps = (5 if args.impl == "reference" else (200 if args.workload in WORKLOADS else 50))
     if args.impl == "reference":
         return run_reference(args)
     if args.workload in WORKLOADS:

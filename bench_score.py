@@ -102,7 +102,7 @@ def run_score(args):
                     algorithmic_flops_per_launch=flops, avg_launch_ms=avg)
     base = None
     if not args.no_cpu:
-        base, _ = cpu_score_baseline(N, D, args.cpu_sample or 64, k, steps=3, warmup=1)
+        base, _ = cpu_score_baseline(N, D, args.cpu_sample or (512 if N <= 1_000_000 else 64), k, steps=6, warmup=1)
     line = dict(metric="fullsort_scored_users_per_s", value=B / (ms_per_step * 1e-3), unit="users/s", n_gpus=world,
                 steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=ms_per_step, higher_is_better=True,
                 scaling="strong", vs_baseline=None, dtype="bf16", data="synthetic",
