@@ -45,6 +45,8 @@ SIGNATURES = {
     "bdlru_add_ln_fwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _i64, _i, _f, _f, _u64, _p, _i, _p]),
     "bdlru_add_ln_bwd_workspace_bytes": (_sz, [_i64, _i]),
     "bdlru_add_ln_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _i64, _i, _f, _u64, _p, _i, _p]),
+    "bdlru_silu_dropout_fwd": (_i, [_p, _p, _i64, _f, _u64, _p, _i, _p]),
+    "bdlru_silu_dropout_bwd": (_i, [_p, _p, _p, _i64, _f, _u64, _p, _i, _p]),
     "bdlru_colsum_workspace_bytes": (_sz, [_i64, _i]),
     "bdlru_colsum": (_i, [_p, _i64, _i, _i64, _i, _p, _p, _sz, _p]),
     "bdlru_fullsort_available": (_i, []),

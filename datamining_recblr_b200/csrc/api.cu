@@ -28,19 +28,20 @@ int sm_count() {
   return n;
 }
 
-__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ part, int n_rows, int row_stride,
+__global__ void __launch_bounds__(1024) colsum_kernel(const float* __restrict__ part, int n_rows, int row_stride,
                                                      int n_cols, int mode, float* __restrict__ out0,
                                                      float* __restrict__ out1, int split, const float* __restrict__ aux) {
-  __shared__ float red[8][33];
+  constexpr int RL = 32;  // row lanes per CTA
+  __shared__ float red[RL][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + tx;
   float s = 0.f;
   if (c < n_cols) {
     float s0 = 0.f, s1 = 0.f;  // two independent chains: the loads of consecutive rows overlap
     int r = ty;
-    for (; r + 8 < n_rows; r += 16) {
+    for (; r + RL < n_rows; r += 2 * RL) {
       s0 += part[(size_t)r * row_stride + c];
-      s1 += part[(size_t)(r + 8) * row_stride + c];
+      s1 += part[(size_t)(r + RL) * row_stride + c];
     }
     if (r < n_rows) s0 += part[(size_t)r * row_stride + c];
     s = s0 + s1;
@@ -50,7 +51,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ p
   if (ty == 0 && c < n_cols) {
     float a = red[0][tx];
 #pragma unroll
-    for (int k = 1; k < 8; ++k) a += red[k][tx];
+    for (int k = 1; k < RL; ++k) a += red[k][tx];
     if (mode == COLSUM_SPLIT) {
       if (c < split) out0[c] = a;
       else if (out1) out1[c - split] = a;
@@ -66,7 +67,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ p
 
 int launch_colsum(const float* part, int n_rows, int row_stride, int n_cols, int mode, float* out0, float* out1,
                   int split, const float* aux, cudaStream_t st) {
-  colsum_kernel<<<(n_cols + 31) / 32, 256, 0, st>>>(part, n_rows, row_stride, n_cols, mode, out0, out1, split, aux);
+  colsum_kernel<<<(n_cols + 31) / 32, 1024, 0, st>>>(part, n_rows, row_stride, n_cols, mode, out0, out1, split, aux);
   BDLRU_LAUNCHED();
   return BDLRU_OK;
 }

@@ -46,7 +46,7 @@ int sm_count();  // SMs of the current device (cached)
 
 // Deterministic second pass of every "per-CTA partials" reduction in this library:
 //     acc[c] = sum_{r < n_rows} part[r * row_stride + c],  c < n_cols
-// 32 columns x 8 row-lanes per CTA (coalesced 128-byte reads, fixed summation order), then an epilogue:
+// 32 columns x 32 row-lanes per CTA (coalesced 128-byte reads, fixed summation order), then an epilogue:
 //   COLSUM_SPLIT   out0[c] = acc[c] for c < split, out1[c - split] = acc[c] otherwise (out1 may be NULL)
 //   COLSUM_SIGMOID out0[c] = acc[c] * sigmoid(aux[c])        (dLambda: d softplus(L)/dL)
 //   COLSUM_CONV    c = ch * (W+1) + j: j < W -> out0[ch * W + j], j == W -> out1[ch]   (split = W)

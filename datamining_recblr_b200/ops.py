@@ -367,6 +367,34 @@ def linear_bias(x, weight, bias):
     return _LinearBias.apply(x, weight, bias)
 
 
+class _SiluDropout(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, p, seed, seed_dev):
+        L.require_cuda(x)
+        xc = x.contiguous()
+        out = torch.empty_like(xc)
+        L.check(L.load().bdlru_silu_dropout_fwd(L.ptr(xc), L.ptr(out), xc.numel(), float(p), int(seed), L.ptr(seed_dev),
+                                                L.dtype_tag(xc), L.stream_ptr(xc)))
+        ctx.save_for_backward(xc)
+        ctx.args = (float(p), int(seed), seed_dev)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        (xc,) = ctx.saved_tensors
+        p, seed, seed_dev = ctx.args
+        dy = dy.to(xc.dtype).contiguous()
+        dx = torch.empty_like(xc)
+        L.check(L.load().bdlru_silu_dropout_bwd(L.ptr(xc), L.ptr(dy), L.ptr(dx), xc.numel(), p, seed, L.ptr(seed_dev),
+                                                L.dtype_tag(xc), L.stream_ptr(xc)))
+        return dx, None, None, None
+
+
+def silu_dropout(x, dropout_p=0.0, seed=0, seed_dev=None):
+    """dropout(silu(x)) in one kernel (RecBLR.py:219-221); numel % 8 == 0."""
+    return _SiluDropout.apply(x, dropout_p, seed, seed_dev)
+
+
 class _AddLN(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, res, gamma, beta, eps, p, seed, seed_dev):

@@ -190,19 +190,30 @@ def _linear(layer, x):
     return layer(x)
 
 
+def _dropout_seed(owner, dropout_ctx, site):
+    """(host seed, device step counter or None) of one fused-dropout call site."""
+    if dropout_ctx is not None and dropout_ctx[1] is not None:
+        return dropout_ctx[0] + 104729 * site, dropout_ctx[1]
+    owner._host_step = getattr(owner, "_host_step", 0) + 1  # standalone layer: advance a host-side step count
+    return (RecBLR._seed_base() + 104729 * site + owner._host_step) & 0x3FFFFFFFFFFFFFFF, None
+
+
+def _silu_dropout(owner, dropout, x, dropout_ctx, site):
+    """dropout(silu(x)) (RecBLR.py:219-221) through the fused kernel."""
+    p = dropout.p if owner.training else 0.0
+    if not x.is_cuda or x.numel() % 8 != 0:
+        return dropout(F.silu(x))
+    seed, seed_dev = _dropout_seed(owner, dropout_ctx, site) if p > 0.0 else (0, None)
+    return ops.silu_dropout(x, dropout_p=p, seed=seed, seed_dev=seed_dev)
+
+
 def _residual_ln(owner, norm, dropout, x, residual, dropout_ctx, site):
     """LayerNorm(dropout(x) + residual) (RecBLR.py:142 / 221-225) through the fused kernel."""
     D = x.shape[-1]
     p = dropout.p if owner.training else 0.0
     if not x.is_cuda or D % 4 != 0 or D > 512:
         return norm(dropout(x) + residual)
-    seed, seed_dev = 0, None
-    if p > 0.0:
-        if dropout_ctx is not None and dropout_ctx[1] is not None:
-            seed, seed_dev = dropout_ctx[0] + 104729 * site, dropout_ctx[1]
-        else:  # standalone layer: advance a host-side step count
-            owner._host_step = getattr(owner, "_host_step", 0) + 1
-            seed = (RecBLR._seed_base() + 104729 * site + owner._host_step) & 0x3FFFFFFFFFFFFFFF
+    seed, seed_dev = _dropout_seed(owner, dropout_ctx, site) if p > 0.0 else (0, None)
     return ops.add_dropout_layernorm(x, residual, norm.weight, norm.bias, eps=norm.eps, dropout_p=p, seed=seed,
                                      seed_dev=seed_dev)
 
@@ -286,6 +297,6 @@ class FeedForward(nn.Module):
         self.layer_norm = nn.LayerNorm(d_model, eps=1e-12)
 
     def forward(self, input_tensor, dropout_ctx=None):
-        hidden_states = self.dropout(F.silu(_linear(self.w_1, input_tensor)))
+        hidden_states = _silu_dropout(self, self.dropout, _linear(self.w_1, input_tensor), dropout_ctx, 3)
         hidden_states = _linear(self.w_2, hidden_states)
         return _residual_ln(self, self.layer_norm, self.dropout, hidden_states, input_tensor, dropout_ctx, 2)

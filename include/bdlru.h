@@ -16,6 +16,8 @@
  *   bdlru_conv1d_fwd / _bwd          causal_conv1d_fn call site RecBLR.py:188-193 (fallback line 185)
  *   bdlru_embed_ln_fwd / _bwd        RecBLR.py:76-78 (embedding gather -> dropout -> LayerNorm)
  *   bdlru_add_ln_fwd / _bwd          RecBLR.py:142, 221-225 (dropout -> + residual -> LayerNorm)
+ *   bdlru_silu_dropout_fwd / _bwd    RecBLR.py:219-221 (FFN activation + dropout)
+ *   bdlru_colsum                     bias gradients of the nn.Linear layers with bias (RecBLR.py:165, 213-214)
  *   bdlru_fullsort_topk              RecBLR.py:114-122 + RecBole mask/top-k ([upstream])
  *   bdlru_fullsort_ce_fwd / _bwd     RecBLR.py:99-103 (logits GEMM + nn.CrossEntropyLoss, mean)
  */
@@ -147,6 +149,13 @@ int bdlru_add_ln_bwd(const void* x, const void* residual, const float* gamma, co
                      const float* rstd, void* dx, void* dresidual, float* dgamma, float* dbeta, void* workspace,
                      size_t workspace_bytes, int64_t n_rows, int D, float dropout_p, uint64_t seed,
                      const uint64_t* seed_device, int dtype, void* stream);
+
+/* FeedForward activation (RecBLR.py:219-221): out = dropout(silu(x)) over n contiguous elements (n % 8 == 0, 16-byte aligned), and its
+ * backward dx = grad_out * mask * silu'(x) with the mask regenerated from (seed [+ *seed_device], element index). */
+int bdlru_silu_dropout_fwd(const void* x, void* out, int64_t n, float dropout_p, uint64_t seed,
+                           const uint64_t* seed_device, int dtype, void* stream);
+int bdlru_silu_dropout_bwd(const void* x, const void* grad_out, void* dx, int64_t n, float dropout_p, uint64_t seed,
+                           const uint64_t* seed_device, int dtype, void* stream);
 
 /* Column sums of a row-major [n_rows, n_cols] matrix (rows `row_stride` elements apart) -> fp32 out[n_cols]: the bias
  * gradient of the nn.Linear layers with bias (gates RecBLR.py:165; FFN RecBLR.py:213-214).  n_cols % 4 (fp32) / 8
