@@ -285,7 +285,10 @@ fullsort_kernel(const __grid_constant__ CUtensorMap tmE, const FsParams p) {
     }
     float run_m = -INFINITY, run_s = 0.f;   // CE: online max / sum of exp
     long pos_local = -1;
-    if (MODE == MODE_CE && user < p.n_users) pos_local = p.pos[user] - p.id_offset;
+    if (MODE == MODE_CE && user < p.n_users) {
+      pos_local = p.pos[user] - p.id_offset;
+      if (pos_local >= p.n_rows) pos_local = -1;  // positive lives in another shard (its tail rows are masked here)
+    }
     constexpr float kLog2e = 1.4426950408889634f;
     long long te_wait = 0, te_ld = 0;
     const long long te_begin = clock64();

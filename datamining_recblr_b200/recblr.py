@@ -70,6 +70,8 @@ def _cfg(config, key, default=None):
 class RecBLR(SequentialRecommender):
     """RecBLR.py:18-122.  Extra (optional) config keys, all defaulting to the fast path:
         ce_impl      'fused' (tcgen05 online-softmax CE, bf16 operands / fp32 accumulate) | 'dense' (fp32 logits)
+                     | 'sharded' (data parallel step, CE row-sharded over torch.distributed's default group: the loss is
+                       the GLOBAL mean, sum gradients over ranks afterwards — sharded.data_parallel_sharded_ce)
         fused_front  True: gather+dropout+LayerNorm in one kernel
     """
 
@@ -157,7 +159,10 @@ class RecBLR(SequentialRecommender):
             neg_score = torch.sum(seq_output * self.item_embedding(neg_items), dim=-1)
             return self.loss_fct(pos_score, neg_score)
         table = self.item_embedding.weight
-        if self.ce_impl == "fused" and ops.fullsort_supported(self.hidden_size):
+        if self.ce_impl == "sharded" and ops.fullsort_supported(self.hidden_size):
+            from .sharded import data_parallel_sharded_ce
+            return data_parallel_sharded_ce(seq_output, table, pos_items)
+        if self.ce_impl in ("fused", "sharded") and ops.fullsort_supported(self.hidden_size):
             return ops.fullsort_cross_entropy(seq_output, table, pos_items)
         logits = torch.matmul(seq_output, table.transpose(0, 1))
         return self.loss_fct(logits, pos_items)

@@ -58,26 +58,67 @@ def combine_ce_stats(row_max, row_sum, pos_logit, group=None):
 
 class _ShardedCE(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, q, table_shard, pos, id_offset, group):
+    def forward(ctx, q, table_shard, pos, id_offset, group, reduce_dq):
         qb, eb = ops._bf16_rows(q), ops._bf16_rows(table_shard)
         m, s, pl = ops.fullsort_ce_stats(qb, eb, pos, id_offset=id_offset)
         lse, pl = combine_ce_stats(m, s, pl, group)
         ctx.save_for_backward(qb, eb, pos, lse)
-        ctx.meta = (id_offset, group, q.dtype, table_shard.dtype)
+        ctx.meta = (id_offset, group, q.dtype, table_shard.dtype, reduce_dq)
         return (lse - pl).mean()
 
     @staticmethod
     def backward(ctx, grad_loss):
         qb, eb, pos, lse = ctx.saved_tensors
-        id_offset, group, qd, ed = ctx.meta
+        id_offset, group, qd, ed, reduce_dq = ctx.meta
         dQ, dE = ops.fullsort_ce_grads(qb, eb, pos, lse, 1.0 / qb.shape[0], id_offset=id_offset)
-        if _world(group) > 1:  # every shard contributes P_shard E_shard to dQ; dE is shard-local
+        if reduce_dq and _world(group) > 1:  # every shard contributes P_shard E_shard to dQ; dE is shard-local
             dist.all_reduce(dQ, op=dist.ReduceOp.SUM, group=group)
         g = grad_loss.float()
-        return (dQ * g).to(qd), (dE * g).to(ed), None, None, None
+        return (dQ * g).to(qd), (dE * g).to(ed), None, None, None, None
 
 
-def sharded_cross_entropy(q, table_shard, pos, id_offset, group=None):
+def sharded_cross_entropy(q, table_shard, pos, id_offset, group=None, reduce_dq=True):
     """Mean full-softmax CE over the whole sharded table; q [B, D] and pos [B] (GLOBAL ids) identical on every rank.
-    Gradients: dq is the full gradient on every rank, dtable_shard is this rank's rows."""
-    return _ShardedCE.apply(q, table_shard, pos.contiguous(), int(id_offset), group)
+    Gradients: dtable_shard is this rank's rows; dq is the full gradient on every rank (one all-reduce) unless
+    reduce_dq=False, in which case it is this shard's partial and the caller sums it (e.g. the reduce-scatter in the
+    backward of an autograd-aware all-gather)."""
+    return _ShardedCE.apply(q, table_shard, pos.contiguous(), int(id_offset), group, bool(reduce_dq))
+
+
+# ----------------------------------------------------------------------------- data parallel + sharded CE (configs[4])
+def data_parallel_sharded_ce(seq_output, table, pos_items, group=None):
+    """Loss of a DATA-PARALLEL step whose full-softmax CE is SHARDED by item rows (BASELINE.json configs[4]).
+
+    Every rank holds the whole (replicated) item table `table [n_items, D]` — it needs it for the input gather — but
+    scores only its row shard: the per-rank seq_output [B, D] / pos_items [B] are all-gathered (autograd-aware), every
+    rank computes the CE statistics and gradients of ALL G*B users against rows [lo, hi) with the fused kernels, and
+    the result is the GLOBAL mean loss (identical on every rank).  Backward: the all-gather's backward sums the per-shard
+    dQ partials over ranks and hands each rank its own users' slice; dE lands in rows [lo, hi) of `table.grad` only.
+    Because the loss is already the global mean, gradients must be SUMMED over ranks afterwards
+    (`allreduce_gradients(params, average=False)`): for the table that sum also assembles the per-shard CE rows."""
+    world = _world(group)
+    if world == 1:
+        return ops.fullsort_cross_entropy(seq_output, table, pos_items)
+    from torch.distributed.nn.functional import all_gather
+    rank = dist.get_rank(group)
+    q_all = torch.cat(all_gather(seq_output.contiguous(), group=group), dim=0)
+    pos_list = [torch.empty_like(pos_items) for _ in range(world)]
+    dist.all_gather(pos_list, pos_items.contiguous(), group=group)
+    b = shard_bounds(table.shape[0], world)
+    # the all_gather's backward reduce-scatters the per-shard dQ partials: no extra all-reduce inside the CE
+    return sharded_cross_entropy(q_all, table[b[rank]:b[rank + 1]], torch.cat(pos_list), id_offset=b[rank], group=group,
+                                 reduce_dq=False)
+
+
+def allreduce_gradients(params, group=None, average=True):
+    """One flat NCCL all-reduce over the gradients of `params` (mean for an ordinary data-parallel loss, sum when the
+    loss is already a global mean as in data_parallel_sharded_ce)."""
+    if _world(group) == 1:
+        return
+    ps = [p for p in params if p.grad is not None]
+    flat = torch.cat([p.grad.reshape(-1) for p in ps])
+    dist.all_reduce(flat, op=dist.ReduceOp.AVG if average else dist.ReduceOp.SUM, group=group)
+    off = 0
+    for p in ps:
+        p.grad.copy_(flat[off:off + p.numel()].view_as(p))
+        off += p.numel()

@@ -40,9 +40,36 @@ def main():
     assert abs(float(l1) - float(l2)) <= 1e-6 * abs(float(l1)), (float(l1), float(l2))
     assert (qs.grad - qf.grad).abs().max() <= 2e-2 * qf.grad.abs().max()
     assert (ts.grad - tf.grad[b[rank]:b[rank + 1]]).abs().max() <= 2e-2 * tf.grad.abs().max()
+    # configs[4]: data-parallel model step with the CE row-sharded over the ranks == one process on the concatenated batch
+    from datamining_recblr_b200.recblr import RecBLR
+    from oracle.reference_loader import FakeDataset, make_config
+    from oracle import torch_port as TP
+    n_items, L, Bl = 3001, 50, 64
+    torch.manual_seed(3)
+    cfgs = {}
+    for impl in ("fused", "sharded"):
+        cfg = make_config(hidden_size=64, num_layers=2, dropout_prob=0.0, max_len=L, ce_impl=impl)
+        cfg["device"] = dev
+        cfgs[impl] = cfg
+    torch.manual_seed(3)
+    ref_model = RecBLR(cfgs["fused"], FakeDataset(n_items)).to(dev)
+    dp_model = RecBLR(cfgs["sharded"], FakeDataset(n_items)).to(dev)
+    dp_model.load_state_dict(ref_model.state_dict())
+    seq, lens, tgt = TP.synthetic_batch(Bl * world, L, n_items, seed=9)
+    full = {"item_id_list": seq.to(dev), "item_length": lens.to(dev), "item_id": tgt.to(dev)}
+    mine = {k: v[rank * Bl:(rank + 1) * Bl] for k, v in full.items()}
+    ref_loss = ref_model.calculate_loss(full)
+    ref_loss.backward()
+    dp_loss = dp_model.calculate_loss(mine)
+    dp_loss.backward()
+    sharded.allreduce_gradients(dp_model.parameters(), average=False)
+    assert abs(float(ref_loss) - float(dp_loss)) <= 1e-5 * abs(float(ref_loss)), (float(ref_loss), float(dp_loss))
+    for (n1, p1), (n2, p2) in zip(ref_model.named_parameters(), dp_model.named_parameters()):
+        den = p1.grad.abs().max().clamp_min(1e-12)
+        assert (p1.grad - p2.grad).abs().max() <= 3e-2 * den, (n1, float((p1.grad - p2.grad).abs().max()), float(den))
     dist.barrier()
     if rank == 0:
-        print(f"dist_check ok: world={world} loss={float(l1):.6f}")
+        print(f"dist_check ok: world={world} loss={float(l1):.6f} dp_sharded_ce_loss={float(dp_loss):.6f}")
     dist.destroy_process_group()
 
 

@@ -148,3 +148,19 @@ def test_sharded_paths_on_two_gpus():
                         "--master-addr", "127.0.0.1", "--master-port", "29631", os.path.join(root, "tests", "dist_check.py")],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "dist_check ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_ce_stats_shard_with_positive_outside_tail_tile():
+    """Regression: a user whose positive item lives in ANOTHER shard, at a global id that falls inside this shard's last
+    (partial, masked) tile, must keep pos_logit = 0 instead of picking up the -inf of a masked tail row."""
+    from datamining_recblr_b200 import ops
+    rng = np.random.default_rng(1)
+    B, N, D = 64, 1500, 64          # 1500 = 15 * 96 + 60: the last tile covers ids 1440..1535
+    qb, eb = _bf(rng.normal(size=(B, D))), _bf(rng.normal(size=(N, D)) * 0.1)
+    pos = np.full(B, 1510)          # outside [0, 1500) but inside the tail tile's id range
+    pos[:5] = [0, 7, 1499, 1441, 1500]
+    m, s, pl = ops.fullsort_ce_stats(qb.cuda(), eb.cuda(), torch.tensor(pos).cuda())
+    logits = qb.double().numpy() @ eb.double().numpy().T
+    assert torch.isfinite(pl).all()
+    assert np.abs(pl[:4].cpu().numpy() - logits[np.arange(4), pos[:4]]).max() <= 1e-5 * np.abs(logits).max()
+    assert float(pl[4:].abs().max()) == 0.0

@@ -1,0 +1,38 @@
+"""Throughput of the fused CE forward / backward kernels at a large shape (tuning aid)."""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from datamining_recblr_b200 import ops  # noqa: E402
+
+B, N, D = int(sys.argv[1]) if len(sys.argv) > 1 else 8192, int(sys.argv[2]) if len(sys.argv) > 2 else 1_000_000, 128
+g = torch.Generator(device="cuda").manual_seed(0)
+q = torch.randn(B, D, device="cuda", generator=g).to(torch.bfloat16)
+e = (torch.randn(N, D, device="cuda", generator=g) * 0.05).to(torch.bfloat16)
+pos = torch.randint(0, N, (B,), device="cuda", generator=g)
+
+
+def timeit(fn, n=5):
+    for _ in range(2):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(n):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        b.synchronize()
+        ts.append(a.elapsed_time(b))
+    return sorted(ts)[len(ts) // 2]
+
+
+m, s, pl = ops.fullsort_ce_stats(q, e, pos)
+lse = m + torch.log(s)
+t_f = timeit(lambda: ops.fullsort_ce_stats(q, e, pos))
+t_b = timeit(lambda: ops.fullsort_ce_grads(q, e, pos, lse, 1.0 / B))
+fl = 2.0 * B * N * D
+print(f"B={B} N={N} D={D}: ce fwd {t_f:.3f} ms = {fl / t_f / 1e9:.0f} TFLOP/s;  ce bwd (dQ+dE) {t_b:.3f} ms = "
+      f"{2 * fl / t_b / 1e9:.0f} TFLOP/s credited (4 GEMM-passes executed: {4 * fl / t_b / 1e9:.0f} TFLOP/s)")
