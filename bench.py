@@ -35,6 +35,9 @@ WORKLOADS = {
     # name: n_items, L, D, layers, train B, eval B
     "beauty": dict(n_items=12102, L=50, D=64, layers=2, B=2048, eval_B=4096),
     "ml1m": dict(n_items=3417, L=200, D=64, layers=2, B=2048, eval_B=4096),
+    # configs[4] (S-train): large catalog, data parallel + row-sharded full-softmax CE; strain1m is the 10x smaller probe
+    "strain1m": dict(n_items=1_000_000, L=200, D=128, layers=2, B=8192, eval_B=4096, big=True),
+    "strain10m": dict(n_items=10_000_000, L=200, D=128, layers=2, B=8192, eval_B=4096, big=True),
 }
 SCORE_WORKLOADS = {"score1m": 1_000_000, "score10m": 10_000_000}
 
@@ -190,7 +193,7 @@ def run_reference(args):
         return
     if args.workload in WORKLOADS:
         w = WORKLOADS[args.workload]
-        base, t = cpu_train_baseline(w, args.steps, max(1, min(args.warmup, 2)), sample_B=args.cpu_sample or 1024)
+        base, t = cpu_train_baseline(w, args.steps, max(1, min(args.warmup, 2)), sample_B=args.cpu_sample or (16 if w.get("big") else 1024))
         line = dict(metric="bdlru_fwd_bwd_seq_tokens_per_s", value=base["value"], unit="seq-tokens/s",
                     config=dict(workload=f"{args.workload}: n_items={w['n_items']} L={w['L']} D={w['D']} "
                                          f"layers={w['layers']} train step (CE over all items + Adam)"),
@@ -223,20 +226,24 @@ def run_train(args):
     w = WORKLOADS[args.workload]
     B, L, D = w["B"], w["L"], w["D"]
     torch.manual_seed(2020)
-    model = RecBLR(make_config(w, dev), _DS(w["n_items"])).to(dev)
+    big = bool(w.get("big"))
+    cfg = make_config(w, dev)
+    if big and world > 1:
+        cfg["ce_impl"] = "sharded"   # global-mean loss: gradients are SUMMED over ranks
+    model = RecBLR(cfg, _DS(w["n_items"])).to(dev)
     opt = torch.optim.Adam(model.parameters(), lr=1e-3, fused=True, capturable=True)
     params = [p for p in model.parameters()]
     amp = args.dtype == "bf16"
 
     # distinct batches per step (and per rank): > L2 is not reachable at this shape, so L2 is flushed between steps
-    n_batches = 4
+    n_batches = 2 if w.get("big") else 4
     host = [synthetic_batch(B, L, w["n_items"], seed=2020 + 97 * rank + i) for i in range(n_batches)]
     host = [tuple(t.pin_memory() for t in b) for b in host]
     devb = [tuple(t.to(dev) for t in b) for b in host]
 
     def allreduce_grads(ps):  # data-parallel gradient all-reduce (mean), one flat NCCL call
         flat = torch.cat([p.grad.reshape(-1) for p in ps])
-        dist.all_reduce(flat, op=dist.ReduceOp.AVG)
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM if model.ce_impl == "sharded" else dist.ReduceOp.AVG)
         off = 0
         for p in ps:
             p.grad.copy_(flat[off:off + p.numel()].view_as(p))
@@ -255,7 +262,7 @@ def run_train(args):
 
     model.train()
     graphed = None
-    if not args.no_graph:
+    if not args.no_graph and not big:   # the large-catalog step is not launch-bound; it runs eagerly
         from datamining_recblr_b200.train_step import GraphedTrainStep
         ex = {"item_id_list": devb[0][0], "item_length": devb[0][1], "item_id": devb[0][2]}
         graphed = GraphedTrainStep(model, opt, ex, autocast_dtype=torch.bfloat16 if amp else None,
@@ -400,14 +407,29 @@ def run_train(args):
             per_kernel[name] = dict(calls_per_step=len(ts) / eager_steps, avg_ms=sum(ts) / len(ts),
                                     share_of_step=(sum(ts) / eager_steps) / ms_per_step if world == 1 else None,
                                     gbs=(alg[name] / (sum(ts) / len(ts)) / 1e6) if name in alg else None)
-    dom = max((n for n in per_kernel if n in alg), key=lambda n: per_kernel[n]["avg_ms"] * per_kernel[n]["calls_per_step"])
-    roofline = dict(bound="hbm", kernel=dom, achieved=per_kernel[dom]["gbs"], peak=P["hbm"], unit="GB/s",
-                    frac=per_kernel[dom]["gbs"] / P["hbm"], traffic=None, peak_source=P["src"],
-                    algorithmic_bytes_per_launch=alg[dom], avg_launch_ms=per_kernel[dom]["avg_ms"],
-                    note="events bracket the C-ABI call on the launching stream (includes its dLambda/dh0 reduction "
-                         "launch); working set is L2-resident at this shape, see DESIGN.md")
+    Bce = B * world if model.ce_impl == "sharded" else B
+    Nce = w["n_items"] // world if model.ce_impl == "sharded" else w["n_items"]
+    flops = {"bdlru_fullsort_ce_fwd": 2.0 * Bce * Nce * D, "bdlru_fullsort_ce_bwd": 4.0 * Bce * Nce * D}
+    for name, f in flops.items():
+        if name in per_kernel:
+            per_kernel[name]["tflops"] = f / (per_kernel[name]["avg_ms"] * 1e-3) / 1e12
+    cand = [n for n in per_kernel if n in alg or n in flops]
+    dom = max(cand, key=lambda n: per_kernel[n]["avg_ms"] * per_kernel[n]["calls_per_step"])
+    if dom in flops:
+        roofline = dict(bound="tensor", kernel=dom, achieved=per_kernel[dom]["tflops"], peak=P["tf_sustained"],
+                        unit="TFLOP/s", frac=per_kernel[dom]["tflops"] / P["tf_sustained"], traffic=None,
+                        peak_source=P["src"] + " (sustained bf16 cuBLAS)", algorithmic_flops_per_launch=flops[dom],
+                        avg_launch_ms=per_kernel[dom]["avg_ms"],
+                        note="credited flops: 2*B*N*D forward, 4*B*N*D backward (dQ and dE; the recompute GEMMs are not credited)")
+    else:
+        roofline = dict(bound="hbm", kernel=dom, achieved=per_kernel[dom]["gbs"], peak=P["hbm"], unit="GB/s",
+                        frac=per_kernel[dom]["gbs"] / P["hbm"], traffic=None, peak_source=P["src"],
+                        algorithmic_bytes_per_launch=alg[dom], avg_launch_ms=per_kernel[dom]["avg_ms"],
+                        note="events bracket the C-ABI call on the launching stream (includes its dLambda/dh0 reduction "
+                             "launch); working set is L2-resident at this shape, see DESIGN.md")
 
-    base, _ = cpu_train_baseline(w, steps=6, warmup=1, sample_B=args.cpu_sample or 1024) if not args.no_cpu else (None, 0)
+    base, _ = (cpu_train_baseline(w, steps=3 if big else 6, warmup=1, sample_B=args.cpu_sample or (16 if big else 1024))
+               if not args.no_cpu else (None, 0))
     line = dict(metric="bdlru_fwd_bwd_seq_tokens_per_s", value=value, unit="seq-tokens/s", n_gpus=world,
                 steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=ms_per_step, higher_is_better=True,
                 scaling="weak", vs_baseline=None, dtype="bf16" if amp else "f32", data="synthetic",
@@ -440,7 +462,8 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="run the training step eagerly instead of as a CUDA graph")
     args = ap.parse_args()
     if args.steps <= 0:
-        args.steps = (5 if args.impl == "reference" else (200 if args.workload in WORKLOADS else 50))
+        big_w = args.workload in WORKLOADS and WORKLOADS[args.workload].get("big")
+        args.steps = (5 if args.impl == "reference" else (20 if big_w else (200 if args.workload in WORKLOADS else 50)))
     if args.impl == "reference":
         return run_reference(args)
     if args.workload in WORKLOADS:

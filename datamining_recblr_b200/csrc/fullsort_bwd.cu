@@ -10,8 +10,8 @@
 // so each gradient recomputes the logits once on the tensor cores (4 GEMM passes in total instead of the 3 of a
 // materialising implementation; no atomics, deterministic).
 //
-// Per CTA (192 threads): warp 0 streams Y tiles by TMA (128-byte-swizzled slabs), warp 1 issues tcgen05.mma, warps 2-5
-// are the softmax warps (thread == row, TMEM lane quarter == warp % 4).  TMEM columns:
+// Per CTA: warp 0 issues GEMM1, warp 1 issues GEMM2, warp 2 streams Y tiles by TMA (128-byte-swizzled slabs), warps 3-10
+// are two groups of softmax warps (thread == row, TMEM lane quarter == warp % 4; group g owns accumulator stage g).  TMEM columns:
 //   X  (A of GEMM1, packed bf16 pairs, written once per row block with tcgen05.st)        D/2
 //   dX (fp32 accumulator of GEMM2, lives across the whole column loop)                   D
 //   S  x NSTG (GEMM1 accumulator, [128, NT] fp32)                                          NSTG * NT
@@ -19,8 +19,7 @@
 // GEMM1: S = X Y^T       M=128, N=NT, K=D : A from TMEM, B = Y slab as K-major (channels contiguous).
 // GEMM2: dX += P Y       M=128, N=D, K=NT : A from TMEM, B = THE SAME shared-memory bytes described as MN-major
 //                                            (N = channels contiguous inside a swizzled 128-byte row, K = tile rows).
-// The MMA warp runs GEMM1 of tile t+1 before GEMM2 of tile t, so the tensor pipe works while the softmax warps turn
-// S(t) into P(t).
+// GEMM1 of tile t+1 is in flight while the other softmax group turns S(t) into P(t) and GEMM2 of tile t-1 runs.
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -47,7 +46,7 @@ struct BwdParams {
 };
 
 template <bool TRANSPOSED, int NT, int NSTG>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(96 + 128 * NSTG, 1)
 ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const BwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -55,17 +54,18 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const BwdParams p) {
   const int n_slab = p.D >> 6;
   constexpr uint32_t kSlabB = NT * 128;
   constexpr int NCH = NT / 32;
+  constexpr int NG = NSTG;                 // softmax warp groups: group g owns accumulator / P stage g
   uint8_t* sY = smem;
-  float* col_lse = reinterpret_cast<float*>(sY + (size_t)p.stages * n_slab * kSlabB);  // [4 warps][NT]
-  int* col_pos = reinterpret_cast<int*>(col_lse + 4 * NT);                              // [4 warps][NT]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(col_pos + 4 * NT);
+  float* col_lse = reinterpret_cast<float*>(sY + (size_t)p.stages * n_slab * kSlabB);  // [8 warps][NT]
+  int* col_pos = reinterpret_cast<int*>(col_lse + 8 * NT);                              // [8 warps][NT]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(col_pos + 8 * NT);
   uint64_t* y_full = bars;
   uint64_t* y_empty = y_full + kBwdMaxStages;
   uint64_t* s_full = y_empty + kBwdMaxStages;
-  uint64_t* s_empty = s_full + NSTG;
-  uint64_t* p_full = s_empty + NSTG;
-  uint64_t* p_empty = p_full + NSTG;
-  uint64_t* x_full = p_empty + NSTG;
+  uint64_t* s_empty = s_full + 2;
+  uint64_t* p_full = s_empty + 2;
+  uint64_t* p_empty = p_full + 2;
+  uint64_t* x_full = p_empty + 2;
   uint64_t* dx_full = x_full + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dx_full + 1);
 
@@ -74,7 +74,7 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const BwdParams p) {
   const uint32_t s_col = dx_col + (uint32_t)p.D;
   const uint32_t p_col = s_col + NSTG * NT;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 2 && lane == 0) {
     tc::prefetch_tensormap(&tmY);
     for (int s = 0; s < p.stages; ++s) {
       tc::mbar_init(&y_full[s], 1);
@@ -86,11 +86,11 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const BwdParams p) {
       tc::mbar_init(&p_full[b], 4);
       tc::mbar_init(&p_empty[b], 1);
     }
-    tc::mbar_init(x_full, 4);
+    tc::mbar_init(x_full, 4 * NG);
     tc::mbar_init(dx_full, 1);
     tc::fence_barrier_init();
   }
-  if (warp == 1) {
+  if (warp == 0) {
     tc::tmem_alloc(tmem_slot, 512);
     tc::tmem_relinquish();
   }
@@ -101,7 +101,7 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const BwdParams p) {
 
   const long n_work = p.row_blocks * p.splits;
   // every role walks the same (work item, tile) sequence; g counts tiles globally for ring / stage parities
-  if (warp == 0) {
+  if (warp == 2) {
     // ===================================================================== TMA producer
     long g = 0;
     for (long w = blockIdx.x; w < n_work; w += gridDim.x) {
@@ -119,23 +119,23 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const BwdParams p) {
         __syncwarp();
       }
     }
-  } else if (warp == 1) {
-    // ===================================================================== MMA issuer
+  } else if (warp == 0) {
+    // ===================================================================== GEMM1 issuer:  S(t) = X Y(t)^T
+    // GEMM1 and GEMM2 are issued by DIFFERENT warps: a tcgen05.mma blocks its issuing thread for about its execution
+    // time and every mbarrier wait costs ~300 cycles, so one issuer serialises waits and MMAs (see fullsort.cu).
     constexpr uint32_t idesc1 = tc::idesc_bf16_f32(kRows, NT, 0, 0);
-    const uint32_t idesc2 = tc::idesc_bf16_f32(kRows, p.D, 0, 1);  // B is MN-major in GEMM2
     long g = 0;
     uint32_t wi = 0;
     for (long w = blockIdx.x; w < n_work; w += gridDim.x, ++wi) {
       const int split = (int)(w / p.row_blocks);
       const long t0 = p.tiles_total * split / p.splits, t1 = p.tiles_total * (split + 1) / p.splits;
-      const long n_t = t1 - t0;
       tc::mbar_wait(x_full, wi & 1u);
       tc::fence_after_sync();
-      auto gemm1 = [&](long gg) {
-        const int s = (int)(gg % p.stages);
-        const uint32_t ph = (uint32_t)(gg / p.stages) & 1u;
-        const int b = (int)(gg % NSTG);
-        const uint32_t bph = (uint32_t)(gg / NSTG) & 1u;
+      for (long t = t0; t < t1; ++t, ++g) {
+        const int s = (int)(g % p.stages);
+        const uint32_t ph = (uint32_t)(g / p.stages) & 1u;
+        const int b = (int)(g % NSTG);
+        const uint32_t bph = (uint32_t)(g / NSTG) & 1u;
         tc::mbar_wait(&y_full[s], ph);
         tc::mbar_wait(&s_empty[b], bph ^ 1u);
         tc::fence_after_sync();
@@ -152,10 +152,16 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const BwdParams p) {
           tc::umma_commit(&s_full[b]);
         }
         __syncwarp();
-      };
-      if (n_t > 0) gemm1(g);
-      for (long t = 0; t < n_t; ++t, ++g) {
-        if (t + 1 < n_t) gemm1(g + 1);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== GEMM2 issuer:  dX += P(t) Y(t)
+    const uint32_t idesc2 = tc::idesc_bf16_f32(kRows, p.D, 0, 1);  // B is MN-major in GEMM2
+    long g = 0;
+    for (long w = blockIdx.x; w < n_work; w += gridDim.x) {
+      const int split = (int)(w / p.row_blocks);
+      const long t0 = p.tiles_total * split / p.splits, t1 = p.tiles_total * (split + 1) / p.splits;
+      for (long t = t0; t < t1; ++t, ++g) {
         const int s = (int)(g % p.stages);
         const int b = (int)(g % NSTG);
         const uint32_t bph = (uint32_t)(g / NSTG) & 1u;
@@ -169,18 +175,22 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const BwdParams p) {
 #pragma unroll
           for (int kk = 0; kk < NT / 16; ++kk)
             tc::umma_bf16_ts(tmem_base + dx_col, a0 + (uint32_t)kk * 8, bd0 + (uint64_t)(kk * (2048 >> 4)), idesc2,
-                             (uint32_t)((t | kk) != 0));
+                             (uint32_t)((t != t0) || kk != 0));
+          // these commits also cover GEMM1(t): it completed before P(t) could be produced
           tc::umma_commit(&y_empty[s]);
           tc::umma_commit(&p_empty[b]);
-          if (t + 1 == n_t) tc::umma_commit(dx_full);
+          if (t + 1 == t1) tc::umma_commit(dx_full);
         }
         __syncwarp();
       }
     }
   } else {
     // ===================================================================== softmax warps: thread == row
+    // NG groups of 4 warps; group g handles the tiles whose accumulator stage is g, so the fixed latencies of one
+    // group's hand-offs (barrier waits, TMEM load / store round trips) overlap the other group's arithmetic.
     const int q = warp & 3;
-    const int ew = warp - 2;                 // private scratch index
+    const int ew = warp - 3;                 // private scratch index
+    const int grp = ew >> 2;
     const int row = q * 32 + lane;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     float* my_lse = col_lse + ew * NT;
@@ -188,14 +198,15 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const BwdParams p) {
     constexpr float kLog2e = 1.4426950408889634f;
     long g = 0;
     uint32_t wi = 0;
+    const int xj_per_grp = (p.D >> 4) / NG;  // 8-column groups of X handled by this warp group
     for (long w = blockIdx.x; w < n_work; w += gridDim.x, ++wi) {
       const long rb = w % p.row_blocks;
       const int split = (int)(w / p.row_blocks);
       const long t0 = p.tiles_total * split / p.splits, t1 = p.tiles_total * (split + 1) / p.splits;
       const long xrow = rb * kRows + row;
-      {  // this thread's row of X -> TMEM (packed bf16 pairs, channel 2j in the low half)
+      {  // this thread's row of X -> TMEM (packed bf16 pairs, channel 2j in the low half); columns split over groups
         const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.X) + xrow * p.D);
-        for (int j = 0; j < (p.D >> 4); ++j) {
+        for (int j = grp * xj_per_grp; j < (grp + 1) * xj_per_grp; ++j) {
           uint4 lo = make_uint4(0, 0, 0, 0), hi = lo;
           if (xrow < p.n_x) {
             lo = src[2 * j];
@@ -222,6 +233,7 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const BwdParams p) {
       }
       for (long t = t0; t < t1; ++t, ++g) {
         const int b = (int)(g % NSTG);
+        if (b != grp) continue;
         const uint32_t bph = (uint32_t)(g / NSTG) & 1u;
         const long cbase = t * NT;
         if (TRANSPOSED) {  // column statistics of this tile -> per-warp scratch (lse*log2e, local positive row)
@@ -234,26 +246,27 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const BwdParams p) {
           }
           __syncwarp();
         }
+        const bool special = !TRANSPOSED && ((cbase + NT > p.n_y) || (row_pos >= cbase && row_pos < cbase + NT));
+        uint32_t packed[NT / 2];
         tc::mbar_wait(&s_full[b], bph);
         tc::fence_after_sync();
-        uint32_t raw[NCH][32];
-#pragma unroll
-        for (int c = 0; c < NCH; ++c) tc::tmem_ld_32x32(lane_addr + s_col + (uint32_t)b * NT + c * 32, raw[c]);
-        tc::tmem_ld_wait();
-        tc::fence_before_sync();
-        __syncwarp();
-        if (lane == 0) tc::mbar_arrive(&s_empty[b]);
-        uint32_t packed[NT / 2];
-        const bool special = !TRANSPOSED && ((cbase + NT > p.n_y) || (row_pos >= cbase && row_pos < cbase + NT));
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
+          uint32_t raw[32];
+          tc::tmem_ld_32x32(lane_addr + s_col + (uint32_t)b * NT + c * 32, raw);
+          tc::tmem_ld_wait();
+          if (c == NCH - 1) {  // S(t) is in registers: GEMM1 of tile t + NSTG may overwrite the stage
+            tc::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&s_empty[b]);
+          }
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
             float pr[2];
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
               const int col = c * 32 + i + u;
-              const float sv = __uint_as_float(raw[c][i + u]);
+              const float sv = __uint_as_float(raw[i + u]);
               if (TRANSPOSED) {
                 pr[u] = ex2_ftz(fmaf(sv, kLog2e, -my_lse[col])) - (my_pos[col] == (int)row_pos ? 1.f : 0.f);
               } else {
@@ -281,11 +294,11 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const BwdParams p) {
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&p_full[b]);
       }
-      // row block finished: dX accumulator -> global (scaled)
+      // row block finished: dX accumulator -> global (scaled); 32-column chunks split over the groups
       tc::mbar_wait(dx_full, wi & 1u);
       tc::fence_after_sync();
       float* orow = p.out + ((size_t)split * p.n_x + xrow) * p.D;
-      for (int c = 0; c < (p.D >> 5); ++c) {
+      for (int c = grp; c < (p.D >> 5); c += NG) {
         uint32_t acc[32];
         tc::tmem_ld_32x32(lane_addr + dx_col + (uint32_t)c * 32, acc);
         tc::tmem_ld_wait();
@@ -302,7 +315,7 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const BwdParams p) {
   }
   tc::fence_before_sync();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == 0) {
     tc::fence_after_sync();
     tc::tmem_dealloc(tmem_base, 512);
   }
@@ -371,7 +384,7 @@ static void bwd_plan(long n_x, long n_y, int D, BwdPlan* pl) {
   pl->row_blocks = (n_x + kRows - 1) / kRows;
   pl->tiles = (n_y + pl->NT - 1) / pl->NT;
   const size_t stage = (size_t)(D / 64) * pl->NT * 128;
-  int stages = (int)(((size_t)kBwdSmem - 1024 - 8 * pl->NT * 4 - 512) / stage);
+  int stages = (int)(((size_t)kBwdSmem - 1024 - 16 * pl->NT * 4 - 512) / stage);
   pl->stages = stages > kBwdMaxStages ? kBwdMaxStages : stages;
   long splits = (long)sm_count() / pl->row_blocks;
   if (splits < 1) splits = 1;
@@ -380,7 +393,7 @@ static void bwd_plan(long n_x, long n_y, int D, BwdPlan* pl) {
   pl->splits = (int)splits;
   const long n_work = pl->row_blocks * splits;
   pl->grid = (int)(n_work < sm_count() ? n_work : sm_count());
-  pl->smem = 1024 + (size_t)pl->stages * stage + 8 * pl->NT * 4 + 512;
+  pl->smem = 1024 + (size_t)pl->stages * stage + 16 * pl->NT * 4 + 512;
 }
 
 template <bool TR>
@@ -389,7 +402,7 @@ static int bwd_launch(const BwdPlan& pl, const CUtensorMap& my, const BwdParams&
   if (pl.NT == NTv && pl.NSTG == NSv) {                                                                         \
     BDLRU_CUDA(cudaFuncSetAttribute(ce_bwd_kernel<TR, NTv, NSv>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
                                     (int)pl.smem));                                                             \
-    ce_bwd_kernel<TR, NTv, NSv><<<pl.grid, 192, pl.smem, st>>>(my, p);                                          \
+    ce_bwd_kernel<TR, NTv, NSv><<<pl.grid, 96 + 128 * NSv, pl.smem, st>>>(my, p);                                          \
     BDLRU_LAUNCHED();                                                                                           \
     return BDLRU_OK;                                                                                            \
   }
