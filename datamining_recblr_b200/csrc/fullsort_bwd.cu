@@ -23,6 +23,8 @@
 #include <cuda.h>
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "tc05.cuh"
 
@@ -34,6 +36,7 @@ constexpr int kBwdSmem = 200 * 1024;
 
 struct BwdParams {
   const void* X;        // [n_x, D] bf16 rows owned by CTAs
+  const void* Y;        // [n_y, D] bf16 (also behind the tensor map); read directly for the onehot row of the dQ pass
   long n_x, n_y;        // rows of X, rows of Y (columns of S)
   int D, stages, splits;
   long row_blocks, tiles_total;
@@ -42,6 +45,7 @@ struct BwdParams {
   long n_users;
   long id_offset;       // global id of item row 0 of this shard
   float scale;
+  int dbg;              // BDLRU_FS_DEBUG & 8: print per-tile phase timings of one softmax warp
   float* out;           // [splits][n_x][D] fp32 (splits == 1: the final gradient)
 };
 
@@ -198,6 +202,8 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const BwdParams p) {
     constexpr float kLog2e = 1.4426950408889634f;
     long g = 0;
     uint32_t wi = 0;
+    long long tq_wait_s = 0, tq_math = 0, tq_wait_p = 0, tq_st = 0, tq_n = 0;
+    const long long tq_begin = clock64();
     const int xj_per_grp = (p.D >> 4) / NG;  // 8-column groups of X handled by this warp group
     for (long w = blockIdx.x; w < n_work; w += gridDim.x, ++wi) {
       const long rb = w % p.row_blocks;
@@ -231,25 +237,57 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const BwdParams p) {
       } else {
         row_pos = xrow;
       }
+      float pre_lse[NCH];
+      int pre_pos[NCH];
+      bool pre_valid = false;
       for (long t = t0; t < t1; ++t, ++g) {
         const int b = (int)(g % NSTG);
         if (b != grp) continue;
         const uint32_t bph = (uint32_t)(g / NSTG) & 1u;
         const long cbase = t * NT;
-        if (TRANSPOSED) {  // column statistics of this tile -> per-warp scratch (lse*log2e, local positive row)
-          __syncwarp();
-          for (int i = lane; i < NT; i += 32) {
-            const long u = cbase + i;
-            const bool ok = u < p.n_users;
-            my_lse[i] = ok ? p.lse[u] * kLog2e : INFINITY;
-            my_pos[i] = ok ? (int)(p.pos[u] - p.id_offset) : -1;
+        bool onehot_here = false;
+        if (TRANSPOSED) {
+          // Column statistics of this tile (lse*log2e, local positive row) -> per-warp scratch.  The values were
+          // prefetched into registers while the previous own tile was processed (first own tile: loaded here).
+          if (!pre_valid) {
+#pragma unroll
+            for (int k = 0; k < NCH; ++k) {
+              const long u = cbase + lane + 32 * k;
+              const bool ok = u < p.n_users;
+              pre_lse[k] = ok ? p.lse[u] * kLog2e : INFINITY;
+              pre_pos[k] = ok ? (int)(p.pos[u] - p.id_offset) : -1;
+            }
           }
           __syncwarp();
+          const int row_lo = (int)(rb * kRows) + q * 32;  // this warp's 32 rows
+          bool mine = false;
+#pragma unroll
+          for (int k = 0; k < NCH; ++k) {
+            my_lse[lane + 32 * k] = pre_lse[k];
+            my_pos[lane + 32 * k] = pre_pos[k];
+            mine |= (pre_pos[k] >= row_lo && pre_pos[k] < row_lo + 32);
+          }
+          onehot_here = __any_sync(0xffffffffu, mine);  // rare: some column's positive item is one of this warp's rows
+          __syncwarp();
+          // prefetch for the next own tile of this work item (latency hidden behind this tile's arithmetic)
+          const long nt = t + NG;
+          pre_valid = nt < t1;
+          if (pre_valid) {
+#pragma unroll
+            for (int k = 0; k < NCH; ++k) {
+              const long u = nt * NT + lane + 32 * k;
+              const bool ok = u < p.n_users;
+              pre_lse[k] = ok ? p.lse[u] * kLog2e : INFINITY;
+              pre_pos[k] = ok ? (int)(p.pos[u] - p.id_offset) : -1;
+            }
+          }
         }
-        const bool special = !TRANSPOSED && ((cbase + NT > p.n_y) || (row_pos >= cbase && row_pos < cbase + NT));
+        const bool tail = !TRANSPOSED && (cbase + NT > p.n_y);  // last tile: columns beyond the table contribute 0
         uint32_t packed[NT / 2];
+        const long long k0 = clock64();
         tc::mbar_wait(&s_full[b], bph);
         tc::fence_after_sync();
+        const long long k1 = clock64();
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
           uint32_t raw[32];
@@ -260,29 +298,37 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const BwdParams p) {
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&s_empty[b]);
           }
+          // P = exp(S - lse) as packed bf16 pairs.  dQ pass: the "- onehot" term is NOT applied here (it would put
+          // per-element 64-bit compares into this MUFU-bound loop); it is subtracted as one row of Y when the row block
+          // is written out.  dE pass: applied here, but only in the rare tiles that contain one of this warp's rows.
+          auto chunk_math = [&](auto check_tag) {
+            constexpr bool CHECK = decltype(check_tag)::value;
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            float pr[2];
+            for (int i = 0; i < 32; i += 2) {
+              float pr[2];
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
-              const int col = c * 32 + i + u;
-              const float sv = __uint_as_float(raw[i + u]);
-              if (TRANSPOSED) {
-                pr[u] = ex2_ftz(fmaf(sv, kLog2e, -my_lse[col])) - (my_pos[col] == (int)row_pos ? 1.f : 0.f);
-              } else {
-                pr[u] = ex2_ftz(fmaf(sv, kLog2e, -row_lse2));
-                if (special) {
-                  if (cbase + col == row_pos) pr[u] -= 1.f;
-                  if (cbase + col >= p.n_y) pr[u] = 0.f;
+              for (int u = 0; u < 2; ++u) {
+                const int col = c * 32 + i + u;
+                const float sv = __uint_as_float(raw[i + u]);
+                if (TRANSPOSED) {
+                  pr[u] = ex2_ftz(fmaf(sv, kLog2e, -my_lse[col]));
+                  if (CHECK && my_pos[col] == (int)row_pos) pr[u] -= 1.f;
+                } else {
+                  pr[u] = ex2_ftz(fmaf(sv, kLog2e, -row_lse2));
+                  if (CHECK && cbase + col >= p.n_y) pr[u] = 0.f;
                 }
               }
+              const __nv_bfloat162 h = __floats2bfloat162_rn(pr[0], pr[1]);
+              packed[(c * 32 + i) >> 1] = *reinterpret_cast<const uint32_t*>(&h);
             }
-            const __nv_bfloat162 h = __floats2bfloat162_rn(pr[0], pr[1]);
-            packed[(c * 32 + i) >> 1] = *reinterpret_cast<const uint32_t*>(&h);
-          }
+          };
+          if (TRANSPOSED ? onehot_here : tail) chunk_math(std::true_type{});
+          else chunk_math(std::false_type{});
         }
+        const long long k2 = clock64();
         tc::mbar_wait(&p_empty[b], bph ^ 1u);   // GEMM2 of the tile that used this P stage has completed
         tc::fence_after_sync();
+        const long long k3 = clock64();
 #pragma unroll
         for (int j = 0; j < NT / 16; ++j) {
           const uint32_t wv[8] = {packed[8 * j], packed[8 * j + 1], packed[8 * j + 2], packed[8 * j + 3],
@@ -293,25 +339,40 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const BwdParams p) {
         tc::fence_before_sync();
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&p_full[b]);
+        const long long k4 = clock64();
+        tq_wait_s += k1 - k0; tq_math += k2 - k1; tq_wait_p += k3 - k2; tq_st += k4 - k3; ++tq_n;
       }
       // row block finished: dX accumulator -> global (scaled); 32-column chunks split over the groups
       tc::mbar_wait(dx_full, wi & 1u);
       tc::fence_after_sync();
       float* orow = p.out + ((size_t)split * p.n_x + xrow) * p.D;
+      // dQ pass: "- onehot" = minus the positive item's row of Y, applied once, by the split that owns that column
+      const bool sub_pos = !TRANSPOSED && xrow < p.n_x && row_pos >= t0 * NT && row_pos < t1 * NT && row_pos < p.n_y;
+      const __nv_bfloat16* yrow = reinterpret_cast<const __nv_bfloat16*>(p.Y) + (sub_pos ? row_pos : 0) * p.D;
       for (int c = grp; c < (p.D >> 5); c += NG) {
         uint32_t acc[32];
         tc::tmem_ld_32x32(lane_addr + dx_col + (uint32_t)c * 32, acc);
         tc::tmem_ld_wait();
         if (xrow < p.n_x) {
 #pragma unroll
-          for (int i = 0; i < 32; i += 4)
-            *reinterpret_cast<float4*>(orow + c * 32 + i) =
-                make_float4(__uint_as_float(acc[i]) * p.scale, __uint_as_float(acc[i + 1]) * p.scale,
-                            __uint_as_float(acc[i + 2]) * p.scale, __uint_as_float(acc[i + 3]) * p.scale);
+          for (int i = 0; i < 32; i += 4) {
+            float o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              o[e] = __uint_as_float(acc[i + e]);
+              if (sub_pos) o[e] -= __bfloat162float(yrow[c * 32 + i + e]);
+              o[e] *= p.scale;
+            }
+            *reinterpret_cast<float4*>(orow + c * 32 + i) = make_float4(o[0], o[1], o[2], o[3]);
+          }
         }
       }
       tc::fence_before_sync();
     }
+    if ((p.dbg & 8) && blockIdx.x == 0 && warp == 3 && lane == 0 && tq_n > 0)
+      printf("[ce_bwd softmax warp, transposed=%d] own tiles %lld: total/own-tile %lld = wait s_full %lld + ld+math %lld + "
+             "wait p_empty %lld + st+arrive %lld cycles\n", (int)TRANSPOSED, tq_n, (clock64() - tq_begin) / tq_n,
+             tq_wait_s / tq_n, tq_math / tq_n, tq_wait_p / tq_n, tq_st / tq_n);
   }
   tc::fence_before_sync();
   __syncthreads();
@@ -422,9 +483,10 @@ static int bwd_one(const void* X, long n_x, const void* Y, long n_y, int D, cons
   int rc = bwd_make_map(&my, Y, n_y, D, pl.NT);
   if (rc) return rc;
   BwdParams p = {};
-  p.X = X; p.n_x = n_x; p.n_y = n_y; p.D = D; p.stages = pl.stages; p.splits = pl.splits;
+  p.X = X; p.Y = Y; p.n_x = n_x; p.n_y = n_y; p.D = D; p.stages = pl.stages; p.splits = pl.splits;
   p.row_blocks = pl.row_blocks; p.tiles_total = pl.tiles;
   p.lse = lse; p.pos = pos; p.n_users = n_users; p.id_offset = id_offset; p.scale = scale;
+  p.dbg = getenv("BDLRU_FS_DEBUG") ? atoi(getenv("BDLRU_FS_DEBUG")) : 0;
   p.out = pl.splits > 1 ? scratch : grad;
   if ((rc = bwd_launch<TR>(pl, my, p, st))) return rc;
   if (pl.splits > 1) {

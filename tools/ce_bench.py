@@ -36,3 +36,23 @@ t_b = timeit(lambda: ops.fullsort_ce_grads(q, e, pos, lse, 1.0 / B))
 fl = 2.0 * B * N * D
 print(f"B={B} N={N} D={D}: ce fwd {t_f:.3f} ms = {fl / t_f / 1e9:.0f} TFLOP/s;  ce bwd (dQ+dE) {t_b:.3f} ms = "
       f"{2 * fl / t_b / 1e9:.0f} TFLOP/s credited (4 GEMM-passes executed: {4 * fl / t_b / 1e9:.0f} TFLOP/s)")
+
+# split of the backward: dQ pass only / dE pass only (through the C ABI directly)
+from datamining_recblr_b200 import _lib as L  # noqa: E402
+lib = L.load()
+nws = lib.bdlru_fullsort_ce_workspace_bytes(B, N, D)
+ws = torch.empty(max(nws, 16), dtype=torch.uint8, device="cuda")
+dQ = torch.empty(B, D, device="cuda")
+dE = torch.empty(N, D, device="cuda")
+st = L.stream_ptr(q)
+lsef = lse.float().contiguous()
+
+
+def run(dq, de):
+    L.check(lib.bdlru_fullsort_ce_bwd(L.ptr(q), L.ptr(e), L.ptr(pos), L.ptr(lsef), 1.0 / B, B, N, D, 0, L.ptr(dq), L.ptr(de),
+                                      L.ptr(ws), nws, st))
+
+
+t_q = timeit(lambda: run(dQ, None))
+t_e = timeit(lambda: run(None, dE))
+print(f"  dQ pass {t_q:.3f} ms ({2 * fl / t_q / 1e9:.0f} TFLOP/s executed), dE pass {t_e:.3f} ms ({2 * fl / t_e / 1e9:.0f} TFLOP/s executed)")
