@@ -102,6 +102,26 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def finish_distributed(world):
+    """Collective teardown that cannot hang the launcher: every rank syncs, meets at a barrier (ranks != 0 wait here for
+    rank 0's rank-0-only legs), then destroys the process group; if NCCL teardown stalls (seen with captured graphs
+    still holding communicator resources) a daemon timer ends the process — the JSON line is already printed."""
+    if world <= 1:
+        return
+    import torch.distributed as dist
+    sys.stdout.flush()
+    torch.cuda.synchronize()
+    try:
+        dist.barrier()
+    except Exception:
+        pass
+    t = threading.Timer(20.0, lambda: os._exit(0))
+    t.daemon = True
+    t.start()
+    dist.destroy_process_group()
+    t.cancel()
+
+
 def dist_env():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -386,8 +406,8 @@ def run_train(args):
         model.train()
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        del graphed
+        finish_distributed(world)
         return
 
     # ---- roofline of the dominant kernel of libbdlru.so in the step (live CUDA-event durations)
@@ -429,7 +449,7 @@ def run_train(args):
                              "launch); working set is L2-resident at this shape, see DESIGN.md")
 
     base, _ = (cpu_train_baseline(w, steps=3 if big else 6, warmup=1, sample_B=args.cpu_sample or (16 if big else 1024))
-               if not args.no_cpu else (None, 0))
+               if not args.no_cpu and world == 1 else (None, 0))   # cpu_baseline: rank 0 at N = 1 only
     line = dict(metric="bdlru_fwd_bwd_seq_tokens_per_s", value=value, unit="seq-tokens/s", n_gpus=world,
                 steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=ms_per_step, higher_is_better=True,
                 scaling="weak", vs_baseline=None, dtype="bf16" if amp else "f32", data="synthetic",
@@ -445,8 +465,8 @@ def run_train(args):
                 gpu_launches=launches, clocks=clocks, roofline=roofline, kernels=per_kernel, fullsort=fullsort,
                 cpu_baseline=base)
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    del graphed
+    finish_distributed(world)
 
 
 def main():

@@ -16,7 +16,7 @@ import torch
 
 def run_score(args):
     import torch.distributed as dist
-    from bench import SCORE_WORKLOADS, ClockSampler, cpu_score_baseline, dist_env, peaks
+    from bench import SCORE_WORKLOADS, ClockSampler, cpu_score_baseline, dist_env, finish_distributed, peaks
     from datamining_recblr_b200 import _lib, ops, sharded
     from datamining_recblr_b200.timing import flush_l2
 
@@ -89,8 +89,7 @@ def run_score(args):
     e2e_s = float(te)
     clocks = sampler.stop() if rank == 0 else None
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        finish_distributed(world)
         return
     P = peaks()
     flops = 2.0 * B * (hi - lo) * D
@@ -101,7 +100,7 @@ def run_score(args):
                     peak_source=P["src"] + " (sustained bf16 cuBLAS; burst %.0f)" % P["tf"],
                     algorithmic_flops_per_launch=flops, avg_launch_ms=avg)
     base = None
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:   # cpu_baseline: rank 0 at N = 1 only
         base, _ = cpu_score_baseline(N, D, args.cpu_sample or (512 if N <= 1_000_000 else 64), k, steps=6, warmup=1)
     line = dict(metric="fullsort_scored_users_per_s", value=B / (ms_per_step * 1e-3), unit="users/s", n_gpus=world,
                 steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=ms_per_step, higher_is_better=True,
@@ -114,5 +113,4 @@ def run_score(args):
                          d2h_bytes_per_step=B * k * 8, ms_per_step=e2e_s / args.steps * 1e3),
                 gpu_launches=launches, clocks=clocks, roofline=roofline, cpu_baseline=base)
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    finish_distributed(world)
