@@ -122,6 +122,14 @@ def finish_distributed(world):
     t.cancel()
 
 
+def ncu_traffic(workload, kernel):
+    """dram bytes per launch of `kernel` from the committed ncu capture of this workload (None if there is none)."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "r1_dram_traffic.json")))[workload][kernel]
+    except Exception:
+        return None
+
+
 def dist_env():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -443,7 +451,8 @@ def run_train(args):
                         note="credited flops: 2*B*N*D forward, 4*B*N*D backward (dQ and dE; the recompute GEMMs are not credited)")
     else:
         roofline = dict(bound="hbm", kernel=dom, achieved=per_kernel[dom]["gbs"], peak=P["hbm"], unit="GB/s",
-                        frac=per_kernel[dom]["gbs"] / P["hbm"], traffic=None, peak_source=P["src"],
+                        frac=per_kernel[dom]["gbs"] / P["hbm"], traffic=ncu_traffic(args.workload, dom),
+                        peak_source=P["src"],
                         algorithmic_bytes_per_launch=alg[dom], avg_launch_ms=per_kernel[dom]["avg_ms"],
                         note="events bracket the C-ABI call on the launching stream (includes its dLambda/dh0 reduction "
                              "launch); working set is L2-resident at this shape, see DESIGN.md")

@@ -16,7 +16,7 @@ import torch
 
 def run_score(args):
     import torch.distributed as dist
-    from bench import SCORE_WORKLOADS, ClockSampler, cpu_score_baseline, dist_env, finish_distributed, peaks
+    from bench import SCORE_WORKLOADS, ClockSampler, cpu_score_baseline, dist_env, finish_distributed, ncu_traffic, peaks
     from datamining_recblr_b200 import _lib, ops, sharded
     from datamining_recblr_b200.timing import flush_l2
 
@@ -95,8 +95,9 @@ def run_score(args):
     flops = 2.0 * B * (hi - lo) * D
     avg = sum(kt) / len(kt)
     tf = flops / (avg * 1e-3) / 1e12
-    roofline = dict(bound="tensor", kernel="fullsort_kernel<UB=2,TOPK> (+ list merge)", achieved=tf,
-                    peak=P["tf_sustained"], unit="TFLOP/s", frac=tf / P["tf_sustained"], traffic=None,
+    roofline = dict(bound="tensor", kernel="fullsort_kernel<UB=2,TOPK,K=10,NT=96,NSTG=2> (+ list merge)", achieved=tf,
+                    peak=P["tf_sustained"], unit="TFLOP/s", frac=tf / P["tf_sustained"],
+                    traffic=ncu_traffic(args.workload, "bdlru_fullsort_topk") if world == 1 else None,
                     peak_source=P["src"] + " (sustained bf16 cuBLAS; burst %.0f)" % P["tf"],
                     algorithmic_flops_per_launch=flops, avg_launch_ms=avg)
     base = None
