@@ -164,3 +164,33 @@ def test_ce_stats_shard_with_positive_outside_tail_tile():
     assert torch.isfinite(pl).all()
     assert np.abs(pl[:4].cpu().numpy() - logits[np.arange(4), pos[:4]]).max() <= 1e-5 * np.abs(logits).max()
     assert float(pl[4:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("B,N,D,k", [(1, 5, 64, 32), (3, 40, 128, 32), (129, 97, 64, 1), (257, 193, 256, 20)])
+def test_topk_edge_sizes(B, N, D, k):
+    """Single user, k larger than the catalog (padding with (-inf, -1)), k = 1, sizes one past a tile / block boundary."""
+    from datamining_recblr_b200 import ops
+    rng = np.random.default_rng(B * N)
+    qb, eb = _bf(rng.integers(-2, 3, size=(B, D))), _bf(rng.integers(-1, 2, size=(N, D)))
+    vals, ids = ops.fullsort_topk(qb.cuda(), eb.cuda(), k, mask_id=0)
+    v_ref, i_ref, _ = _oracle_topk(qb, eb, k, 0)
+    kk = min(k, N - 1)
+    assert (ids.cpu().numpy()[:, :kk] == i_ref[:, :kk]).all()
+    assert (vals.cpu().numpy()[:, :kk] == v_ref[:, :kk]).all()
+    if kk < k:
+        assert (ids.cpu().numpy()[:, kk:] == -1).all()
+
+
+def test_fullsort_rejects_bad_arguments():
+    from datamining_recblr_b200 import ops
+    from datamining_recblr_b200._lib import BdlruError
+    q = torch.randn(4, 48, device="cuda")
+    e = torch.randn(10, 48, device="cuda")
+    with pytest.raises(BdlruError):          # D must be a multiple of 64
+        ops.fullsort_topk(q, e, 5)
+    q = torch.randn(4, 64, device="cuda")
+    e = torch.randn(10, 64, device="cuda")
+    with pytest.raises(BdlruError):          # k <= 32
+        ops.fullsort_topk(q, e, 33)
+    with pytest.raises(Exception):           # no CPU fallback
+        ops.fullsort_topk(q.cpu(), e.cpu(), 5)
