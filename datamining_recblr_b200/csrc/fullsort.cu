@@ -48,6 +48,7 @@ struct FsParams {
   // top-k partials [n_users][splits][k]
   float* part_scores;
   int* part_ids;
+  unsigned* shared_thr;       // [n_users] order-preserving encoding of the best K-th score seen by ANY split (0 = none)
   // CE partials [n_users][splits] and direct outputs
   float* part_max;
   float* part_sum;
@@ -112,6 +113,17 @@ __device__ __forceinline__ void topk_insert(float (&ls)[K], int (&li)[K], float 
     ls[0] = v;
     li[0] = id;
   }
+}
+
+// Order-preserving float <-> unsigned (0 is below every float): lets the splits of a user group share their K-th best
+// score through atomicMax.
+__device__ __forceinline__ unsigned thr_encode(float f) {
+  const unsigned u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float thr_decode(unsigned k) {
+  if (k == 0u) return -INFINITY;
+  return __uint_as_float((k & 0x80000000u) ? (k ^ 0x80000000u) : ~k);
 }
 
 // 3-input max (FMNMX3 on sm_100): 32 values in 16 instructions instead of 31 — the epilogue's threshold filter is
@@ -283,6 +295,13 @@ fullsort_kernel(const __grid_constant__ CUtensorMap tmE, const FsParams p) {
       ls[j] = -INFINITY;
       li[j] = -1;
     }
+    // top-k: the CTAs that stream different item ranges for the SAME users publish their K-th best score; an item below
+    // the best published K-th cannot be in the final top-K, so every split filters with it (>=: ties are still admitted
+    // and resolved by id in the merge).  This makes S short streams insert like ONE long stream (K ln(N/K) in total
+    // instead of per split).  `sthr` lags by one tile so the L2 read is never waited for.
+    float sthr = -INFINITY;
+    unsigned sthr_raw = 0u;  // loaded one tile ago, decoded (= first use) only now
+    const bool share = MODE == MODE_TOPK && p.shared_thr != nullptr && user < p.n_users;
     float run_m = -INFINITY, run_s = 0.f;   // CE: online max / sum of exp
     long pos_local = -1;
     if (MODE == MODE_CE && user < p.n_users) {
@@ -302,6 +321,10 @@ fullsort_kernel(const __grid_constant__ CUtensorMap tmE, const FsParams p) {
       const long long e1c = clock64();
       te_wait += e1c - e0c;
       tc::fence_after_sync();
+      if (share) {
+        sthr = fmaxf(sthr, thr_decode(sthr_raw));
+        sthr_raw = __ldcg(p.shared_thr + user);
+      }
       const uint32_t taddr = lane_addr + acc_col0 + (uint32_t)((b * UB + ub) * NT);
       // The accumulator tile is pulled into registers CH chunks (CH*32 columns) at a time; once the last group has
       // landed the TMEM buffer is handed back to the MMA warp BEFORE the scores are processed, so the tensor pipe
@@ -344,12 +367,14 @@ fullsort_kernel(const __grid_constant__ CUtensorMap tmE, const FsParams p) {
 #pragma unroll
         for (int c = 1; c < CH; ++c) mt = fmaxf(mt, m[c]);
         if (MODE == MODE_TOPK) {
-          if (__any_sync(0xffffffffu, mt > ls[K - 1])) {
+          if (__any_sync(0xffffffffu, mt > ls[K - 1] && mt >= sthr)) {
+            const float kth_before = ls[K - 1];
 #pragma unroll
             for (int c = 0; c < CH; ++c) {
               const int id0 = (int)(p.id_offset + base + (g * CH + c) * 32);
-              while (__any_sync(0xffffffffu, m[c] > ls[K - 1])) {  // insert rounds: lanes with a candidate act together
-                if (m[c] > ls[K - 1]) {
+              // insert rounds: lanes with a candidate act together
+              while (__any_sync(0xffffffffu, m[c] > ls[K - 1] && m[c] >= sthr)) {
+                if (m[c] > ls[K - 1] && m[c] >= sthr) {
                   int idx = 31;
 #pragma unroll
                   for (int i = 30; i >= 0; --i) idx = (v[c][i] == m[c]) ? i : idx;  // first index among equal scores
@@ -360,6 +385,7 @@ fullsort_kernel(const __grid_constant__ CUtensorMap tmE, const FsParams p) {
                 }
               }
             }
+            if (share && ls[K - 1] > kth_before) atomicMax(p.shared_thr + user, thr_encode(ls[K - 1]));
           }
         } else {
           if (mt > run_m) {  // rescale the running sum to the new maximum (mt is finite here)
@@ -581,7 +607,7 @@ extern "C" BDLRU_API int bdlru_fullsort_available(void) { return 1; }
 extern "C" BDLRU_API size_t bdlru_fullsort_topk_workspace_bytes(int64_t n_users, int64_t n_rows, int D, int k) {
   FsPlan pl;
   if (D % 64 != 0 || D < 64 || D > 256 || k < 1 || k > 32 || !fs_plan(n_users, n_rows, D, k, &pl)) return 0;
-  return (size_t)n_users * pl.splits * k * 8;
+  return (size_t)n_users * pl.splits * k * 8 + (size_t)n_users * 4;
 }
 
 extern "C" BDLRU_API int bdlru_fullsort_topk(const void* Q, const void* E, int64_t n_users, int64_t n_rows, int D, int k,
@@ -594,7 +620,7 @@ extern "C" BDLRU_API int bdlru_fullsort_topk(const void* Q, const void* E, int64
   BDLRU_REQUIRE(id_offset >= 0 && id_offset + n_rows < (1L << 31), "fullsort_topk: item ids must fit int32");
   FsPlan pl;
   BDLRU_REQUIRE(fs_plan(n_users, n_rows, D, k, &pl), "fullsort_topk: no tiling fits shared memory (D=%d k=%d)", D, k);
-  const size_t need = (size_t)n_users * pl.splits * k * 8;
+  const size_t need = (size_t)n_users * pl.splits * k * 8 + (size_t)n_users * 4;
   BDLRU_REQUIRE(workspace && workspace_bytes >= need, "fullsort_topk: workspace %zu < %zu bytes", workspace_bytes, need);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   CUtensorMap me;
@@ -608,6 +634,11 @@ extern "C" BDLRU_API int bdlru_fullsort_topk(const void* Q, const void* E, int64
   p.tiles_total = pl.tiles_total;
   p.part_scores = reinterpret_cast<float*>(workspace);
   p.part_ids = reinterpret_cast<int*>(p.part_scores + (size_t)n_users * pl.splits * k);
+  p.shared_thr = nullptr;
+  if (pl.splits > 1 && !(fs_debug() & 16)) {  // BDLRU_FS_DEBUG & 16: disable threshold sharing (tuning / A-B runs)
+    p.shared_thr = reinterpret_cast<unsigned*>(p.part_ids + (size_t)n_users * pl.splits * k);
+    BDLRU_CUDA(cudaMemsetAsync(p.shared_thr, 0, (size_t)n_users * 4, st));
+  }
   if ((rc = fs_launch<MODE_TOPK>(pl, me, p, st))) return rc;
   const int n_cand = pl.splits * k;
   const size_t msmem = (size_t)4 * n_cand * 8;
