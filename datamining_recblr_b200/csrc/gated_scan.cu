@@ -16,6 +16,8 @@
 // The backward mirrors this in reverse time with u_t = a_t * dh~_t as the carried quantity.
 // HBM traffic is the algorithmic minimum: fwd reads x', r, i and writes h (4 units);
 // bwd reads x', r, i, h, g and writes dx', dr, di (8 units).   [SURVEY §8d: 12*E*s bytes fwd+bwd]
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace bdlru {
@@ -444,6 +446,8 @@ static Tiling make_tiling(int B, int T, int C) {
   // time slices per CTA: enough to cover T when it is short, at most 256 threads / 32 slices
   int ns = 256 / t.tcn;
   if (ns > 32) ns = 32;  // tcn < 8 (C/4 not a multiple of 8): fewer threads rather than a long combine loop
+  static const int force_ns = getenv("BDLRU_GSCAN_NS") ? atoi(getenv("BDLRU_GSCAN_NS")) : 0;  // tuning
+  if (force_ns > 0 && force_ns < ns) ns = force_ns;
   t.NS = ns;
   (void)T;
   t.NT = t.tcn * t.NS;
