@@ -194,3 +194,35 @@ def test_fullsort_rejects_bad_arguments():
         ops.fullsort_topk(q, e, 33)
     with pytest.raises(Exception):           # no CPU fallback
         ops.fullsort_topk(q.cpu(), e.cpu(), 5)
+
+
+@pytest.mark.parametrize("B,N,D", [(200, 20000, 64), (20000, 300, 64), (19000, 19500, 128)])
+def test_fused_ce_many_row_blocks(B, N, D):
+    """More row blocks than SMs in the dE pass (N > 148 * 128) and in the dQ pass (B > 148 * 128): every CTA of the
+    persistent backward kernel walks several work items (X reloaded into TMEM, accumulator reused), and the forward /
+    top-k kernels run several waves of user groups."""
+    from datamining_recblr_b200 import ops
+    rng = np.random.default_rng(B + N)
+    qb, eb = _bf(rng.normal(size=(B, D)) * 1.5), _bf(rng.normal(size=(N, D)) * 0.3)
+    pos = rng.integers(0, N, size=B)
+    q = qb.float().cuda().requires_grad_(True)
+    e = eb.float().cuda().requires_grad_(True)
+    loss = ops.fullsort_cross_entropy(q, e, torch.tensor(pos).cuda())
+    loss.backward()
+    qd, ed = qb.double().cuda(), eb.double().cuda()     # float64 reference on the GPU (the matrices are large)
+    logits = qd @ ed.T
+    lse = torch.logsumexp(logits, dim=1)
+    tp = torch.tensor(pos).cuda()
+    loss_ref = (lse - logits[torch.arange(B), tp]).mean()
+    p = torch.exp(logits - lse[:, None])
+    p[torch.arange(B), tp] -= 1.0
+    p /= B
+    dQ, dE = p @ ed, p.T @ qd
+    assert abs(float(loss) - float(loss_ref)) <= 1e-5 * abs(float(loss_ref))
+    assert float((q.grad.double() - dQ).abs().max()) <= 1e-2 * float(dQ.abs().max())
+    assert float((e.grad.double() - dE).abs().max()) <= 1e-2 * float(dE.abs().max())
+    vals, ids = ops.fullsort_topk(qb.cuda(), eb.cuda(), 10, mask_id=0)
+    logits[:, 0] = float("-inf")
+    ref_ids = torch.sort(logits, dim=1, descending=True, stable=True).indices[:, :10]
+    agree = (ids.long() == ref_ids).all(dim=1).double().mean()
+    assert float(agree) >= 0.999     # fp32 vs float64 near-ties only
