@@ -124,6 +124,18 @@ __device__ __forceinline__ float rsqrt_ftz(float x) {
 }
 __device__ __forceinline__ float exp_f(float x) { return ex2_ftz(x * 1.4426950408889634f); }
 __device__ __forceinline__ float sigmoid_f(float x) { return rcp_ftz(1.0f + ex2_ftz(x * -1.4426950408889634f)); }
+// One-MUFU sigmoid (tanh.approx, abs error ~5e-4): used by the bf16-I/O instantiations only, where the result is rounded
+// to 8 bits anyway and the kernels are SFU-bound rather than HBM-bound (6-8 SFU ops per element with the exact form).
+template <bool FAST>
+__device__ __forceinline__ float sigmoid_t(float x) {
+  if constexpr (FAST) {
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
+    return fmaf(0.5f, t, 0.5f);
+  } else {
+    return sigmoid_f(x);
+  }
+}
 __device__ __forceinline__ float silu_f(float x) { return x * sigmoid_f(x); }
 // d/dx silu(x) given s = sigmoid(x)
 __device__ __forceinline__ float silu_grad_f(float x, float s) { return s * (1.0f + x * (1.0f - s)); }
@@ -142,14 +154,16 @@ __device__ __forceinline__ float one_minus_exp_neg(float u, float e) {
 struct Gate {
   float sr, si, a, rq, q;  // sigmoid(r), sigmoid(i), alpha, 1/sqrt(1-a^2+1e-8), sqrt(1-a^2+1e-8)
 };
+template <bool FAST = false>
 __device__ __forceinline__ float gate_alpha(float c, float r, float& sr) {
-  sr = sigmoid_f(r);
+  sr = sigmoid_t<FAST>(r);
   return exp_f(-c * sr);
 }
+template <bool FAST = false>
 __device__ __forceinline__ Gate gate_full(float c, float r, float i) {
   Gate g;
-  g.a = gate_alpha(c, r, g.sr);
-  g.si = sigmoid_f(i);
+  g.a = gate_alpha<FAST>(c, r, g.sr);
+  g.si = sigmoid_t<FAST>(i);
   float v = one_minus_exp_neg(2.0f * c * g.sr, g.a * g.a) + 1e-8f;
   g.rq = rsqrt_ftz(v);
   g.q = v * g.rq;

@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(256) gscan_fwd_kernel(const GScanParams p) {
         for (int e = 0; e < 4; ++e) {
           float a, bb;
           if (GATED) {
-            Gate gt = gate_full(csp[e], rv[e], iv[e]);
+            Gate gt = gate_full<(sizeof(T) == 2)>(csp[e], rv[e], iv[e]);
             a = gt.a;
             bb = gt.q * gt.si * xv[e];
           } else {
@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(256) gscan_fwd_kernel(const GScanParams p) {
           float zv[4], yv[4];
           IO<T>::load(src + ((NARR - 1) * S + s) * ROW, zv);
 #pragma unroll
-          for (int e = 0; e < 4; ++e) yv[e] = silu_f(zv[e]) * hv[e];
+          for (int e = 0; e < 4; ++e) yv[e] = zv[e] * sigmoid_t<(sizeof(T) == 2)>(zv[e]) * hv[e];
           IO<T>::store(py + s * yrb, yv);
         }
       }
@@ -302,7 +302,7 @@ __global__ void __launch_bounds__(256) gscan_bwd_kernel(const GScanParams p) {
           IO<T>::load(src + (OFF_H + s + 1) * ROW, hv);
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const float sz = sigmoid_f(zv[e]);
+            const float sz = sigmoid_t<(sizeof(T) == 2)>(zv[e]);
             dzv[e] = gv[e] * hv[e] * silu_grad_f(zv[e], sz);
             gv[e] *= zv[e] * sz;
           }
@@ -311,7 +311,7 @@ __global__ void __launch_bounds__(256) gscan_bwd_kernel(const GScanParams p) {
         if (GATED) {
           float srv[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) av[e] = gate_alpha(csp[e], rv[e], srv[e]);
+          for (int e = 0; e < 4; ++e) av[e] = gate_alpha<(sizeof(T) == 2)>(csp[e], rv[e], srv[e]);
           *scr_sr(s) = make_float4(srv[0], srv[1], srv[2], srv[3]);
           *scr_a(s) = make_float4(av[0], av[1], av[2], av[3]);
         } else {
@@ -381,7 +381,7 @@ __global__ void __launch_bounds__(256) gscan_bwd_kernel(const GScanParams p) {
           const float av[4] = {a4.x, a4.y, a4.z, a4.w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const float si = sigmoid_f(iv[e]);
+            const float si = sigmoid_t<(sizeof(T) == 2)>(iv[e]);
             const float v = one_minus_exp_neg(2.0f * csp[e] * srv[e], av[e] * av[e]) + 1e-8f;
             const float rq = rsqrt_ftz(v), q = v * rq;
             const float dbeta = d[e] * xv[e];
