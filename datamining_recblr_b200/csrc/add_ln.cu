@@ -2,7 +2,7 @@
 //     out = LayerNorm(dropout(x) + residual) * gamma + beta          eps = 1e-12, fp32 statistics
 // as ONE kernel (the reference runs dropout, add and an ATen LayerNorm that spends ~150 us on a [102400, 64] tensor).
 // One warp per row, lanes hold 4-channel vectors (128-bit I/O), mean/variance by warp shuffles; dropout uses the same
-// Philox counter stream as the front end (embed_ln.cu), keyed by (seed [+ device counter], row, vector) and
+// counter-based hash stream as the front end (common.cuh keep_mask4), keyed by (seed [+ device counter], row, vector) and
 // regenerated in the backward.  Backward: LayerNorm backward per row -> d(sum) written as dresidual and, masked, as dx;
 // dgamma/dbeta accumulated in registers over a grid-stride loop, block-reduced, finished by a deterministic second pass.
 #include "common.cuh"
@@ -11,26 +11,8 @@ namespace bdlru {
 
 constexpr int kAV = 4;  // vectors per lane: D <= 512
 
-__device__ __forceinline__ void philox_a(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
-                                         uint32_t (&out)[4]) {
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
-    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
-    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
-  }
-  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
-}
-
 __device__ __forceinline__ void keep_scale4(uint64_t seed, long row, int vec, float p, float (&m)[4]) {
-  uint32_t r[4];
-  philox_a((uint32_t)row, (uint32_t)((uint64_t)row >> 32), (uint32_t)vec, 0x2545F491u, (uint32_t)seed,
-           (uint32_t)(seed >> 32), r);
-  const float inv = 1.0f / (1.0f - p);
-#pragma unroll
-  for (int e = 0; e < 4; ++e) m[e] = ((float)(r[e] >> 8) * (1.0f / 16777216.0f)) >= p ? inv : 0.f;
+  keep_mask4(seed ^ 0x2545F4914F6CDD1Dull, ((uint64_t)row << 8) | (uint32_t)vec, p, m);  // vec < 128
 }
 
 __device__ __forceinline__ float wsum(float v) {

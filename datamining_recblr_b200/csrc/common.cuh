@@ -104,6 +104,27 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
+// ----------------------------------------------------------------------------- dropout masks
+// Counter-based keep-mask for 4 consecutive elements: 16 random bits per element from three rounds of the lowbias32
+// integer hash keyed by (seed, 64-bit vector index).  ~18 integer instructions per 4 elements; a Philox4x32-10 call (~60)
+// made the LayerNorm kernels instruction-bound at ~50 % of HBM bandwidth.  Stateless, so the backward regenerates it.
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352du;
+  x ^= x >> 15; x *= 0x846ca68bu;
+  x ^= x >> 16;
+  return x;
+}
+__device__ __forceinline__ void keep_mask4(uint64_t seed, uint64_t vec_index, float p, float (&m)[4]) {
+  const uint32_t h = mix32(mix32((uint32_t)vec_index ^ (uint32_t)seed) ^ (uint32_t)(vec_index >> 32) ^ (uint32_t)(seed >> 32));
+  const uint32_t r0 = h, r1 = mix32(h ^ 0x68bc21ebu);
+  const uint32_t thr = (uint32_t)(p * 65536.0f);
+  const float inv = 1.0f / (1.0f - p);
+  m[0] = (r0 & 0xffffu) >= thr ? inv : 0.f;
+  m[1] = (r0 >> 16) >= thr ? inv : 0.f;
+  m[2] = (r1 & 0xffffu) >= thr ? inv : 0.f;
+  m[3] = (r1 >> 16) >= thr ? inv : 0.f;
+}
+
 // ----------------------------------------------------------------------------- math
 // Single-instruction SFU approximations (MUFU.EX2 / RCP / RSQ, flush-to-zero): ~1e-7 relative error, far
 // inside the 1e-4 budget, and none of the fix-up sequences the IEEE-rounded intrinsics expand to.

@@ -2,7 +2,7 @@
 // fused so the [B, L, D] activation makes one HBM round trip (one 4*D-byte random row read + one write).
 //
 // One warp per token; lanes hold 4-channel vectors (128-bit row reads), mean/variance by warp shuffles,
-// fp32 statistics.  Dropout uses Philox-4x32-10 keyed by (seed, token, channel vector) so the backward
+// fp32 statistics.  Dropout uses a counter-based hash (common.cuh keep_mask4) keyed by (seed, token, channel vector) so the backward
 // regenerates the mask instead of storing it.  Backward: LayerNorm backward per token, scatter-add of the
 // row gradient into dtable with vector atomics (red.global.add.v4.f32), dgamma/dbeta accumulated in
 // registers across a grid-stride loop and reduced deterministically in a second pass.
@@ -12,30 +12,9 @@ namespace bdlru {
 
 constexpr int kMaxV = 4;  // 4-channel vectors per lane: D <= 32 * 4 * kMaxV = 512
 
-__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
-                                              uint32_t k1, uint32_t (&out)[4]) {
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
-    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
-    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
-  }
-  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
-}
-
 // keep-mask * 1/(1-p) for the 4 channels of vector `vec` of token `tok`
 __device__ __forceinline__ void dropout_scale4(uint64_t seed, long tok, int vec, float p, float (&m)[4]) {
-  uint32_t r[4];
-  philox4x32_10((uint32_t)tok, (uint32_t)((uint64_t)tok >> 32), (uint32_t)vec, 0x5bd1e995u, (uint32_t)seed,
-                (uint32_t)(seed >> 32), r);
-  const float inv = 1.0f / (1.0f - p);
-#pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    const float u = (float)(r[e] >> 8) * (1.0f / 16777216.0f);  // [0, 1)
-    m[e] = u >= p ? inv : 0.f;
-  }
+  keep_mask4(seed, ((uint64_t)tok << 8) | (uint32_t)vec, p, m);  // vec < 128
 }
 
 __device__ __forceinline__ float warp_sum(float v) {
