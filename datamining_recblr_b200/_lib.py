@@ -34,6 +34,8 @@ SIGNATURES = {
     "bdlru_gated_scan_bwd_workspace_bytes": (_sz, [_i, _i, _i]),
     "bdlru_gated_scan_bwd": (_i, [View, View, View, _p, _p, _i64, View, View, View, View, View, View, View,
                                   _p, _p, _p, _sz, _i, _i, _i, _i, _p]),
+    "bdlru_phantom_h0_fwd": (_i, [_p, _p, _p, _p, _i, _i, _p, _p, _p]),
+    "bdlru_phantom_h0_bwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _p, _p, _p, _p, _p]),
     "bdlru_scan_cl_fwd": (_i, [View, View, _p, _i64, View, _i, _i, _i, _i, _p]),
     "bdlru_scan_cl_bwd": (_i, [View, _p, _i64, View, View, View, View, _p, _p, _sz, _i, _i, _i, _i, _p]),
     "bdlru_conv1d_fwd": (_i, [View, _p, _p, View, _i, _i, _i, _i, _i, _i, _p]),

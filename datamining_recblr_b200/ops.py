@@ -182,6 +182,42 @@ def gated_scan_packed(xp, ri, Lambda, h0=None, z=None):
     return out[0] if z is not None else out
 
 
+class _PhantomH0(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, conv_bias, gates_w, gates_b, Lambda, pad_len):
+        L.require_cuda(conv_bias, gates_w, gates_b, Lambda)
+        C = Lambda.shape[0]
+        assert gates_w.shape == (2 * C, C) and gates_b.shape == (2 * C,) and conv_bias.shape == (C,)
+        cb, gw, gb, lam = (t.detach().float().contiguous() for t in (conv_bias, gates_w, gates_b, Lambda))
+        h0 = torch.empty(C, dtype=torch.float32, device=lam.device)
+        saved = torch.empty(5 * C, dtype=torch.float32, device=lam.device)
+        L.check(L.load().bdlru_phantom_h0_fwd(L.ptr(cb), L.ptr(gw), L.ptr(gb), L.ptr(lam), C, int(pad_len), L.ptr(h0),
+                                              L.ptr(saved), L.stream_ptr(lam)))
+        ctx.save_for_backward(cb, gw, lam, saved)
+        ctx.meta = (int(pad_len), conv_bias.dtype, gates_w.dtype, gates_b.dtype, Lambda.dtype)
+        return h0
+
+    @staticmethod
+    def backward(ctx, dh0):
+        cb, gw, lam, saved = ctx.saved_tensors
+        pad_len, d0, d1, d2, d3 = ctx.meta
+        C = lam.shape[0]
+        dcb = torch.empty_like(cb)
+        dgw = torch.empty_like(gw)
+        dgb = torch.empty(2 * C, dtype=torch.float32, device=lam.device)
+        dlam = torch.empty_like(lam)
+        L.check(L.load().bdlru_phantom_h0_bwd(L.ptr(cb), L.ptr(gw), L.ptr(lam), L.ptr(saved),
+                                              L.ptr(dh0.float().contiguous()), C, pad_len, L.ptr(dcb), L.ptr(dgw), L.ptr(dgb),
+                                              L.ptr(dlam), L.stream_ptr(lam)))
+        return dcb.to(d0), dgw.to(d1), dgb.to(d2), dlam.to(d3), None
+
+
+def phantom_h0(conv_bias, gates_w, gates_b, Lambda, pad_len):
+    """Initial state equivalent to the reference's `pad_len` left-padded phantom steps (RecBLR.py:177-199), fp32 [C],
+    differentiable w.r.t. conv bias, gates weight/bias and Lambda — one kernel each way."""
+    return _PhantomH0.apply(conv_bias, gates_w, gates_b, Lambda, pad_len)
+
+
 class _ScanCL(torch.autograd.Function):
     @staticmethod
     def forward(ctx, a, b, h0):

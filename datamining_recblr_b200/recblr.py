@@ -273,6 +273,8 @@ class GatedRecurrentLayer(nn.Module):
         pad_len = 2 ** ((seq_len - 1).bit_length()) - seq_len
         if pad_len == 0 or self.disable_conv1d:
             return None
+        if self.Lambda.is_cuda:  # one fused kernel each way instead of ~45 tiny torch kernels per layer and step
+            return ops.phantom_h0(self.conv1d.bias, self.gates.weight, self.gates.bias, self.Lambda, pad_len)
         s = F.silu(self.conv1d.bias.float())
         rec, inp = F.linear(s, self.gates.weight.float(), self.gates.bias.float()).chunk(2, dim=-1)
         a = torch.exp(-F.softplus(self.Lambda.float()) * torch.sigmoid(rec))

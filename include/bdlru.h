@@ -91,6 +91,17 @@ int bdlru_gated_scan_bwd(bdlru_view xp, bdlru_view r, bdlru_view i, const float*
                          float* dLambda, float* dh0, void* workspace, size_t workspace_bytes,
                          int B, int T, int C, int dtype, void* stream);
 
+/* The left-pad quirk as an initial state (RecBLR.py:177-199): with s = silu(conv_bias), g = gates_w s + gates_b
+ * ([2C]: recurrence | input), a = exp(-softplus(Lambda) * sigmoid(g_rec)), b' = sqrt(1 - a^2 + 1e-8) * sigmoid(g_in) * s:
+ *   h0 = b' * sum_{k < pad_len} a^k      (fp32 [C], batch independent; pad_len = 2^ceil(log2 T) - T >= 1)
+ * `saved` is a [5*C] fp32 scratch written by fwd and read by bwd.  bwd OVERWRITES dconv_bias [C], dgates_w [2C, C],
+ * dgates_b [2C], dLambda [C] with the gradient contributions of dh0. */
+int bdlru_phantom_h0_fwd(const float* conv_bias, const float* gates_w, const float* gates_b, const float* Lambda, int C,
+                         int pad_len, float* h0, float* saved, void* stream);
+int bdlru_phantom_h0_bwd(const float* conv_bias, const float* gates_w, const float* Lambda, const float* saved,
+                         const float* dh0, int C, int pad_len, float* dconv_bias, float* dgates_w, float* dgates_b,
+                         float* dLambda, void* stream);
+
 /* Channel-last raw scan (no gate math): h_t = a_t * h_{t-1} + b_t on [B, T, C] views, fp32 or bf16 I/O.
  * Same tiling as S1; used when gates are produced elsewhere.  bwd writes da, db (and dh0 like S1). */
 int bdlru_scan_cl_fwd(bdlru_view a, bdlru_view b, const float* h0, int64_t h0_bstride, bdlru_view h,
