@@ -141,6 +141,19 @@ __device__ __forceinline__ float max32(const float (&v)[32]) {
   return max3(max3(a, b, c), max3(m[9], v[30], v[31]), -INFINITY);
 }
 
+// First index i with v[i] == m, where m = max32(v): winners of the ten triples are found independently, then a 10-long
+// select chain (instead of 31 dependent selects over the elements — the insert rounds are latency-bound).
+__device__ __forceinline__ int first_argmax32(const float (&v)[32], float m) {
+  int best = (v[30] == m) ? 30 : 31;
+#pragma unroll
+  for (int j = 9; j >= 0; --j) {
+    const float t = max3(v[3 * j], v[3 * j + 1], v[3 * j + 2]);
+    const int li = (v[3 * j] == t) ? 3 * j : ((v[3 * j + 1] == t) ? 3 * j + 1 : 3 * j + 2);
+    best = (t == m) ? li : best;
+  }
+  return best;
+}
+
 template <int UB, int MODE, int K, int NT, int NSTG>
 __global__ void __launch_bounds__(96 + 128 * UB, 1)
 fullsort_kernel(const __grid_constant__ CUtensorMap tmE, const FsParams p) {
@@ -375,9 +388,7 @@ fullsort_kernel(const __grid_constant__ CUtensorMap tmE, const FsParams p) {
               // insert rounds: lanes with a candidate act together
               while (__any_sync(0xffffffffu, m[c] > ls[K - 1] && m[c] >= sthr)) {
                 if (m[c] > ls[K - 1] && m[c] >= sthr) {
-                  int idx = 31;
-#pragma unroll
-                  for (int i = 30; i >= 0; --i) idx = (v[c][i] == m[c]) ? i : idx;  // first index among equal scores
+                  const int idx = first_argmax32(v[c], m[c]);  // first index among equal scores
                   topk_insert<K>(ls, li, m[c], id0 + idx);
 #pragma unroll
                   for (int i = 0; i < 32; ++i) v[c][i] = (i == idx) ? -INFINITY : v[c][i];
