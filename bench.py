@@ -241,7 +241,7 @@ def run_reference(args):
 # ----------------------------------------------------------------------------- our arm: training step
 def run_train(args):
     import torch.distributed as dist
-    from datamining_recblr_b200 import _lib
+    from datamining_recblr_b200 import _lib, sharded
     from datamining_recblr_b200.recblr import RecBLR
     from datamining_recblr_b200.timing import flush_l2
 
@@ -269,13 +269,8 @@ def run_train(args):
     host = [tuple(t.pin_memory() for t in b) for b in host]
     devb = [tuple(t.to(dev) for t in b) for b in host]
 
-    def allreduce_grads(ps):  # data-parallel gradient all-reduce (mean), one flat NCCL call
-        flat = torch.cat([p.grad.reshape(-1) for p in ps])
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM if model.ce_impl == "sharded" else dist.ReduceOp.AVG)
-        off = 0
-        for p in ps:
-            p.grad.copy_(flat[off:off + p.numel()].view_as(p))
-            off += p.numel()
+    def allreduce_grads(ps):
+        sharded.allreduce_gradients(ps, average=model.ce_impl != "sharded")   # one flat NCCL call, grads become views
 
     def eager_step(batch):
         inter = {"item_id_list": batch[0], "item_length": batch[1], "item_id": batch[2]}

@@ -119,6 +119,6 @@ def allreduce_gradients(params, group=None, average=True):
     flat = torch.cat([p.grad.reshape(-1) for p in ps])
     dist.all_reduce(flat, op=dist.ReduceOp.AVG if average else dist.ReduceOp.SUM, group=group)
     off = 0
-    for p in ps:
-        p.grad.copy_(flat[off:off + p.numel()].view_as(p))
+    for p in ps:  # the reduced gradients are handed back as VIEWS of the flat buffer: no copy-back kernels
+        p.grad = flat[off:off + p.numel()].view_as(p)
         off += p.numel()
