@@ -400,6 +400,7 @@ class _LinearBias(torch.autograd.Function):
 
 def linear_bias(x, weight, bias):
     """Drop-in for nn.Linear(...)(x) when the layer has a bias (autocast aware)."""
+    L.require_cuda(x, weight, bias)
     return _LinearBias.apply(x, weight, bias)
 
 

@@ -190,8 +190,8 @@ class RecBLR(SequentialRecommender):
 
 def _linear(layer, x):
     """nn.Linear with bias evaluated through ops.linear_bias (same math; fast bias gradient) on CUDA tensors."""
-    if x.is_cuda and layer.bias is not None:
-        return ops.linear_bias(x, layer.weight, layer.bias)
+    if layer.bias is not None:
+        return ops.linear_bias(x, layer.weight, layer.bias)   # raises on CPU tensors: there is no CPU path
     return layer(x)
 
 
@@ -206,7 +206,7 @@ def _dropout_seed(owner, dropout_ctx, site):
 def _silu_dropout(owner, dropout, x, dropout_ctx, site):
     """dropout(silu(x)) (RecBLR.py:219-221) through the fused kernel."""
     p = dropout.p if owner.training else 0.0
-    if not x.is_cuda or x.numel() % 8 != 0:
+    if x.numel() % 8 != 0:  # shape the kernel does not take: ATen on the same device
         return dropout(F.silu(x))
     seed, seed_dev = _dropout_seed(owner, dropout_ctx, site) if p > 0.0 else (0, None)
     return ops.silu_dropout(x, dropout_p=p, seed=seed, seed_dev=seed_dev)
@@ -216,7 +216,7 @@ def _residual_ln(owner, norm, dropout, x, residual, dropout_ctx, site):
     """LayerNorm(dropout(x) + residual) (RecBLR.py:142 / 221-225) through the fused kernel."""
     D = x.shape[-1]
     p = dropout.p if owner.training else 0.0
-    if not x.is_cuda or D % 4 != 0 or D > 512:
+    if D % 4 != 0 or D > 512:  # shape the kernel does not take: ATen on the same device
         return norm(dropout(x) + residual)
     seed, seed_dev = _dropout_seed(owner, dropout_ctx, site) if p > 0.0 else (0, None)
     return ops.add_dropout_layernorm(x, residual, norm.weight, norm.bias, eps=norm.eps, dropout_p=p, seed=seed,
@@ -273,14 +273,8 @@ class GatedRecurrentLayer(nn.Module):
         pad_len = 2 ** ((seq_len - 1).bit_length()) - seq_len
         if pad_len == 0 or self.disable_conv1d:
             return None
-        if self.Lambda.is_cuda:  # one fused kernel each way instead of ~45 tiny torch kernels per layer and step
-            return ops.phantom_h0(self.conv1d.bias, self.gates.weight, self.gates.bias, self.Lambda, pad_len)
-        s = F.silu(self.conv1d.bias.float())
-        rec, inp = F.linear(s, self.gates.weight.float(), self.gates.bias.float()).chunk(2, dim=-1)
-        a = torch.exp(-F.softplus(self.Lambda.float()) * torch.sigmoid(rec))
-        b = torch.sqrt(1 - a.pow(2) + 1e-8) * torch.sigmoid(inp) * s
-        # (1 - a^P)/(1 - a) as the explicit geometric sum's closed form; a < 1 strictly since softplus > 0
-        return b * (1 - a.pow(pad_len)) / (1 - a)
+        # one fused kernel each way (as torch ops this is ~45 tiny kernels per layer and step); CUDA only
+        return ops.phantom_h0(self.conv1d.bias, self.gates.weight, self.gates.bias, self.Lambda, pad_len)
 
     def forward(self, x):
         _, seq_len, _ = x.shape
