@@ -29,6 +29,7 @@
 
 #include "common.cuh"
 #include "tc05.cuh"
+#include "tma_host.cuh"
 
 namespace bdlru {
 
@@ -518,52 +519,6 @@ __global__ void ce_merge_kernel(const float* __restrict__ pm, const float* __res
 }
 
 // ----------------------------------------------------------------------------- host side
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (fn) return fn;
-  void* ptr = nullptr;
-  cudaDriverEntryPointQueryResult qres;
-  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
-      qres != cudaDriverEntryPointSuccess || !ptr) {
-    cudaGetLastError();
-    return nullptr;
-  }
-  fn = reinterpret_cast<EncodeTiledFn>(ptr);
-  return fn;
-}
-
-// [rows, D] bf16 row-major -> boxes of box_rows rows x 64 channels, 128-byte swizzle, zero fill out of bounds.
-static int make_map(CUtensorMap* m, const void* base, long rows, int D, int box_rows) {
-  EncodeTiledFn fn = encode_fn();
-  if (!fn) {
-    set_error("cuTensorMapEncodeTiled entry point not available");
-    return BDLRU_ERR_CUDA;
-  }
-  // The driver entry point needs the primary context bound on THIS thread; PyTorch's autograd threads only bind it
-  // lazily through runtime calls (CUDA_ERROR_INVALID_CONTEXT otherwise).  cudaFree(nullptr) binds it and is a no-op.
-  static thread_local bool bound = false;
-  if (!bound) {
-    cudaFree(nullptr);
-    bound = true;
-  }
-  cuuint64_t dims[2] = {(cuuint64_t)D, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)D * 2};
-  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%ld D=%d)", (int)r, rows, D);
-    return BDLRU_ERR_CUDA;
-  }
-  return BDLRU_OK;
-}
-
 static int fs_debug() {
   static int v = -1;
   if (v < 0) {
@@ -635,7 +590,7 @@ extern "C" BDLRU_API int bdlru_fullsort_topk(const void* Q, const void* E, int64
   BDLRU_REQUIRE(workspace && workspace_bytes >= need, "fullsort_topk: workspace %zu < %zu bytes", workspace_bytes, need);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   CUtensorMap me;
-  if ((rc = make_map(&me, E, n_rows, D, pl.NT))) return rc;
+  if ((rc = make_rows_map(&me, E, n_rows, D, pl.NT))) return rc;
   FsParams p = {};
   p.Q = Q;
   p.D = D; p.k = k; p.stages = pl.stages; p.splits = pl.splits; p.n_ug = pl.n_ug;
@@ -698,7 +653,7 @@ extern "C" BDLRU_API int bdlru_fullsort_ce_fwd(const void* Q, const void* E, con
   BDLRU_REQUIRE(workspace && workspace_bytes >= need, "fullsort_ce_fwd: workspace %zu < %zu bytes", workspace_bytes, need);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   CUtensorMap me;
-  if ((rc = make_map(&me, E, n_rows, D, pl.NT))) return rc;
+  if ((rc = make_rows_map(&me, E, n_rows, D, pl.NT))) return rc;
   FsParams p = {};
   p.Q = Q;
   p.dbg = fs_debug();

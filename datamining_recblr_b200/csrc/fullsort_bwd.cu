@@ -27,6 +27,7 @@
 
 #include "common.cuh"
 #include "tc05.cuh"
+#include "tma_host.cuh"
 
 namespace bdlru {
 
@@ -395,44 +396,6 @@ __global__ void sum_partials_kernel(const float4* __restrict__ part, long n4, in
 }
 
 // ----------------------------------------------------------------------------- host side
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static int bwd_make_map(CUtensorMap* m, const void* base, long rows, int D, int box_rows) {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* ptr = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
-        qres != cudaDriverEntryPointSuccess || !ptr) {
-      cudaGetLastError();
-      set_error("cuTensorMapEncodeTiled entry point not available");
-      return BDLRU_ERR_CUDA;
-    }
-    fn = reinterpret_cast<EncodeTiledFn>(ptr);
-  }
-  // The driver entry point needs the primary context bound on THIS thread; PyTorch's autograd threads only bind it
-  // lazily through runtime calls (CUDA_ERROR_INVALID_CONTEXT otherwise).  cudaFree(nullptr) binds it and is a no-op.
-  static thread_local bool bound = false;
-  if (!bound) {
-    cudaFree(nullptr);
-    bound = true;
-  }
-  cuuint64_t dims[2] = {(cuuint64_t)D, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)D * 2};
-  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%ld D=%d)", (int)r, rows, D);
-    return BDLRU_ERR_CUDA;
-  }
-  return BDLRU_OK;
-}
-
 struct BwdPlan {
   int NT, NSTG, stages, splits, grid;
   long row_blocks, tiles;
@@ -480,7 +443,7 @@ static int bwd_one(const void* X, long n_x, const void* Y, long n_y, int D, cons
   BwdPlan pl;
   bwd_plan(n_x, n_y, D, &pl);
   CUtensorMap my;
-  int rc = bwd_make_map(&my, Y, n_y, D, pl.NT);
+  int rc = make_rows_map(&my, Y, n_y, D, pl.NT);
   if (rc) return rc;
   BwdParams p = {};
   p.X = X; p.Y = Y; p.n_x = n_x; p.n_y = n_y; p.D = D; p.stages = pl.stages; p.splits = pl.splits;
