@@ -301,6 +301,97 @@ def causal_conv1d_channel_last(x, weight, bias=None, silu=True):
     return _Conv1dCL.apply(x, weight, bias, silu)
 
 
+class _BDLRUBlock(torch.autograd.Function):
+    """The middle of GatedRecurrentLayer.forward (RecBLR.py:174-206 without the two projections) as ONE autograd node:
+        x, z = xz.chunk(2);  x' = silu(conv(x));  (r | i) = gates(x');  y = silu(z) * scan(gate_math(x', r, i), h0)
+    Same kernels as the separate ops; what it removes is autograd glue: the gradient of xz is ONE buffer whose halves
+    are written in place by the conv backward (dx) and the scan backward (dz) instead of being concatenated, and the two
+    contributions to dx' (scan and gates GEMM) are summed inside the GEMM (addmm) instead of by an extra add kernel."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=None)
+    def forward(ctx, xz, conv_w, conv_b, gates_w, gates_b, Lambda, h0, use_conv):
+        L.require_cuda(xz, gates_w, gates_b, Lambda, h0)
+        B, T, C2 = xz.shape
+        C = C2 // 2
+        lib = L.load()
+        xz = L.as_cl(xz)
+        dt = L.dtype_tag(xz)
+        st = L.stream_ptr(xz)
+        x, z = xz[..., :C], xz[..., C:]
+        if use_conv:
+            wf = conv_w.detach().float().contiguous()
+            bf = conv_b.detach().float().contiguous()
+            xc = torch.empty((B, T, C), dtype=xz.dtype, device=xz.device)
+            L.check(lib.bdlru_conv1d_fwd(L.view3(x), L.ptr(wf), L.ptr(bf), L.view3(xc), B, T, C, wf.shape[1], 1, dt, st))
+        else:
+            wf = bf = None
+            xc = x
+        gw = gates_w.detach().to(xz.dtype)
+        gb = gates_b.detach().to(xz.dtype)
+        with torch.autocast("cuda", enabled=False):
+            ri = torch.nn.functional.linear(xc, gw, gb)          # [B, T, 2C], cuBLAS
+        Lf = Lambda.detach().float().contiguous()
+        h0f = h0.detach().float().contiguous() if h0 is not None else None
+        h = torch.empty((B, T, C), dtype=xz.dtype, device=xz.device)
+        y = torch.empty_like(h)
+        L.check(lib.bdlru_gated_scan_fwd(L.view3(xc), L.view3(ri[..., :C]), L.view3(ri[..., C:]), L.ptr(Lf), L.ptr(h0f), 0,
+                                         L.view3(z), L.view3(h), L.view3(y), B, T, C, dt, st))
+        ctx.save_for_backward(xz, xc, ri, h, wf, bf, gw, Lf, h0f)
+        ctx.meta = (use_conv, conv_w.dtype if conv_w is not None else None, conv_b.dtype if conv_b is not None else None,
+                    gates_w.dtype, gates_b.dtype, Lambda.dtype, h0.dtype if h0 is not None else None)
+        return y
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, dy):
+        xz, xc, ri, h, wf, bf, gw, Lf, h0f = ctx.saved_tensors
+        use_conv, cw_dt, cb_dt, gw_dt, gb_dt, lam_dt, h0_dt = ctx.meta
+        B, T, C2 = xz.shape
+        C = C2 // 2
+        lib = L.load()
+        dt = L.dtype_tag(xz)
+        st = L.stream_ptr(xz)
+        x, z = xz[..., :C], xz[..., C:]
+        dy = L.as_cl(dy.to(xz.dtype))
+        dxz = torch.empty((B, T, C2), dtype=xz.dtype, device=xz.device)     # (dx | dz), filled in place
+        dxc = torch.empty((B, T, C), dtype=xz.dtype, device=xz.device)
+        dri = torch.empty((B, T, C2), dtype=xz.dtype, device=xz.device)
+        dLambda = torch.empty(C, dtype=torch.float32, device=xz.device)
+        dh0 = torch.empty_like(h0f) if h0f is not None else None
+        nws = lib.bdlru_gated_scan_bwd_workspace_bytes(B, T, C)
+        ws = _workspace(xz.device, nws)
+        L.check(lib.bdlru_gated_scan_bwd(L.view3(xc), L.view3(ri[..., :C]), L.view3(ri[..., C:]), L.ptr(Lf), L.ptr(h0f), 0,
+                                         L.view3(z), L.view3(h), L.view3(dy), L.view3(dxc), L.view3(dri[..., :C]),
+                                         L.view3(dri[..., C:]), L.view3(dxz[..., C:]), L.ptr(dLambda), L.ptr(dh0), L.ptr(ws),
+                                         nws, B, T, C, dt, st))
+        dri2, xc2 = dri.view(-1, C2), xc.reshape(-1, C)
+        # d x' = scan part + dri @ W_gates, summed by the GEMM epilogue
+        dxc_tot = torch.addmm(dxc.view(-1, C), dri2, gw).view(B, T, C)
+        dgw = dri2.t() @ xc2
+        vw = 4 if dri2.dtype == torch.float32 else 8
+        dgb = colsum(dri2) if (C2 % vw == 0 and C2 // vw <= 256) else dri2.float().sum(0)
+        if use_conv:
+            dw = torch.empty_like(wf)
+            db = torch.empty(C, dtype=torch.float32, device=xz.device)
+            nwc = lib.bdlru_conv1d_bwd_workspace_bytes(B, T, C, wf.shape[1])
+            wsc = _workspace(xz.device, nwc)
+            L.check(lib.bdlru_conv1d_bwd(L.view3(x), L.ptr(wf), L.ptr(bf), L.view3(dxc_tot), L.view3(dxz[..., :C]), L.ptr(dw),
+                                         L.ptr(db), L.ptr(wsc), nwc, B, T, C, wf.shape[1], 1, dt, st))
+            dcw, dcb = dw.to(cw_dt), db.to(cb_dt)
+        else:
+            dxz[..., :C].copy_(dxc_tot)
+            dcw = dcb = None
+        return (dxz, dcw, dcb, dgw.to(gw_dt), dgb.to(gb_dt), dLambda.to(lam_dt),
+                dh0.to(h0_dt) if dh0 is not None else None, None)
+
+
+def bdlru_block(xz, conv_w, conv_b, gates_w, gates_b, Lambda, h0=None, use_conv=True):
+    """y = silu(z) * BD-LRU(silu(conv(x))) for xz = (x | z) [B, T, 2C] — conv, gates GEMM, gate math, scan and z-gate of
+    RecBLR.py:174-206 as one autograd node (see _BDLRUBlock).  conv_w [C, W], gates_w [2C, C]; autocast aware."""
+    return _BDLRUBlock.apply(xz, conv_w, conv_b, gates_w, gates_b, Lambda, h0, use_conv)
+
+
 class _EmbedLN(torch.autograd.Function):
     @staticmethod
     def forward(ctx, ids, table, gamma, beta, eps, p, seed, padding_idx, seed_dev):

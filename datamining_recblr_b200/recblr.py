@@ -278,12 +278,9 @@ class GatedRecurrentLayer(nn.Module):
 
     def forward(self, x):
         _, seq_len, _ = x.shape
-        xz = self.input(x)
-        x, z = xz.chunk(2, dim=-1)  # strided channel-last views, consumed in place by the kernels
-        if not self.disable_conv1d:
-            x = ops.causal_conv1d_channel_last(x, self.conv1d.weight.squeeze(1), self.conv1d.bias, silu=True)
-        gates = _linear(self.gates, x)  # [B, T, 2C] = (recurrence | input) halves, consumed in place
-        y = ops.gated_scan_packed(x, gates, self.Lambda, h0=self.phantom_state(seq_len), z=z)
+        xz = self.input(x)  # [B, T, 2C] = (x | z); consumed in place by the kernels, no chunk copies
+        y = ops.bdlru_block(xz, self.conv1d.weight.squeeze(1), self.conv1d.bias, self.gates.weight, self.gates.bias,
+                            self.Lambda, h0=self.phantom_state(seq_len), use_conv=not self.disable_conv1d)
         return self.output(y)
 
 
