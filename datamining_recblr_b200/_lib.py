@@ -9,7 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libbdlru.so")
 
 F32, BF16 = 0, 1
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class View(ctypes.Structure):
@@ -41,9 +41,9 @@ SIGNATURES = {
     "bdlru_conv1d_fwd": (_i, [View, _p, _p, View, _i, _i, _i, _i, _i, _i, _p]),
     "bdlru_conv1d_bwd_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "bdlru_conv1d_bwd": (_i, [View, _p, _p, View, View, _p, _p, _p, _sz, _i, _i, _i, _i, _i, _i, _p]),
-    "bdlru_embed_ln_fwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i, _f, _f, _u64, _p, _i, _p]),
+    "bdlru_embed_ln_fwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i, _f, _f, _u64, _p, _i, _i, _p]),
     "bdlru_embed_ln_bwd_workspace_bytes": (_sz, [_i64, _i]),
-    "bdlru_embed_ln_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _i64, _i64, _i, _f, _u64, _p, _i64, _i, _p]),
+    "bdlru_embed_ln_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _i64, _i64, _i, _f, _u64, _p, _i64, _i, _i, _p]),
     "bdlru_add_ln_fwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _i64, _i, _f, _f, _u64, _p, _i, _p]),
     "bdlru_add_ln_bwd_workspace_bytes": (_sz, [_i64, _i]),
     "bdlru_add_ln_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _i64, _i, _f, _u64, _p, _i, _p]),

@@ -32,10 +32,10 @@ __device__ __forceinline__ float group_sum(float v) {
   return v;
 }
 
-template <typename T, int LPR, int VPL>
+template <typename T, typename TO, int LPR, int VPL>
 __global__ void __launch_bounds__(256) embed_ln_fwd_kernel(const int64_t* __restrict__ ids, const T* __restrict__ table,
                                                            const float* __restrict__ gamma,
-                                                           const float* __restrict__ beta, T* __restrict__ out,
+                                                           const float* __restrict__ beta, TO* __restrict__ out,
                                                            float* __restrict__ mean_out, float* __restrict__ rstd_out,
                                                            long n_tokens, long n_items, int D, float eps, float p,
                                                            uint64_t seed, const uint64_t* __restrict__ seed_dev) {
@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(256) embed_ln_fwd_kernel(const int64_t* __rest
         o[1] = fmaf((x[v][1] - mean) * rstd, g4.y, b4.y);
         o[2] = fmaf((x[v][2] - mean) * rstd, g4.z, b4.z);
         o[3] = fmaf((x[v][3] - mean) * rstd, g4.w, b4.w);
-        IO<T>::store(out + n * D + vec * 4, o);
+        IO<TO>::store(out + n * D + vec * 4, o);
       }
     }
     if (live && sl == 0) {
@@ -102,9 +102,9 @@ __global__ void __launch_bounds__(256) embed_ln_fwd_kernel(const int64_t* __rest
   }
 }
 
-template <typename T, int LPR, int VPL>
+template <typename T, typename TO, int LPR, int VPL>
 __global__ void __launch_bounds__(256) embed_ln_bwd_kernel(const int64_t* __restrict__ ids, const T* __restrict__ table,
-                                                           const float* __restrict__ gamma, const T* __restrict__ dy,
+                                                           const float* __restrict__ gamma, const TO* __restrict__ dy,
                                                            const float* __restrict__ mean_in,
                                                            const float* __restrict__ rstd_in, float* __restrict__ dtable,
                                                            float* __restrict__ part /* [grid][2][D] */, long n_tokens,
@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(256) embed_ln_bwd_kernel(const int64_t* __rest
       if (live && vec < nvec) {
         float x[4], g[4];
         IO<T>::load(row + vec * 4, x);
-        IO<T>::load(dy + n * D + vec * 4, g);
+        IO<TO>::load(dy + n * D + vec * 4, g);
         if (p > 0.f) dropout_scale4(seed, n, vec, p, msk[v]);
         const float4 g4 = *reinterpret_cast<const float4*>(gamma + vec * 4);
         const float gm[4] = {g4.x, g4.y, g4.z, g4.w};
@@ -230,29 +230,33 @@ using namespace bdlru;
 extern "C" BDLRU_API int bdlru_embed_ln_fwd(const int64_t* ids, const void* table, const float* gamma,
                                             const float* beta, void* out, float* mean, float* rstd, int64_t n_tokens,
                                             int64_t n_items, int D, float eps, float dropout_p, uint64_t seed,
-                                            const uint64_t* seed_device, int dtype, void* stream) {
+                                            const uint64_t* seed_device, int dtype, int out_dtype, void* stream) {
   int rc = embed_check(n_tokens, n_items, D, dtype, dropout_p);
   if (rc) return rc;
+  BDLRU_REQUIRE(out_dtype == dtype || (dtype == BDLRU_F32 && out_dtype == BDLRU_BF16),
+                "embed_ln_fwd: out_dtype must equal the table dtype, or be bf16 for an fp32 table");
   BDLRU_REQUIRE(ids && table && gamma && beta && out && mean && rstd, "embed_ln_fwd: null pointer");
   BDLRU_REQUIRE(aligned(table, 16) && aligned(out, 16) && aligned(gamma, 16) && aligned(beta, 16),
                 "embed_ln_fwd: pointers must be 16-byte aligned");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int grid = embed_grid(n_tokens, D);
-#define EFWD_F32(LPR, VPL)                                                                                       \
-  embed_ln_fwd_kernel<float, LPR, VPL><<<grid, 256, 0, st>>>(ids, (const float*)table, gamma, beta, (float*)out,   \
-                                                             mean, rstd, n_tokens, n_items, D, eps, dropout_p, seed, \
-                                                             seed_device)
-#define EFWD_BF16(LPR, VPL)                                                                                      \
-  embed_ln_fwd_kernel<__nv_bfloat16, LPR, VPL><<<grid, 256, 0, st>>>(                                              \
-      ids, (const __nv_bfloat16*)table, gamma, beta, (__nv_bfloat16*)out, mean, rstd, n_tokens, n_items, D, eps,   \
-      dropout_p, seed, seed_device)
-  if (dtype == BDLRU_F32) {
-    EMBED_DISPATCH(D, EFWD_F32);
+#define EFWD(TT, TTO, LPR, VPL)                                                                                  \
+  embed_ln_fwd_kernel<TT, TTO, LPR, VPL><<<grid, 256, 0, st>>>(ids, (const TT*)table, gamma, beta, (TTO*)out, mean, rstd, \
+                                                               n_tokens, n_items, D, eps, dropout_p, seed, seed_device)
+#define EFWD_FF(LPR, VPL) EFWD(float, float, LPR, VPL)
+#define EFWD_BB(LPR, VPL) EFWD(__nv_bfloat16, __nv_bfloat16, LPR, VPL)
+#define EFWD_FB(LPR, VPL) EFWD(float, __nv_bfloat16, LPR, VPL)
+  if (dtype == BDLRU_F32 && out_dtype == BDLRU_F32) {
+    EMBED_DISPATCH(D, EFWD_FF);
+  } else if (dtype == BDLRU_BF16) {
+    EMBED_DISPATCH(D, EFWD_BB);
   } else {
-    EMBED_DISPATCH(D, EFWD_BF16);
+    EMBED_DISPATCH(D, EFWD_FB);
   }
-#undef EFWD_F32
-#undef EFWD_BF16
+#undef EFWD_FF
+#undef EFWD_BB
+#undef EFWD_FB
+#undef EFWD
   BDLRU_LAUNCHED();
   return BDLRU_OK;
 }
@@ -266,9 +270,12 @@ extern "C" BDLRU_API int bdlru_embed_ln_bwd(const int64_t* ids, const void* tabl
                                             const void* grad_out, const float* mean, const float* rstd, float* dtable,
                                             float* dgamma, float* dbeta, void* workspace, size_t workspace_bytes,
                                             int64_t n_tokens, int64_t n_items, int D, float dropout_p, uint64_t seed,
-                                            const uint64_t* seed_device, int64_t padding_idx, int dtype, void* stream) {
+                                            const uint64_t* seed_device, int64_t padding_idx, int dtype, int out_dtype,
+                                            void* stream) {
   int rc = embed_check(n_tokens, n_items, D, dtype, dropout_p);
   if (rc) return rc;
+  BDLRU_REQUIRE(out_dtype == dtype || (dtype == BDLRU_F32 && out_dtype == BDLRU_BF16),
+                "embed_ln_bwd: out_dtype must equal the table dtype, or be bf16 for an fp32 table");
   BDLRU_REQUIRE(ids && table && gamma && grad_out && mean && rstd && dtable && dgamma && dbeta,
                 "embed_ln_bwd: null pointer");
   BDLRU_REQUIRE(aligned(table, 16) && aligned(grad_out, 16) && aligned(dtable, 16) && aligned(gamma, 16),
@@ -280,22 +287,24 @@ extern "C" BDLRU_API int bdlru_embed_ln_bwd(const int64_t* ids, const void* tabl
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   float* part = reinterpret_cast<float*>(workspace);
   const size_t smem = (size_t)8 * embed_rpw(D) * 2 * D * sizeof(float);
-#define EBWD_F32(LPR, VPL)                                                                                         \
-  embed_ln_bwd_kernel<float, LPR, VPL><<<grid, 256, smem, st>>>(ids, (const float*)table, gamma,                     \
-                                                                (const float*)grad_out, mean, rstd, dtable, part,    \
-                                                                n_tokens, n_items, D, dropout_p, seed, seed_device,  \
-                                                                padding_idx)
-#define EBWD_BF16(LPR, VPL)                                                                                        \
-  embed_ln_bwd_kernel<__nv_bfloat16, LPR, VPL><<<grid, 256, smem, st>>>(                                             \
-      ids, (const __nv_bfloat16*)table, gamma, (const __nv_bfloat16*)grad_out, mean, rstd, dtable, part, n_tokens,   \
-      n_items, D, dropout_p, seed, seed_device, padding_idx)
-  if (dtype == BDLRU_F32) {
-    EMBED_DISPATCH(D, EBWD_F32);
+#define EBWD(TT, TTO, LPR, VPL)                                                                                       \
+  embed_ln_bwd_kernel<TT, TTO, LPR, VPL><<<grid, 256, smem, st>>>(ids, (const TT*)table, gamma, (const TTO*)grad_out, mean, \
+                                                                  rstd, dtable, part, n_tokens, n_items, D, dropout_p,      \
+                                                                  seed, seed_device, padding_idx)
+#define EBWD_FF(LPR, VPL) EBWD(float, float, LPR, VPL)
+#define EBWD_BB(LPR, VPL) EBWD(__nv_bfloat16, __nv_bfloat16, LPR, VPL)
+#define EBWD_FB(LPR, VPL) EBWD(float, __nv_bfloat16, LPR, VPL)
+  if (dtype == BDLRU_F32 && out_dtype == BDLRU_F32) {
+    EMBED_DISPATCH(D, EBWD_FF);
+  } else if (dtype == BDLRU_BF16) {
+    EMBED_DISPATCH(D, EBWD_BB);
   } else {
-    EMBED_DISPATCH(D, EBWD_BF16);
+    EMBED_DISPATCH(D, EBWD_FB);
   }
-#undef EBWD_F32
-#undef EBWD_BF16
+#undef EBWD_FF
+#undef EBWD_BB
+#undef EBWD_FB
+#undef EBWD
   BDLRU_LAUNCHED();
   return launch_colsum(part, grid, 2 * D, 2 * D, COLSUM_SPLIT, dgamma, dbeta, D, nullptr, st);
 }

@@ -368,7 +368,7 @@ class _BDLRUBlock(torch.autograd.Function):
         dri2, xc2 = dri.view(-1, C2), xc.reshape(-1, C)
         # d x' = scan part + dri @ W_gates, summed by the GEMM epilogue
         dxc_tot = torch.addmm(dxc.view(-1, C), dri2, gw).view(B, T, C)
-        dgw = dri2.t() @ xc2
+        dgw = _weight_grad(dri2, xc2, gw_dt)
         vw = 4 if dri2.dtype == torch.float32 else 8
         dgb = colsum(dri2) if (C2 % vw == 0 and C2 // vw <= 256) else dri2.float().sum(0)
         if use_conv:
@@ -382,7 +382,7 @@ class _BDLRUBlock(torch.autograd.Function):
         else:
             dxz[..., :C].copy_(dxc_tot)
             dcw = dcb = None
-        return (dxz, dcw, dcb, dgw.to(gw_dt), dgb.to(gb_dt), dLambda.to(lam_dt),
+        return (dxz, dcw, dcb, dgw, dgb.to(gb_dt), dLambda.to(lam_dt),
                 dh0.to(h0_dt) if dh0 is not None else None, None)
 
 
@@ -394,7 +394,7 @@ def bdlru_block(xz, conv_w, conv_b, gates_w, gates_b, Lambda, h0=None, use_conv=
 
 class _EmbedLN(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, ids, table, gamma, beta, eps, p, seed, padding_idx, seed_dev):
+    def forward(ctx, ids, table, gamma, beta, eps, p, seed, padding_idx, seed_dev, out_dtype):
         L.require_cuda(ids, table, gamma, beta)
         assert ids.dtype == torch.int64 and table.dim() == 2
         n_items, D = table.shape
@@ -402,24 +402,25 @@ class _EmbedLN(torch.autograd.Function):
         tab = table.detach().contiguous()
         gf, bf = gamma.detach().float().contiguous(), beta.detach().float().contiguous()
         n = ids_c.numel()
-        out = torch.empty((*ids.shape, D), dtype=table.dtype, device=table.device)
+        out_dtype = out_dtype or table.dtype
+        out = torch.empty((*ids.shape, D), dtype=out_dtype, device=table.device)
         mean = torch.empty(n, dtype=torch.float32, device=table.device)
         rstd = torch.empty_like(mean)
         L.check(L.load().bdlru_embed_ln_fwd(L.ptr(ids_c), L.ptr(tab), L.ptr(gf), L.ptr(bf), L.ptr(out), L.ptr(mean),
                                             L.ptr(rstd), n, n_items, D, float(eps), float(p), int(seed),
-                                            L.ptr(seed_dev), L.dtype_tag(tab), L.stream_ptr(tab)))
+                                            L.ptr(seed_dev), L.dtype_tag(tab), L.dtype_tag(out), L.stream_ptr(tab)))
         ctx.save_for_backward(ids_c, tab, gf, mean, rstd)
         ctx.seed_dev = seed_dev
-        ctx.args = (float(p), int(seed), int(padding_idx), gamma.dtype, beta.dtype)
+        ctx.args = (float(p), int(seed), int(padding_idx), gamma.dtype, beta.dtype, out_dtype)
         return out
 
     @staticmethod
     def backward(ctx, grad_out):
         ids_c, tab, gf, mean, rstd = ctx.saved_tensors
-        p, seed, padding_idx, g_dtype, b_dtype = ctx.args
+        p, seed, padding_idx, g_dtype, b_dtype, out_dtype = ctx.args
         n_items, D = tab.shape
         n = ids_c.numel()
-        grad_out = grad_out.to(tab.dtype).contiguous()
+        grad_out = grad_out.to(out_dtype).contiguous()
         dtable = torch.zeros((n_items, D), dtype=torch.float32, device=tab.device)
         dgamma = torch.empty(D, dtype=torch.float32, device=tab.device)
         dbeta = torch.empty_like(dgamma)
@@ -428,16 +429,18 @@ class _EmbedLN(torch.autograd.Function):
         ws = _workspace(tab.device, nws)
         L.check(lib.bdlru_embed_ln_bwd(L.ptr(ids_c), L.ptr(tab), L.ptr(gf), L.ptr(grad_out), L.ptr(mean), L.ptr(rstd),
                                        L.ptr(dtable), L.ptr(dgamma), L.ptr(dbeta), L.ptr(ws), nws, n, n_items, D, p,
-                                       seed, L.ptr(ctx.seed_dev), padding_idx, L.dtype_tag(tab), L.stream_ptr(tab)))
-        return None, dtable.to(tab.dtype), dgamma.to(g_dtype), dbeta.to(b_dtype), None, None, None, None, None
+                                       seed, L.ptr(ctx.seed_dev), padding_idx, L.dtype_tag(tab), L.dtype_tag(grad_out),
+                                       L.stream_ptr(tab)))
+        return None, dtable.to(tab.dtype), dgamma.to(g_dtype), dbeta.to(b_dtype), None, None, None, None, None, None
 
 
-def embed_layernorm(ids, table, gamma, beta, eps=1e-12, dropout_p=0.0, seed=0, padding_idx=-1, seed_dev=None):
+def embed_layernorm(ids, table, gamma, beta, eps=1e-12, dropout_p=0.0, seed=0, padding_idx=-1, seed_dev=None,
+                    out_dtype=None):
     """LayerNorm(dropout(table[ids])) in one kernel (RecBLR.py:76-78).  ids int64 [...]; returns [..., D] in
-    table.dtype.  Rows equal to padding_idx receive no gather gradient (nn.Embedding(padding_idx=0) semantics).
+    table.dtype (or out_dtype = bf16 for an fp32 table).  Rows equal to padding_idx receive no gather gradient (nn.Embedding(padding_idx=0) semantics).
     seed_dev: optional int64[1] CUDA tensor added to `seed` on the device (the mask must NOT change between this
     call's forward and backward: bump it once per step, before the forward)."""
-    return _EmbedLN.apply(ids, table, gamma, beta, eps, dropout_p, seed, padding_idx, seed_dev)
+    return _EmbedLN.apply(ids, table, gamma, beta, eps, dropout_p, seed, padding_idx, seed_dev, out_dtype)
 
 
 def colsum(x2d):
@@ -454,6 +457,15 @@ def colsum(x2d):
     return out
 
 
+def _weight_grad(dy2, x2, want_dtype):
+    """dW = dy2^T x2 in `want_dtype`; bf16 operands with an fp32 master weight accumulate and WRITE in fp32 (no bf16 rounding
+    of the gradient, no cast kernel)."""
+    with torch.autocast("cuda", enabled=False):
+        if dy2.dtype == torch.bfloat16 and want_dtype == torch.float32:
+            return torch.mm(dy2.t(), x2, out_dtype=torch.float32)
+        return (dy2.t() @ x2).to(want_dtype)
+
+
 class _LinearBias(torch.autograd.Function):
     """y = x W^T + b with the reference's nn.Linear semantics; GEMMs stay cuBLAS, only the bias gradient (a column sum
     ATen computes with a slow generic reduction) goes through bdlru_colsum."""
@@ -461,6 +473,7 @@ class _LinearBias(torch.autograd.Function):
     @staticmethod
     @torch.amp.custom_fwd(device_type="cuda", cast_inputs=None)
     def forward(ctx, x, weight, bias):
+        ctx.w_dtype = weight.dtype
         if torch.is_autocast_enabled("cuda"):
             dt = torch.get_autocast_dtype("cuda")
             x, weight, bias_c = x.to(dt), weight.to(dt), bias.to(dt)
@@ -480,7 +493,7 @@ class _LinearBias(torch.autograd.Function):
             dy2 = dy2.contiguous()
         x2 = x.reshape(-1, x.shape[-1])
         dx = (dy2 @ weight).view_as(x)
-        dw = dy2.t() @ x2
+        dw = _weight_grad(dy2, x2, ctx.w_dtype)
         vw = 4 if dy2.dtype == torch.float32 else 8
         if dy2.shape[1] % vw == 0 and dy2.shape[1] // vw <= 256 and dy2.dtype in (torch.float32, torch.bfloat16):
             db = colsum(dy2)

@@ -58,6 +58,13 @@ def softplus_inverse(x):
     return torch.log(torch.expm1(x))
 
 
+def _autocast_bf16():
+    """torch.bfloat16 under a bf16 autocast region (activations then leave the front end in bf16), else None."""
+    if torch.is_autocast_enabled("cuda") and torch.get_autocast_dtype("cuda") == torch.bfloat16:
+        return torch.bfloat16
+    return None
+
+
 def _cfg(config, key, default=None):
     """RecBole's Config returns None for unknown keys; plain dicts raise — accept both."""
     try:
@@ -133,7 +140,8 @@ class RecBLR(SequentialRecommender):
             seed = self._seed_base()
             return ops.embed_layernorm(item_seq, self.item_embedding.weight, self.layer_norm.weight,
                                        self.layer_norm.bias, eps=self.layer_norm.eps, dropout_p=p, seed=seed,
-                                       padding_idx=0, seed_dev=seed_dev)
+                                       padding_idx=0, seed_dev=seed_dev,
+                                       out_dtype=_autocast_bf16())
         return self.layer_norm(self.dropout(self.item_embedding(item_seq)))
 
     def forward(self, item_seq, item_seq_len):

@@ -127,7 +127,8 @@ int bdlru_conv1d_bwd(bdlru_view x, const float* weight, const float* bias, bdlru
 
 /* ---------------------------------------------------------------------------------------------
  * Front end: out[n,:] = LayerNorm(dropout(table[ids[n],:])) * gamma + beta   (RecBLR.py:76-78).
- * ids int64 [n_tokens]; table fp32 or bf16 [n_items, D] (dtype); out in `dtype`; gamma/beta fp32.
+ * ids int64 [n_tokens]; table fp32 or bf16 [n_items, D] (dtype); out / grad_out in `out_dtype` (= dtype, or bf16 for an
+ * fp32 table: mixed-precision training keeps fp32 master rows and bf16 activations); gamma/beta fp32.
  * Dropout (p in [0,1)) uses a counter-based generator keyed by (seed, token, channel); the mask is
  * recomputed in the backward from the same seed.  seed_device (may be NULL) points to a DEVICE uint64 added to
  * `seed` inside the kernel, so a step captured in a CUDA graph draws a fresh mask on every replay.  rstd/mean (fp32 [n_tokens]) are saved for backward.
@@ -136,14 +137,14 @@ int bdlru_conv1d_bwd(bdlru_view x, const float* weight, const float* bias, bdlru
  * ------------------------------------------------------------------------------------------- */
 int bdlru_embed_ln_fwd(const int64_t* ids, const void* table, const float* gamma, const float* beta,
                        void* out, float* mean, float* rstd, int64_t n_tokens, int64_t n_items, int D,
-                       float eps, float dropout_p, uint64_t seed, const uint64_t* seed_device, int dtype,
+                       float eps, float dropout_p, uint64_t seed, const uint64_t* seed_device, int dtype, int out_dtype,
                        void* stream);
 size_t bdlru_embed_ln_bwd_workspace_bytes(int64_t n_tokens, int D);
 int bdlru_embed_ln_bwd(const int64_t* ids, const void* table, const float* gamma, const void* grad_out,
                        const float* mean, const float* rstd, float* dtable, float* dgamma, float* dbeta,
                        void* workspace, size_t workspace_bytes, int64_t n_tokens, int64_t n_items, int D,
                        float dropout_p, uint64_t seed, const uint64_t* seed_device, int64_t padding_idx, int dtype,
-                       void* stream);
+                       int out_dtype, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Residual epilogue: out[n,:] = LayerNorm(dropout(x[n,:]) + residual[n,:]) * gamma + beta
