@@ -502,6 +502,56 @@ class _LinearBias(torch.autograd.Function):
         return dx, dw, db.to(ctx.bias_dtype)
 
 
+class _LinearTap(torch.autograd.Function):
+    """(x W^T [+ b], x): a Linear whose INPUT is also handed on as a second output (the residual branch of
+    RecurrentLayer.forward RecBLR.py:141-142 and FeedForward.forward RecBLR.py:219-225).  With x consumed by this single
+    node, the two contributions to dL/dx (through the GEMM and through the residual) are summed inside the GEMM
+    (addmm) instead of by autograd's gradient-accumulation add kernel."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=None)
+    def forward(ctx, x, weight, bias):
+        ctx.w_dtype = weight.dtype
+        ctx.b_dtype = bias.dtype if bias is not None else None
+        xc, w, b = x, weight, bias
+        if torch.is_autocast_enabled("cuda"):
+            dt = torch.get_autocast_dtype("cuda")
+            xc, w = x.to(dt), weight.to(dt)
+            b = bias.to(dt) if bias is not None else None
+        ctx.save_for_backward(xc, w)
+        ctx.x_dtype = x.dtype
+        with torch.autocast("cuda", enabled=False):
+            y = torch.nn.functional.linear(xc, w, b)
+        return y, x
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, dy, dtap):
+        xc, w = ctx.saved_tensors
+        dy2 = dy.reshape(-1, dy.shape[-1])
+        if not dy2.is_contiguous():
+            dy2 = dy2.contiguous()
+        x2 = xc.reshape(-1, xc.shape[-1])
+        with torch.autocast("cuda", enabled=False):
+            if dtap is not None:
+                dx = torch.addmm(dtap.to(dy2.dtype).reshape(-1, xc.shape[-1]), dy2, w).view_as(xc)
+            else:
+                dx = (dy2 @ w).view_as(xc)
+        dw = _weight_grad(dy2, x2, ctx.w_dtype)
+        db = None
+        if ctx.b_dtype is not None:
+            vw = 4 if dy2.dtype == torch.float32 else 8
+            ok = dy2.shape[1] % vw == 0 and dy2.shape[1] // vw <= 256 and dy2.dtype in (torch.float32, torch.bfloat16)
+            db = (colsum(dy2) if ok else dy2.float().sum(0)).to(ctx.b_dtype)
+        return dx.to(ctx.x_dtype), dw, db
+
+
+def linear_tap(x, weight, bias=None):
+    """Returns (linear(x), x) as one autograd node (see _LinearTap); autocast aware."""
+    L.require_cuda(x, weight)
+    return _LinearTap.apply(x, weight, bias)
+
+
 def linear_bias(x, weight, bias):
     """Drop-in for nn.Linear(...)(x) when the layer has a bias (autocast aware)."""
     L.require_cuda(x, weight, bias)

@@ -247,8 +247,9 @@ class RecurrentLayer(nn.Module):
     def forward(self, input_tensor, dropout_ctx=None):
         """dropout_ctx = (seed, device step counter or None): the counter stream shared by the model's fused dropouts
         (RecBLR.forward supplies it; standalone use falls back to a host-side step count)."""
-        hidden_states = self.behavior_modeling(input_tensor)
-        hidden_states = _residual_ln(self, self.layer_norm, self.dropout, hidden_states, input_tensor, dropout_ctx, 1)
+        # the layer input feeds the in-projection AND the residual: taken from one autograd node (ops.linear_tap)
+        hidden_states, residual = self.behavior_modeling(input_tensor, return_tap=True)
+        hidden_states = _residual_ln(self, self.layer_norm, self.dropout, hidden_states, residual, dropout_ctx, 1)
         if not self.disable_ffn:
             hidden_states = self.ffn(hidden_states, dropout_ctx)
         return hidden_states
@@ -284,12 +285,18 @@ class GatedRecurrentLayer(nn.Module):
         # one fused kernel each way (as torch ops this is ~45 tiny kernels per layer and step); CUDA only
         return ops.phantom_h0(self.conv1d.bias, self.gates.weight, self.gates.bias, self.Lambda, pad_len)
 
-    def forward(self, x):
+    def forward(self, x, return_tap=False):
+        """return_tap=True also returns x as a second output of the in-projection's autograd node (for the caller's
+        residual connection)."""
         _, seq_len, _ = x.shape
-        xz = self.input(x)  # [B, T, 2C] = (x | z); consumed in place by the kernels, no chunk copies
+        # [B, T, 2C] = (x | z); consumed in place by the kernels, no chunk copies
+        if return_tap:
+            xz, x = ops.linear_tap(x, self.input.weight)
+        else:
+            xz = self.input(x)
         y = ops.bdlru_block(xz, self.conv1d.weight.squeeze(1), self.conv1d.bias, self.gates.weight, self.gates.bias,
                             self.Lambda, h0=self.phantom_state(seq_len), use_conv=not self.disable_conv1d)
-        return self.output(y)
+        return (self.output(y), x) if return_tap else self.output(y)
 
 
 class FeedForward(nn.Module):
@@ -303,6 +310,7 @@ class FeedForward(nn.Module):
         self.layer_norm = nn.LayerNorm(d_model, eps=1e-12)
 
     def forward(self, input_tensor, dropout_ctx=None):
-        hidden_states = _silu_dropout(self, self.dropout, _linear(self.w_1, input_tensor), dropout_ctx, 3)
+        hidden_states, residual = ops.linear_tap(input_tensor, self.w_1.weight, self.w_1.bias)
+        hidden_states = _silu_dropout(self, self.dropout, hidden_states, dropout_ctx, 3)
         hidden_states = _linear(self.w_2, hidden_states)
-        return _residual_ln(self, self.layer_norm, self.dropout, hidden_states, input_tensor, dropout_ctx, 2)
+        return _residual_ln(self, self.layer_norm, self.dropout, hidden_states, residual, dropout_ctx, 2)
