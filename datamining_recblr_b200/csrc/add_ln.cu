@@ -203,7 +203,7 @@ static int add_ln_rpw(int D) { const int nv = D / 4; return nv <= 8 ? 4 : (nv <=
 static int add_ln_grid(long n_rows, int D) {
   const int rpb = 8 * add_ln_rpw(D);
   long blocks = (n_rows + rpb - 1) / rpb;
-  const long cap = (long)sm_count() * 8;
+  const long cap = (long)sm_count() * 4;
   if (blocks > cap) blocks = cap;
   return (int)(blocks < 1 ? 1 : blocks);
 }

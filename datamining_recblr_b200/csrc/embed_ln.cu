@@ -208,7 +208,7 @@ static int embed_rpw(int D) { const int nv = D / 4; return nv <= 8 ? 4 : (nv <= 
 static int embed_grid(long n_tokens, int D) {
   const int rpb = 8 * embed_rpw(D);
   long blocks = (n_tokens + rpb - 1) / rpb;
-  const long cap = (long)sm_count() * 8;
+  const long cap = (long)sm_count() * 4;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   return (int)blocks;
