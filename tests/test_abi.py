@@ -40,3 +40,17 @@ def test_bad_arguments_return_error_codes_without_a_gpu():
     rc = lib.bdlru_scan_fwd(None, None, None, 0, 0, None)
     assert rc == 1
     assert lib.bdlru_last_error()
+
+
+def test_ctypes_signatures_match_header_parameter_counts():
+    """Every ctypes `argtypes` list in _lib.SIGNATURES has as many entries as the C declaration in include/bdlru.h has
+    parameters (a bdlru_view passed by value counts as one) — guards against the binding drifting from the header."""
+    from datamining_recblr_b200 import _lib
+    src = open(os.path.join(ROOT, "include", "bdlru.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    decls = re.findall(r"\b(bdlru_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S)
+    assert len(decls) == len(_lib.SIGNATURES)
+    for name, params in decls:
+        params = params.strip()
+        n = 0 if params in ("", "void") else len([p for p in params.split(",") if p.strip()])
+        assert n == len(_lib.SIGNATURES[name][1]), (name, n, len(_lib.SIGNATURES[name][1]))
