@@ -153,7 +153,12 @@ class RecBLR(SequentialRecommender):
 
     @staticmethod
     def _seed_base():
-        return (torch.initial_seed() * 0x9E3779B97F4A7C15) & 0x3FFFFFFFFFFFFFFF
+        """Host part of the fused dropouts' seed: torch's global seed, decorrelated across data-parallel ranks (every rank
+        usually calls manual_seed with the same value, but must not drop the same (row, channel) positions)."""
+        rank = 0
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            rank = torch.distributed.get_rank()
+        return ((torch.initial_seed() + 0x632BE59BD9B4E019 * rank) * 0x9E3779B97F4A7C15) & 0x3FFFFFFFFFFFFFFF
 
     # ------------------------------------------------------------------ RecBLR.py:86-103
     def calculate_loss(self, interaction):
