@@ -410,10 +410,18 @@ static void bwd_plan(long n_x, long n_y, int D, BwdPlan* pl) {
   const size_t stage = (size_t)(D / 64) * pl->NT * 128;
   int stages = (int)(((size_t)kBwdSmem - 1024 - 16 * pl->NT * 4 - 512) / stage);
   pl->stages = stages > kBwdMaxStages ? kBwdMaxStages : stages;
-  long splits = (long)sm_count() / pl->row_blocks;
-  if (splits < 1) splits = 1;
+  // column splits per row block: the smallest count whose work items fill the persistent grid to >= 95 % in whole waves
+  // (e.g. 64 row blocks on 148 SMs: 2 splits leave 20 SMs idle, 9 splits = 576 items = 3.9 waves), at least 4 tiles each
+  const long sm = sm_count();
   const long max_s = pl->tiles / 4 > 0 ? pl->tiles / 4 : 1;
-  if (splits > max_s) splits = max_s;
+  long splits = 1;
+  double best = 0.0;
+  for (long s = 1; s <= max_s && s <= 64; ++s) {
+    const long n = pl->row_blocks * s;
+    const double util = (double)n / (double)(((n + sm - 1) / sm) * sm);
+    if (util > best + 1e-9) { best = util; splits = s; }
+    if (util >= 0.95) break;
+  }
   pl->splits = (int)splits;
   const long n_work = pl->row_blocks * splits;
   pl->grid = (int)(n_work < sm_count() ? n_work : sm_count());
