@@ -6,7 +6,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbdlru.so")
+# BDLRU_LIB selects another build of the SAME library (tuning variants from tools/ce_variants.py); never a fallback
+LIB_PATH = os.environ.get("BDLRU_LIB") or os.path.join(_HERE, "libbdlru.so")
 
 F32, BF16 = 0, 1
 ABI_VERSION = 3

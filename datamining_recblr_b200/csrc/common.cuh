@@ -133,6 +133,35 @@ __device__ __forceinline__ float ex2_ftz(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// 2^x on the FMA/ALU pipes instead of the SFU (the softmax epilogues of the fused CE kernels are MUFU.EX2-bound at 16
+// results/clk/SM; routing a fraction of the elements through this ~9-instruction sequence balances the two pipes).
+// Round-to-nearest split x = n + f, f in [-0.5, 0.5] (the magic-number add leaves n in the low mantissa bits), minimax
+// polynomial for 2^f (relative error 7.5e-5 at degree 3, 2.7e-6 at degree 4), n added straight into the exponent field.
+// x is clamped at -125 (result ~2e-38 instead of a denormal/0); x up to +126 is fine.
+template <int DEG>
+__device__ __forceinline__ float ex2_poly(float x) {
+  static_assert(DEG == 3 || DEG == 4, "degree");
+  x = fmaxf(x, -125.f);
+  const float xf = x + 12582912.f;
+  const float f = x - (xf - 12582912.f);
+  float p;
+  if constexpr (DEG == 3) {
+    p = fmaf(0.05517132207751274f, f, 0.24261054396629333f);
+    p = fmaf(p, f, 0.6932609677314758f);
+    p = fmaf(p, f, 0.9999281167984009f);
+  } else {
+    p = fmaf(0.009570068679749966f, f, 0.055917806923389435f);
+    p = fmaf(p, f, 0.240247443318367f);
+    p = fmaf(p, f, 0.6931218504905701f);
+    p = fmaf(p, f, 0.9999992847442627f);
+  }
+  return __int_as_float(__float_as_int(p) + (__float_as_int(xf) << 23));
+}
+// ex2 of element `i` of an unrolled 32-wide chunk: SFU, or the polynomial where bit i of MASK is set (compile time)
+template <uint32_t MASK, int DEG>
+__device__ __forceinline__ float ex2_mixed(float x, int i) {
+  return ((MASK >> (i & 31)) & 1u) ? ex2_poly<DEG>(x) : ex2_ftz(x);
+}
 __device__ __forceinline__ float rcp_ftz(float x) {
   float y;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));

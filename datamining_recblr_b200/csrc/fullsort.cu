@@ -36,6 +36,11 @@ namespace bdlru {
 constexpr int kTile = 128;                 // users per block (TMEM lanes) and items per E tile (MMA N)
 constexpr int kMaxSmem = 227 * 1024;
 constexpr int kMaxStages = 8;
+// CE forward: elements of each 32-column chunk whose exp2 runs on the FMA pipe (common.cuh ex2_mixed, degree 4)
+#ifndef BDLRU_CE_FWD_POLY_MASK
+#define BDLRU_CE_FWD_POLY_MASK 0u
+#endif
+constexpr uint32_t kPolyMaskFwd = BDLRU_CE_FWD_POLY_MASK;
 
 enum { MODE_TOPK = 0, MODE_CE = 1 };
 
@@ -412,7 +417,7 @@ fullsort_kernel(const __grid_constant__ CUtensorMap tmE, const FsParams p) {
 #pragma unroll
               for (int i = 0; i < 32; i += 4) {
 #pragma unroll
-                for (int u = 0; u < 4; ++u) acc[u] += ex2_ftz(fmaf(v[c][i + u], kLog2e, -mb));
+                for (int u = 0; u < 4; ++u) acc[u] += ex2_mixed<kPolyMaskFwd, 4>(fmaf(v[c][i + u], kLog2e, -mb), i + u);
               }
             run_s += (acc[0] + acc[1]) + (acc[2] + acc[3]);
           }

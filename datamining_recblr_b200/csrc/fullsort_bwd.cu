@@ -34,6 +34,17 @@ namespace bdlru {
 constexpr int kRows = 128;
 constexpr int kBwdMaxStages = 6;
 constexpr int kBwdSmem = 200 * 1024;
+// Which elements of each 32-column chunk take exp2 on the FMA pipe instead of the SFU (bit i = column i; common.cuh
+// ex2_mixed).  Overridable at build time for tuning (tools/ce_variants.py).  Measured at 8192 x 1 M x 128
+// (profiles/r1_ce_exp_offload.md): the dQ pass only gets slower with any offload (it runs at 0.92 of the sustained
+// tensor rate; its softmax warps are issue-bound, not SFU-bound), the dE pass gains ~3 % at 8 of 32.
+#ifndef BDLRU_CE_DQ_POLY_MASK
+#define BDLRU_CE_DQ_POLY_MASK 0u
+#endif
+#ifndef BDLRU_CE_DE_POLY_MASK
+#define BDLRU_CE_DE_POLY_MASK 0x88888888u
+#endif
+constexpr uint32_t kPolyMaskDQ = BDLRU_CE_DQ_POLY_MASK, kPolyMaskDE = BDLRU_CE_DE_POLY_MASK;
 
 struct BwdParams {
   const void* X;        // [n_x, D] bf16 rows owned by CTAs
@@ -312,10 +323,10 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const BwdParams p) {
                 const int col = c * 32 + i + u;
                 const float sv = __uint_as_float(raw[i + u]);
                 if (TRANSPOSED) {
-                  pr[u] = ex2_ftz(fmaf(sv, kLog2e, -my_lse[col]));
+                  pr[u] = ex2_mixed<TRANSPOSED ? kPolyMaskDE : kPolyMaskDQ, 3>(fmaf(sv, kLog2e, -my_lse[col]), i + u);
                   if (CHECK && my_pos[col] == (int)row_pos) pr[u] -= 1.f;
                 } else {
-                  pr[u] = ex2_ftz(fmaf(sv, kLog2e, -row_lse2));
+                  pr[u] = ex2_mixed<TRANSPOSED ? kPolyMaskDE : kPolyMaskDQ, 3>(fmaf(sv, kLog2e, -row_lse2), i + u);
                   if (CHECK && cbase + col >= p.n_y) pr[u] = 0.f;
                 }
               }

@@ -53,3 +53,41 @@ def full_sort_evaluate(model, eval_batches, topk=(10, 20), item_field="item_id",
     records = [topk_record(model, inter, inter[item_field], max(topk)) for inter in eval_batches]
     model.train(was_training)
     return metrics_from_record(torch.cat(records, dim=0), topk, decimal_place)
+
+
+@torch.no_grad()
+def evaluate_unseen_users(model, item_id_lists, item_lengths, true_item_ids, k=10, batch_size=4096,
+                          item_list_field="item_id_list", length_field="item_length"):
+    """Batched form of the reference's per-user loop `evaluate_with_preprocessing` (run_with_unseen.py:196-261):
+    that loop calls `full_sort_predict` with B = 1, copies the dense score row to the host, drops the pad column, and
+    computes sklearn's `ndcg_score(k=10)` and an argpartition Hit@10 over a dense [users, n_items - 1] matrix.  Here the
+    users go through the fused scorer `batch_size` at a time and only the [B, k] ids come back.
+
+    item_id_lists [n, L] (right-padded with 0), item_lengths [n], true_item_ids [n] are integer tensors / arrays of item
+    IDS (token -> id conversion stays with the caller); rows with true_item_ids <= 0 (unknown target, or a history that
+    could not be converted: the reference `continue`s over those) are excluded from the means, as its `valid_rows` filter
+    does.  One positive per user: ndcg@k = 1 / log2(rank + 1) if the target is ranked <= k else 0 (sklearn's value when no
+    scores tie), hit@k = target in the top k.  Returns {'hit@k': float, 'ndcg@k': float} unrounded, like the reference."""
+    dev = next(model.parameters()).device
+    lists = torch.as_tensor(item_id_lists).long()
+    lens = torch.as_tensor(item_lengths).long()
+    true = torch.as_tensor(true_item_ids).long()
+    keep = true > 0
+    if not bool(keep.any()):
+        return {f"hit@{k}": 0.0, f"ndcg@{k}": 0.0}
+    lists, lens, true = lists[keep], lens[keep], true[keep]
+    was_training = model.training
+    model.eval()
+    hit = torch.zeros((), dtype=torch.float64, device=dev)
+    ndcg = torch.zeros((), dtype=torch.float64, device=dev)
+    discount = 1.0 / torch.log2(torch.arange(2, k + 2, dtype=torch.float64, device=dev))
+    for s in range(0, lists.shape[0], batch_size):
+        inter = {item_list_field: lists[s:s + batch_size].to(dev, non_blocking=True),
+                 length_field: lens[s:s + batch_size].to(dev, non_blocking=True)}
+        _, ids = model.full_sort_topk(inter, k, mask_padding_item=True)
+        pos = (ids == true[s:s + batch_size].to(dev).view(-1, 1)).to(torch.float64)
+        hit += pos.sum()
+        ndcg += (pos * discount).sum()
+    model.train(was_training)
+    n = lists.shape[0]
+    return {f"hit@{k}": float(hit) / n, f"ndcg@{k}": float(ndcg) / n}

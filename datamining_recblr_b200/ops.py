@@ -647,16 +647,47 @@ def _bf16_rows(t):
     return t.contiguous()
 
 
-def fullsort_topk(q, table, k, mask_id=0, id_offset=0):
+BIAS_COLS = 64  # K granule of the full-sort kernels: an item bias rides the tensor cores as one extra granule
+
+
+def fullsort_bias_supported(D):
+    return fullsort_supported(D + BIAS_COLS)
+
+
+def _augment_with_bias(qb, eb, item_bias):
+    """Operands of `q @ table^T + item_bias` (the BERT4Rec scorer, bert4rec.py:230-242) as ONE bf16 GEMM with fp32
+    accumulation: q' = [q | 1 1 1 0...], table' = [table | b_hi b_mid b_lo 0...] with b = b_hi + b_mid + b_lo the EXACT
+    three-way bf16 split of the fp32 bias (3 x 8 mantissa bits), so the epilogues (top-k, softmax statistics, softmax
+    backward) need no bias path and d(bias) falls out as column D of d(table')."""
+    assert item_bias.dim() == 1 and item_bias.shape[0] == eb.shape[0]
+    b = item_bias.detach().float()
+    hi = b.to(torch.bfloat16)
+    r1 = b - hi.float()
+    mid = r1.to(torch.bfloat16)
+    lo = (r1 - mid.float()).to(torch.bfloat16)
+    B, D = qb.shape
+    qa = qb.new_zeros((B, D + BIAS_COLS))
+    qa[:, :D] = qb
+    qa[:, D:D + 3] = 1
+    ea = eb.new_zeros((eb.shape[0], D + BIAS_COLS))
+    ea[:, :D] = eb
+    ea[:, D], ea[:, D + 1], ea[:, D + 2] = hi, mid, lo
+    return qa, ea
+
+
+def fullsort_topk(q, table, k, mask_id=0, id_offset=0, item_bias=None):
     """Fused full-sort scoring + top-k (RecBLR.py:114-122 + RecBole's `scores[:, 0] = -inf; torch.topk`): returns
-    (scores fp32 [B, k], ids int32 [B, k]) of q @ table^T without forming [B, n_rows].  Operands are rounded to bf16,
-    accumulated in fp32 on the tcgen05 tensor cores; ordering is score descending, LOWEST id first among ties; the row
-    with global id `mask_id` is excluded (-1: none).  Row j of `table` has global id id_offset + j (row shards)."""
+    (scores fp32 [B, k], ids int32 [B, k]) of q @ table^T (+ item_bias [n_rows], bert4rec.py:230-242) without forming
+    [B, n_rows].  Operands are rounded to bf16, accumulated in fp32 on the tcgen05 tensor cores; ordering is score
+    descending, LOWEST id first among ties; the row with global id `mask_id` is excluded (-1: none).  Row j of `table`
+    has global id id_offset + j (row shards)."""
     L.require_cuda(q, table)
     assert q.dim() == 2 and table.dim() == 2 and q.shape[1] == table.shape[1]
-    B, D = q.shape
-    N = table.shape[0]
     qb, eb = _bf16_rows(q), _bf16_rows(table)
+    if item_bias is not None:
+        qb, eb = _augment_with_bias(qb, eb, item_bias)
+    B, D = qb.shape
+    N = table.shape[0]
     lib = L.load()
     out_s = torch.empty((B, k), dtype=torch.float32, device=q.device)
     out_i = torch.empty((B, k), dtype=torch.int32, device=q.device)
@@ -679,13 +710,15 @@ def topk_merge(cand_scores, cand_ids, k):
     return out_s, out_i
 
 
-def fullsort_ce_stats(q, table, pos, id_offset=0):
-    """Per-user (row_max, row_sumexp, pos_logit) of the logits q @ table^T over this table (shard), never materialised.
-    pos_logit is written only for users whose positive row lives in this shard (others keep 0)."""
+def fullsort_ce_stats(q, table, pos, id_offset=0, item_bias=None):
+    """Per-user (row_max, row_sumexp, pos_logit) of the logits q @ table^T (+ item_bias) over this table (shard), never
+    materialised.  pos_logit is written only for users whose positive row lives in this shard (others keep 0)."""
     L.require_cuda(q, table, pos)
-    B, D = q.shape
-    N = table.shape[0]
     qb, eb = _bf16_rows(q), _bf16_rows(table)
+    if item_bias is not None:
+        qb, eb = _augment_with_bias(qb, eb, item_bias)
+    B, D = qb.shape
+    N = table.shape[0]
     lib = L.load()
     row_max = torch.empty(B, dtype=torch.float32, device=q.device)
     row_sum = torch.empty_like(row_max)
@@ -717,25 +750,33 @@ class _FullsortCE(torch.autograd.Function):
     """mean_b(logsumexp_n(q_b . E_n) - q_b . E_pos_b) over ALL rows of E (RecBLR.py:99-103), logits never stored."""
 
     @staticmethod
-    def forward(ctx, q, table, pos):
+    def forward(ctx, q, table, pos, item_bias):
         qb, eb = _bf16_rows(q), _bf16_rows(table)
+        if item_bias is not None:
+            qb, eb = _augment_with_bias(qb, eb, item_bias)
         m, s, pl = fullsort_ce_stats(qb, eb, pos)
         lse = m + torch.log(s)
         ctx.save_for_backward(qb, eb, pos, lse)
-        ctx.dtypes = (q.dtype, table.dtype)
+        ctx.meta = (q.dtype, table.dtype, q.shape[1], None if item_bias is None else item_bias.dtype)
         return (lse - pl).mean()
 
     @staticmethod
     def backward(ctx, grad_loss):
         qb, eb, pos, lse = ctx.saved_tensors
+        qd, ed, D, bd = ctx.meta
         # dloss/dlogit = (softmax - onehot) / B, times the upstream scalar (kept on the device: no sync)
         dQ, dE = fullsort_ce_grads(qb, eb, pos, lse, 1.0 / qb.shape[0])
         g = grad_loss.float()
-        return (dQ * g).to(ctx.dtypes[0]), (dE * g).to(ctx.dtypes[1]), None
+        if bd is None:
+            return (dQ * g).to(qd), (dE * g).to(ed), None, None
+        # augmented operands: the bias gradient is the column of d(table') that multiplies q' = 1
+        return (dQ[:, :D] * g).to(qd), (dE[:, :D] * g).to(ed), None, (dE[:, D] * g).to(bd)
 
 
-def fullsort_cross_entropy(q, table, pos):
+def fullsort_cross_entropy(q, table, pos, item_bias=None):
     """Fused full-softmax cross-entropy over every row of `table` (incl. the pad row 0), mean over the
-    batch: bf16 operands, fp32 accumulation and statistics, [B, n_items] never materialised in forward or backward."""
+    batch: bf16 operands, fp32 accumulation and statistics, [B, n_items] never materialised in forward or backward.
+    `item_bias` [n_rows] adds BERT4Rec's `output_bias` to the logits (bert4rec.py:200-213; select the masked positions
+    before the call — the reference's `sum(loss * targets) / sum(targets)` is the mean over the rows with target 1)."""
     L.require_cuda(q, table, pos)
-    return _FullsortCE.apply(q, table, pos.contiguous())
+    return _FullsortCE.apply(q, table, pos.contiguous(), item_bias)

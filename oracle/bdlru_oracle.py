@@ -232,15 +232,19 @@ def recblr_forward(state, item_seq, item_seq_len, num_layers, disable_conv1d=Fal
 
 
 # ----------------------------------------------------------------------------- scoring, CE, full-sort eval
-def full_sort_scores(seq_output, item_emb):
-    """scores = seq_output @ E^T  -> [B, n_items]   (RecBLR.py:118-122)."""
-    return seq_output @ item_emb.T
+def full_sort_scores(seq_output, item_emb, item_bias=None):
+    """scores = seq_output @ E^T  -> [B, n_items]   (RecBLR.py:118-122); `+ output_bias` for the BERT4Rec baseline
+    (bert4rec.py:230-242)."""
+    s = seq_output @ item_emb.T
+    return s if item_bias is None else s + item_bias[None, :]
 
 
-def ce_loss(seq_output, item_emb, pos_items):
-    """Mean cross-entropy over ALL n_items rows incl. row 0 (RecBLR.py:99-103).
-    Returns (loss, lse[B], dQ[B,D], dE[N,D]) with gradients of the mean loss."""
-    logits = seq_output @ item_emb.T
+def ce_loss(seq_output, item_emb, pos_items, item_bias=None):
+    """Mean cross-entropy over ALL n_items rows incl. row 0 (RecBLR.py:99-103; with `item_bias`: bert4rec.py:200-213
+    restricted to the rows whose target weight is 1).
+    Returns (loss, lse[B], dQ[B,D], dE[N,D]) with gradients of the mean loss; d(item_bias) = column sums of the
+    softmax-minus-onehot matrix = `ce_bias_grad`."""
+    logits = full_sort_scores(seq_output, item_emb, item_bias)
     m = logits.max(axis=1, keepdims=True)
     lse = (m + np.log(np.exp(logits - m).sum(axis=1, keepdims=True)))[:, 0]
     B = logits.shape[0]
@@ -249,6 +253,17 @@ def ce_loss(seq_output, item_emb, pos_items):
     p[np.arange(B), pos_items] -= 1.0
     p /= B
     return loss, lse, p @ item_emb, p.T @ seq_output
+
+
+def ce_bias_grad(seq_output, item_emb, pos_items, item_bias):
+    """d(mean CE)/d(item_bias) [N] for logits = Q E^T + bias (bert4rec.py:200-213)."""
+    logits = full_sort_scores(seq_output, item_emb, item_bias)
+    m = logits.max(axis=1, keepdims=True)
+    p = np.exp(logits - m)
+    p /= p.sum(axis=1, keepdims=True)
+    B = logits.shape[0]
+    p[np.arange(B), pos_items] -= 1.0
+    return p.sum(axis=0) / B
 
 
 def topk_lowest_index(scores, k, mask_col0=True):

@@ -136,6 +136,108 @@ def test_fused_ce_forward_backward_match_oracle(B, N, D):
     assert np.abs(ge[0]).max() > 0   # the pad row receives gradient as a never/rarely-positive class (quirk 2)
 
 
+# ----------------------------------------------------------------------------- item bias (BERT4Rec scorer)
+@pytest.mark.parametrize("B,N,D,k", [(256, 1000, 64, 10), (130, 5000, 128, 20), (64, 777, 192, 10)])
+def test_topk_with_item_bias_matches_oracle(B, N, D, k):
+    """scores = Q E^T + output_bias (bert4rec.py:230-242): the fp32 bias rides the GEMM as an exact 3-way bf16 split."""
+    from datamining_recblr_b200 import ops
+    rng = np.random.default_rng(B + N + D + 1)
+    qb, eb = _bf(rng.normal(size=(B, D))), _bf(rng.normal(size=(N, D)) * 0.05)
+    bias = torch.tensor(rng.normal(size=N) * 0.5, dtype=torch.float32)   # fp32, NOT bf16-representable
+    vals, ids = ops.fullsort_topk(qb.cuda(), eb.cuda(), k, mask_id=0, item_bias=bias.cuda())
+    s = O.full_sort_scores(qb.double().numpy(), eb.double().numpy(), bias.double().numpy())
+    v_ref, i_ref = O.topk_lowest_index(s, k)
+    ids, vals = ids.cpu().numpy(), vals.cpu().numpy()
+    bad = ids != i_ref
+    for r in np.where(bad.any(axis=1))[0]:   # only fp32-accumulation near-ties may swap
+        assert np.abs(s[r, ids[r]] - s[r, i_ref[r]]).max() <= 1e-6 * np.abs(s[r, i_ref[r]]).max(), (r, ids[r], i_ref[r])
+    assert np.abs(vals - v_ref).max() <= 1e-5 * np.abs(v_ref).max()
+    # the bias must matter: without it the ranking differs
+    _, ids0 = ops.fullsort_topk(qb.cuda(), eb.cuda(), k, mask_id=0)
+    assert (ids0.cpu().numpy() != i_ref).any()
+
+
+def test_topk_with_integer_bias_exact_ties():
+    """Integer operands and integer biases: every score exact, massive ties, lowest id first."""
+    from datamining_recblr_b200 import ops
+    rng = np.random.default_rng(11)
+    B, N, D, k = 200, 3000, 64, 20
+    q = rng.integers(-2, 3, size=(B, D)).astype(np.float64)
+    e = rng.integers(-1, 2, size=(N, D)).astype(np.float64)
+    bias = rng.integers(-3, 4, size=N).astype(np.float64)
+    e[1500:], bias[1500:] = e[:1500], bias[:1500]
+    vals, ids = ops.fullsort_topk(_bf(q).cuda(), _bf(e).cuda(), k, mask_id=0, item_bias=torch.tensor(bias).float().cuda())
+    v_ref, i_ref = O.topk_lowest_index(O.full_sort_scores(q, e, bias), k)
+    assert (ids.cpu().numpy() == i_ref).all()
+    assert (vals.cpu().numpy() == v_ref).all()
+
+
+@pytest.mark.parametrize("B,N,D", [(300, 3417, 64), (130, 5000, 128), (64, 777, 192)])
+def test_fused_ce_with_item_bias_forward_backward(B, N, D):
+    """CE over logits Q E^T + bias (bert4rec.py:200-213): loss at fp32 accuracy, dQ / dE / d(bias) within the bf16-P bound."""
+    from datamining_recblr_b200 import ops
+    rng = np.random.default_rng(B * 3 + N)
+    qb, eb = _bf(rng.normal(size=(B, D)) * 2), _bf(rng.normal(size=(N, D)) * 0.3)
+    bias = rng.normal(size=N).astype(np.float32)
+    pos = rng.integers(0, N, size=B)
+    q = qb.float().cuda().requires_grad_(True)
+    e = eb.float().cuda().requires_grad_(True)
+    bt = torch.tensor(bias).cuda().requires_grad_(True)
+    loss = ops.fullsort_cross_entropy(q, e, torch.tensor(pos).cuda(), item_bias=bt)
+    (loss * 2.0).backward()
+    b64 = bias.astype(np.float64)
+    loss_ref, _, dQ, dE = O.ce_loss(qb.double().numpy(), eb.double().numpy(), pos, b64)
+    db = O.ce_bias_grad(qb.double().numpy(), eb.double().numpy(), pos, b64)
+    assert abs(float(loss) - loss_ref) <= 1e-5 * abs(loss_ref)
+    assert q.grad.shape == (B, D) and e.grad.shape == (N, D) and bt.grad.shape == (N,)
+    assert np.abs(q.grad.double().cpu().numpy() / 2 - dQ).max() <= 1e-2 * np.abs(dQ).max()
+    assert np.abs(e.grad.double().cpu().numpy() / 2 - dE).max() <= 1e-2 * np.abs(dE).max()
+    assert np.abs(bt.grad.double().cpu().numpy() / 2 - db).max() <= 1e-2 * np.abs(db).max()
+
+
+def test_baseline_model_heads_match_reference_expressions():
+    """scoring.py against the literal torch expressions of bert4rec.py:200-213,230-242 (bias, [MASK] row dropped,
+    target-weighted CE) and sasrec.py:129-133 on the same bf16-rounded operands."""
+    from datamining_recblr_b200 import scoring
+    g = torch.Generator(device="cuda").manual_seed(4)
+    B, ML, H, n_items = 48, 5, 64, 900
+    w = (torch.randn(n_items + 1, H, device="cuda", generator=g) * 0.3).bfloat16().float().requires_grad_(True)
+    bias = torch.randn(n_items, device="cuda", generator=g).requires_grad_(True)
+    seq = torch.randn(B, ML, H, device="cuda", generator=g).bfloat16().float().requires_grad_(True)
+    pos = torch.randint(0, n_items, (B, ML), device="cuda", generator=g)
+    masked_index = torch.randint(0, 3, (B, ML), device="cuda", generator=g)
+    # reference, in float64
+    w64, b64, s64 = (t.detach().double().requires_grad_(True) for t in (w, bias, seq))
+    logits = torch.matmul(s64, w64[:n_items].transpose(0, 1)) + b64
+    targets = (masked_index > 0).double().view(-1)
+    ref = torch.sum(torch.nn.CrossEntropyLoss(reduction="none")(logits.view(-1, n_items), pos.view(-1)) * targets) / targets.sum()
+    ref.backward()
+    loss = scoring.cross_entropy(seq, w, pos, n_items=n_items, output_bias=bias, targets=masked_index > 0)
+    loss.backward()
+    assert abs(float(loss) - float(ref)) <= 1e-5 * abs(float(ref))
+    for got, want in ((seq.grad, s64.grad), (w.grad, w64.grad), (bias.grad, b64.grad)):
+        assert got.shape == want.shape
+        assert (got.double() - want).abs().max() <= 1e-2 * want.abs().max()
+    assert w.grad[n_items].abs().max() == 0       # the [MASK] row takes no part in the softmax
+    # BERT4Rec full sort (last position) and SASRec (no bias, whole table)
+    q = seq[:, -1].detach()
+    sc, ids = scoring.full_sort_topk(q, w.detach(), 10, n_items=n_items, output_bias=bias.detach())
+    dense = (q.double() @ w64[:n_items].detach().T + b64.detach()).cpu().numpy()
+    v_ref, i_ref = O.topk_lowest_index(dense, 10)
+    assert (ids.cpu().numpy() == i_ref).all() and ids.dtype == torch.int64
+    sc2, ids2 = scoring.full_sort_topk(q, w.detach(), 10)
+    v2, i2 = O.topk_lowest_index((q.double() @ w64.detach().T).cpu().numpy(), 10)
+    assert (ids2.cpu().numpy() == i2).all()
+    l2 = scoring.cross_entropy(q, w.detach(), pos[:, 0])
+    ref2 = torch.nn.functional.cross_entropy(q.double() @ w64.detach().T, pos[:, 0])
+    assert abs(float(l2) - float(ref2)) <= 1e-5 * abs(float(ref2))
+
+
+def test_item_bias_unsupported_width_raises():
+    from datamining_recblr_b200 import ops
+    assert ops.fullsort_bias_supported(64) and ops.fullsort_bias_supported(192) and not ops.fullsort_bias_supported(256)
+
+
 def test_sharded_paths_on_two_gpus():
     """Launches tests/dist_check.py on 2 GPUs of this node (NCCL); skipped on a 1-GPU box."""
     import os
