@@ -55,7 +55,8 @@ struct FsParams {
   float* part_scores;
   int* part_ids;
   unsigned* shared_thr;       // [n_users] order-preserving encoding of the best K-th score seen by ANY split (0 = none)
-  // CE partials [n_users][splits] and direct outputs
+  // CE partials [n_users][ce_parts = splits * softmax warp sets] and direct outputs
+  int ce_parts;
   float* part_max;
   float* part_sum;
   const int64_t* pos;
@@ -71,7 +72,7 @@ struct FsPlan {
 // One plan for (n_users, n_rows, D): used by the launch AND by the workspace query, so both agree.
 // TMEM budget (512 columns): UB*D/2 for Q + 2*UB*NT for the double-buffered accumulators -> NT = 96 up to D = 128,
 // 64 above.
-static bool fs_plan(long n_users, long n_rows, int D, int k, FsPlan* pl) {
+static bool fs_plan(long n_users, long n_rows, int D, int k, int mode, FsPlan* pl) {
   (void)k;
   const int n_slab = D / 64;
   const int UB = n_users > kTile ? 2 : 1;
@@ -98,6 +99,24 @@ static bool fs_plan(long n_users, long n_rows, int D, int k, FsPlan* pl) {
   long want = (long)sm_count() / pl->n_ug;
   if (want < 1) want = 1;
   pl->splits = (int)(want < max_s ? want : max_s);
+  if (mode == MODE_CE) {
+    // The softmax statistics have no per-stream cost that grows with the split count (a (max, sum) pair per split), so
+    // the CE grid need not be one wave: with 32 user groups one wave is 128 CTAs on 148 SMs (ncu: SMs active 85 % of
+    // the time).  Take more, shorter streams (>= 32 tiles each) when that fills whole waves better.
+    auto eff = [&](long sp) {
+      const long ctas = (long)pl->n_ug * sp, sm = sm_count();
+      return (double)ctas / (double)(((ctas + sm - 1) / sm) * sm);
+    };
+    long best = pl->splits;
+    double best_eff = eff(best);
+    const long cap = tiles / 32 < 256 ? tiles / 32 : 256;
+    for (long sp = best + 1; sp <= cap; ++sp)
+      if (eff(sp) > best_eff + 0.02) {
+        best = sp;
+        best_eff = eff(sp);
+      }
+    pl->splits = (int)best;
+  }
   pl->threads = 96 + 128 * UB;
   pl->smem = 1024 + (size_t)stages * stage + 256;
   pl->tiles_total = tiles;
@@ -160,9 +179,20 @@ __device__ __forceinline__ int first_argmax32(const float (&v)[32], float m) {
   return best;
 }
 
-template <int UB, int MODE, int K, int NT, int NSTG>
-__global__ void __launch_bounds__(96 + 128 * UB, 1)
+// ES = epilogue warp SETS (CE only).  The softmax statistics need one MUFU.EX2 per logit (16/clk/SM: 1 536 cycles per
+// 256 x 96 tile against 768 of MMA), and with one set the two warps of each scheduler run in lock step behind the same
+// accumulator hand-off: they fight over the SFU while exponentiating and leave it idle while waiting / loading / taking
+// maxima (measured ~2 600 cycles per tile).  With two sets, set s owns tiles it = s (mod 2) and walks them one 32-column
+// chunk at a time (register budget at 19 warps), so some warp of every scheduler is always in its exp phase; each set
+// keeps its own (max, sum) pair and the merge kernel combines splits x sets partials.
+// Measured at 8192 x 1 M x 128: 3.38 -> 2.85 ms on the same box (2.77 with 64-item tiles and 3 accumulator stages, not
+// adopted: the tiling plan is shared with the top-k).  Keeping the next chunk's tcgen05.ld in flight while a chunk is
+// processed (double-buffered registers) gave 3.38 ms at 96-item tiles, i.e. nothing: dropped.
+template <int UB, int MODE, int K, int NT, int NSTG, int ES>
+__global__ void __launch_bounds__(96 + 128 * UB * ES, 1)
 fullsort_kernel(const __grid_constant__ CUtensorMap tmE, const FsParams p) {
+  static_assert(ES == 1 || MODE == MODE_CE, "a second epilogue set exists for the CE statistics only");
+  constexpr int NSETS = ES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -283,12 +313,13 @@ fullsort_kernel(const __grid_constant__ CUtensorMap tmE, const FsParams p) {
   } else {
     // ===================================================================== epilogue: thread == user
     const int e = warp - 3;
-    const int ub = e >> 2;
+    const int ub = (e >> 2) % UB;
+    const int eset = e / (4 * UB);          // epilogue set (CE with ES = 2: tiles it = eset mod 2), else 0
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;          // user row inside the block
     const long user = user0 + ub * kTile + row;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-    {
+    if (ES == 1 || eset == 0) {
       // This thread's user row of Q -> TMEM lane `row`, columns ub*D/2 .. : bf16 pairs, channel 2j in the low half.
       // The A operand of every MMA of this CTA then comes from TMEM, which halves the shared-memory operand traffic
       // (with both operands in shared memory a 128x128x16 MMA needs 128 B/clk, all the SM has: measured half rate).
@@ -328,16 +359,17 @@ fullsort_kernel(const __grid_constant__ CUtensorMap tmE, const FsParams p) {
       if (pos_local >= p.n_rows) pos_local = -1;  // positive lives in another shard (its tail rows are masked here)
     }
     constexpr float kLog2e = 1.4426950408889634f;
+    constexpr bool CLK = ES == 1;           // clock64 phase counters (BDLRU_FS_DEBUG & 8) only where registers allow
     long long te_wait = 0, te_ld = 0;
-    const long long te_begin = clock64();
-    for (int it = 0; it < n_iter; ++it) {
+    const long long te_begin = CLK ? clock64() : 0;
+    for (int it = (ES == 1 ? 0 : eset); it < n_iter; it += NSETS) {
       const int b = it % NSTG;
       const uint32_t bph = (uint32_t)(it / NSTG) & 1u;
       const long base = (t_begin + it) * NT;  // local row index of the tile's first item
       const bool special = (base + NT > p.n_rows) || (p.mask_local >= base && p.mask_local < base + NT);
-      const long long e0c = clock64();
+      const long long e0c = CLK ? clock64() : 0;
       tc::mbar_wait(&acc_full[b], bph);
-      const long long e1c = clock64();
+      const long long e1c = CLK ? clock64() : 0;
       te_wait += e1c - e0c;
       tc::fence_after_sync();
       if (share) {
@@ -348,7 +380,7 @@ fullsort_kernel(const __grid_constant__ CUtensorMap tmE, const FsParams p) {
       // The accumulator tile is pulled into registers CH chunks (CH*32 columns) at a time; once the last group has
       // landed the TMEM buffer is handed back to the MMA warp BEFORE the scores are processed, so the tensor pipe
       // only ever waits for the loads, not for the top-k / softmax arithmetic.
-      constexpr int CH = (MODE == MODE_TOPK && K > 16) ? 1 : NCH;
+      constexpr int CH = ((MODE == MODE_TOPK && K > 16) || ES > 1) ? 1 : NCH;
       if (p.dbg & 1) {
         tc::fence_before_sync();
         __syncwarp();
@@ -365,7 +397,7 @@ fullsort_kernel(const __grid_constant__ CUtensorMap tmE, const FsParams p) {
           tc::fence_before_sync();
           __syncwarp();
           if (lane == 0) tc::mbar_arrive(&acc_empty[b]);
-          te_ld += clock64() - e1c;
+          if (CLK) te_ld += clock64() - e1c;
         }
         // all CH chunk maxima first (independent trees: ILP), one vote for the common case "nothing to insert"
         float v[CH][32];
@@ -435,7 +467,7 @@ fullsort_kernel(const __grid_constant__ CUtensorMap tmE, const FsParams p) {
         }
       }
     }
-    if ((p.dbg & 8) && lane == 0 && blockIdx.x == 0 && warp == 3 && n_iter > 0)
+    if (CLK && (p.dbg & 8) && lane == 0 && blockIdx.x == 0 && warp == 3 && n_iter > 0)
       printf("[fs epilogue warp] per tile: total %lld, wait acc_full %lld, ld+release %lld cycles\n",
              (clock64() - te_begin) / n_iter, te_wait / n_iter, te_ld / n_iter);
     if (user < p.n_users) {
@@ -449,8 +481,8 @@ fullsort_kernel(const __grid_constant__ CUtensorMap tmE, const FsParams p) {
             oi[j] = li[j];
           }
       } else {
-        p.part_max[(size_t)user * p.splits + split] = run_m;
-        p.part_sum[(size_t)user * p.splits + split] = run_s;
+        p.part_max[(size_t)user * p.ce_parts + split * NSETS + eset] = run_m;
+        p.part_sum[(size_t)user * p.ce_parts + split * NSETS + eset] = run_s;
       }
     }
   }
@@ -542,31 +574,38 @@ static int fs_check(const void* Q, const void* E, long n_users, long n_rows, int
   return BDLRU_OK;
 }
 
-template <int UB, int MODE, int K, int NT, int NSTG>
+// Softmax warp sets of the CE forward (see fullsort_kernel).  BDLRU_CE_SETS=1 selects the single-set kernel (A/B runs).
+static int ce_sets() {
+  static const int v = (getenv("BDLRU_CE_SETS") && atoi(getenv("BDLRU_CE_SETS")) == 1) ? 1 : 2;
+  return v;
+}
+
+template <int UB, int MODE, int K, int NT, int NSTG, int ES>
 static int fs_launch_one(const FsPlan& pl, const CUtensorMap& me, const FsParams& p, cudaStream_t st) {
-  BDLRU_CUDA(cudaFuncSetAttribute(fullsort_kernel<UB, MODE, K, NT, NSTG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  BDLRU_CUDA(cudaFuncSetAttribute(fullsort_kernel<UB, MODE, K, NT, NSTG, ES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)pl.smem));
-  fullsort_kernel<UB, MODE, K, NT, NSTG><<<pl.n_ug * pl.splits, pl.threads, pl.smem, st>>>(me, p);
+  fullsort_kernel<UB, MODE, K, NT, NSTG, ES><<<pl.n_ug * pl.splits, 96 + 128 * UB * ES, pl.smem, st>>>(me, p);
   BDLRU_LAUNCHED();
   return BDLRU_OK;
 }
 
-template <int MODE, int K>
+template <int MODE, int K, int ES>
 static int fs_launch_k(const FsPlan& pl, const CUtensorMap& me, const FsParams& p, cudaStream_t st) {
   if (pl.NT == 96)
-    return pl.UB == 2 ? fs_launch_one<2, MODE, K, 96, 2>(pl, me, p, st) : fs_launch_one<1, MODE, K, 96, 2>(pl, me, p, st);
+    return pl.UB == 2 ? fs_launch_one<2, MODE, K, 96, 2, ES>(pl, me, p, st) : fs_launch_one<1, MODE, K, 96, 2, ES>(pl, me, p, st);
   if (pl.NSTG == 3)
-    return pl.UB == 2 ? fs_launch_one<2, MODE, K, 64, 3>(pl, me, p, st) : fs_launch_one<1, MODE, K, 64, 3>(pl, me, p, st);
-  return pl.UB == 2 ? fs_launch_one<2, MODE, K, 64, 2>(pl, me, p, st) : fs_launch_one<1, MODE, K, 64, 2>(pl, me, p, st);
+    return pl.UB == 2 ? fs_launch_one<2, MODE, K, 64, 3, ES>(pl, me, p, st) : fs_launch_one<1, MODE, K, 64, 3, ES>(pl, me, p, st);
+  return pl.UB == 2 ? fs_launch_one<2, MODE, K, 64, 2, ES>(pl, me, p, st) : fs_launch_one<1, MODE, K, 64, 2, ES>(pl, me, p, st);
 }
 
 template <int MODE>
 static int fs_launch(const FsPlan& pl, const CUtensorMap& me, const FsParams& p, cudaStream_t st) {
-  if (MODE == MODE_CE) return fs_launch_k<MODE_CE, 1>(pl, me, p, st);
-  if (p.k <= 10) return fs_launch_k<MODE_TOPK, 10>(pl, me, p, st);
-  if (p.k <= 16) return fs_launch_k<MODE_TOPK, 16>(pl, me, p, st);
-  if (p.k <= 20) return fs_launch_k<MODE_TOPK, 20>(pl, me, p, st);
-  return fs_launch_k<MODE_TOPK, 32>(pl, me, p, st);
+  if (MODE == MODE_CE)
+    return ce_sets() == 2 ? fs_launch_k<MODE_CE, 1, 2>(pl, me, p, st) : fs_launch_k<MODE_CE, 1, 1>(pl, me, p, st);
+  if (p.k <= 10) return fs_launch_k<MODE_TOPK, 10, 1>(pl, me, p, st);
+  if (p.k <= 16) return fs_launch_k<MODE_TOPK, 16, 1>(pl, me, p, st);
+  if (p.k <= 20) return fs_launch_k<MODE_TOPK, 20, 1>(pl, me, p, st);
+  return fs_launch_k<MODE_TOPK, 32, 1>(pl, me, p, st);
 }
 
 }  // namespace bdlru
@@ -577,7 +616,7 @@ extern "C" BDLRU_API int bdlru_fullsort_available(void) { return 1; }
 
 extern "C" BDLRU_API size_t bdlru_fullsort_topk_workspace_bytes(int64_t n_users, int64_t n_rows, int D, int k) {
   FsPlan pl;
-  if (D % 64 != 0 || D < 64 || D > 256 || k < 1 || k > 32 || !fs_plan(n_users, n_rows, D, k, &pl)) return 0;
+  if (D % 64 != 0 || D < 64 || D > 256 || k < 1 || k > 32 || !fs_plan(n_users, n_rows, D, k, MODE_TOPK, &pl)) return 0;
   return (size_t)n_users * pl.splits * k * 8 + (size_t)n_users * 4;
 }
 
@@ -590,7 +629,7 @@ extern "C" BDLRU_API int bdlru_fullsort_topk(const void* Q, const void* E, int64
   BDLRU_REQUIRE(out_scores && out_ids, "fullsort_topk: null outputs");
   BDLRU_REQUIRE(id_offset >= 0 && id_offset + n_rows < (1L << 31), "fullsort_topk: item ids must fit int32");
   FsPlan pl;
-  BDLRU_REQUIRE(fs_plan(n_users, n_rows, D, k, &pl), "fullsort_topk: no tiling fits shared memory (D=%d k=%d)", D, k);
+  BDLRU_REQUIRE(fs_plan(n_users, n_rows, D, k, MODE_TOPK, &pl), "fullsort_topk: no tiling fits shared memory (D=%d k=%d)", D, k);
   const size_t need = (size_t)n_users * pl.splits * k * 8 + (size_t)n_users * 4;
   BDLRU_REQUIRE(workspace && workspace_bytes >= need, "fullsort_topk: workspace %zu < %zu bytes", workspace_bytes, need);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -639,8 +678,8 @@ namespace bdlru { size_t ce_bwd_workspace_bytes(long n_users, long n_rows, int D
 
 extern "C" BDLRU_API size_t bdlru_fullsort_ce_workspace_bytes(int64_t n_users, int64_t n_rows, int D) {
   FsPlan pl;
-  if (D % 64 != 0 || D < 64 || D > 256 || !fs_plan(n_users, n_rows, D, 1, &pl)) return 0;
-  const size_t fwd = (size_t)n_users * pl.splits * 8;
+  if (D % 64 != 0 || D < 64 || D > 256 || !fs_plan(n_users, n_rows, D, 1, MODE_CE, &pl)) return 0;
+  const size_t fwd = (size_t)n_users * pl.splits * ce_sets() * 8;
   const size_t bwd = ce_bwd_workspace_bytes(n_users, n_rows, D);
   return fwd > bwd ? fwd : bwd;
 }
@@ -653,8 +692,9 @@ extern "C" BDLRU_API int bdlru_fullsort_ce_fwd(const void* Q, const void* E, con
   if (rc) return rc;
   BDLRU_REQUIRE(pos && row_max && row_sumexp && pos_logit, "fullsort_ce_fwd: null pointer");
   FsPlan pl;
-  BDLRU_REQUIRE(fs_plan(n_users, n_rows, D, 1, &pl), "fullsort_ce_fwd: no tiling fits shared memory (D=%d)", D);
-  const size_t need = (size_t)n_users * pl.splits * 8;
+  BDLRU_REQUIRE(fs_plan(n_users, n_rows, D, 1, MODE_CE, &pl), "fullsort_ce_fwd: no tiling fits shared memory (D=%d)", D);
+  const int parts = pl.splits * ce_sets();
+  const size_t need = (size_t)n_users * parts * 8;
   BDLRU_REQUIRE(workspace && workspace_bytes >= need, "fullsort_ce_fwd: workspace %zu < %zu bytes", workspace_bytes, need);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   CUtensorMap me;
@@ -665,12 +705,13 @@ extern "C" BDLRU_API int bdlru_fullsort_ce_fwd(const void* Q, const void* E, con
   p.D = D; p.k = 1; p.stages = pl.stages; p.splits = pl.splits; p.n_ug = pl.n_ug;
   p.n_users = n_users; p.n_rows = n_rows; p.id_offset = id_offset; p.mask_local = -1;
   p.tiles_total = pl.tiles_total;
+  p.ce_parts = parts;
   p.part_max = reinterpret_cast<float*>(workspace);
-  p.part_sum = p.part_max + (size_t)n_users * pl.splits;
+  p.part_sum = p.part_max + (size_t)n_users * parts;
   p.pos = pos;
   p.pos_logit = pos_logit;
   if ((rc = fs_launch<MODE_CE>(pl, me, p, st))) return rc;
-  ce_merge_kernel<<<(unsigned)((n_users + 255) / 256), 256, 0, st>>>(p.part_max, p.part_sum, n_users, pl.splits,
+  ce_merge_kernel<<<(unsigned)((n_users + 255) / 256), 256, 0, st>>>(p.part_max, p.part_sum, n_users, parts,
                                                                      row_max, row_sumexp);
   BDLRU_LAUNCHED();
   return BDLRU_OK;

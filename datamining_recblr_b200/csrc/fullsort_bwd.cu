@@ -37,12 +37,12 @@ constexpr int kBwdSmem = 200 * 1024;
 // Which elements of each 32-column chunk take exp2 on the FMA pipe instead of the SFU (bit i = column i; common.cuh
 // ex2_mixed).  Overridable at build time for tuning (tools/ce_variants.py).  Measured at 8192 x 1 M x 128
 // (profiles/r1_ce_exp_offload.md): the dQ pass only gets slower with any offload (it runs at 0.92 of the sustained
-// tensor rate; its softmax warps are issue-bound, not SFU-bound), the dE pass gains ~3 % at 8 of 32.
+// tensor rate; its softmax warps are issue-bound, not SFU-bound), the dE pass is unchanged within run-to-run noise.
 #ifndef BDLRU_CE_DQ_POLY_MASK
 #define BDLRU_CE_DQ_POLY_MASK 0u
 #endif
 #ifndef BDLRU_CE_DE_POLY_MASK
-#define BDLRU_CE_DE_POLY_MASK 0x88888888u
+#define BDLRU_CE_DE_POLY_MASK 0u
 #endif
 constexpr uint32_t kPolyMaskDQ = BDLRU_CE_DQ_POLY_MASK, kPolyMaskDE = BDLRU_CE_DE_POLY_MASK;
 

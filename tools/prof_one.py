@@ -19,6 +19,17 @@ h0 = torch.randn(C, device="cuda", requires_grad=True)
 g = torch.randn(B, T, C, device="cuda", dtype=dt)
 w = torch.randn(C, 4, device="cuda", requires_grad=True)
 bias = torch.randn(C, device="cuda", requires_grad=True)
+if op == "cefwd":   # fused CE forward statistics (tcgen05): ncu -k regex:fullsort_kernel
+    Bq, N, D = 8192, 300_000, 128
+    gq = torch.Generator(device="cuda").manual_seed(0)
+    q = torch.randn(Bq, D, device="cuda", generator=gq).to(torch.bfloat16)
+    e = (torch.randn(N, D, device="cuda", generator=gq) * 0.05).to(torch.bfloat16)
+    pos = torch.randint(0, N, (Bq,), device="cuda", generator=gq)
+    for _ in range(4):
+        ops.fullsort_ce_stats(q, e, pos)
+    torch.cuda.synchronize()
+    print("done")
+    sys.exit(0)
 for _ in range(4):
     if op == "gscan":
         r, i = ri.chunk(2, -1)
