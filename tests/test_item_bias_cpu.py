@@ -44,3 +44,16 @@ def test_bias_split_is_exact_and_augmented_gemm_equals_biased_scores():
     s0 = qb.double() @ eb.double().T + bias.double()
     s1 = qa.double() @ ea.double().T
     assert (s0[:, ok] == s1[:, ok]).all()
+
+
+def test_baseline_heads_fail_loudly_on_cpu_tensors():
+    """scoring.py is CUDA-only: no dense fallback may answer for CPU tensors (the product path must not degrade silently)."""
+    import pytest
+    from datamining_recblr_b200 import scoring
+    from datamining_recblr_b200._lib import BdlruError
+    q, w, b = torch.randn(4, 64), torch.randn(30, 64), torch.randn(30)
+    pos = torch.randint(0, 30, (4,))
+    with pytest.raises(BdlruError):
+        scoring.cross_entropy(q, w, pos, output_bias=b)
+    with pytest.raises(BdlruError):
+        scoring.full_sort_topk(q, w, 5, output_bias=b)
