@@ -24,12 +24,14 @@ def _world(group):
     return dist.get_world_size(group) if dist.is_initialized() else 1
 
 
-def sharded_topk(q, table_shard, k, id_offset, mask_id=0, group=None, local_topk=None, local_merge=None):
-    """Top-k of q @ table^T over the whole (sharded) table.  q [B, D] must be identical on every rank.
+def sharded_topk(q, table_shard, k, id_offset, mask_id=0, group=None, local_topk=None, local_merge=None, item_bias=None):
+    """Top-k of q @ table^T (+ item_bias) over the whole (sharded) table.  q [B, D] must be identical on every rank;
+    `item_bias` is this rank's slice [rows of table_shard] of the bias vector (bert4rec.py:230-242).
     Returns (scores [B, k] fp32, ids [B, k] int32), identical on every rank and to the single-table result."""
     local_topk = local_topk or ops.fullsort_topk
     local_merge = local_merge or ops.topk_merge
-    s, i = local_topk(q, table_shard, k, mask_id=mask_id, id_offset=id_offset)
+    kw = {} if item_bias is None else {"item_bias": item_bias}
+    s, i = local_topk(q, table_shard, k, mask_id=mask_id, id_offset=id_offset, **kw)
     world = _world(group)
     if world == 1:
         return s, i
@@ -58,31 +60,37 @@ def combine_ce_stats(row_max, row_sum, pos_logit, group=None):
 
 class _ShardedCE(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, q, table_shard, pos, id_offset, group, reduce_dq):
+    def forward(ctx, q, table_shard, pos, id_offset, group, reduce_dq, item_bias):
         qb, eb = ops._bf16_rows(q), ops._bf16_rows(table_shard)
+        if item_bias is not None:   # the bias rides the GEMM as 64 extra K columns (ops._augment_with_bias)
+            qb, eb = ops._augment_with_bias(qb, eb, item_bias)
         m, s, pl = ops.fullsort_ce_stats(qb, eb, pos, id_offset=id_offset)
         lse, pl = combine_ce_stats(m, s, pl, group)
         ctx.save_for_backward(qb, eb, pos, lse)
-        ctx.meta = (id_offset, group, q.dtype, table_shard.dtype, reduce_dq)
+        ctx.meta = (id_offset, group, q.dtype, table_shard.dtype, reduce_dq, q.shape[1],
+                    None if item_bias is None else item_bias.dtype)
         return (lse - pl).mean()
 
     @staticmethod
     def backward(ctx, grad_loss):
         qb, eb, pos, lse = ctx.saved_tensors
-        id_offset, group, qd, ed, reduce_dq = ctx.meta
+        id_offset, group, qd, ed, reduce_dq, D, bd = ctx.meta
         dQ, dE = ops.fullsort_ce_grads(qb, eb, pos, lse, 1.0 / qb.shape[0], id_offset=id_offset)
+        dQ = dQ[:, :D].contiguous()          # no-op without a bias; drops the gradient of the constant 1-columns
         if reduce_dq and _world(group) > 1:  # every shard contributes P_shard E_shard to dQ; dE is shard-local
             dist.all_reduce(dQ, op=dist.ReduceOp.SUM, group=group)
         g = grad_loss.float()
-        return (dQ * g).to(qd), (dE * g).to(ed), None, None, None, None
+        dbias = None if bd is None else (dE[:, D] * g).to(bd)
+        return (dQ * g).to(qd), (dE[:, :D] * g).to(ed), None, None, None, None, dbias
 
 
-def sharded_cross_entropy(q, table_shard, pos, id_offset, group=None, reduce_dq=True):
+def sharded_cross_entropy(q, table_shard, pos, id_offset, group=None, reduce_dq=True, item_bias=None):
     """Mean full-softmax CE over the whole sharded table; q [B, D] and pos [B] (GLOBAL ids) identical on every rank.
     Gradients: dtable_shard is this rank's rows; dq is the full gradient on every rank (one all-reduce) unless
     reduce_dq=False, in which case it is this shard's partial and the caller sums it (e.g. the reduce-scatter in the
-    backward of an autograd-aware all-gather)."""
-    return _ShardedCE.apply(q, table_shard, pos.contiguous(), int(id_offset), group, bool(reduce_dq))
+    backward of an autograd-aware all-gather).  `item_bias` = this rank's slice of a per-item logit bias
+    (bert4rec.py:200-213); its gradient is shard-local like the table's."""
+    return _ShardedCE.apply(q, table_shard, pos.contiguous(), int(id_offset), group, bool(reduce_dq), item_bias)
 
 
 # ----------------------------------------------------------------------------- data parallel + sharded CE (configs[4])
