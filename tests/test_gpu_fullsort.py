@@ -233,6 +233,30 @@ def test_baseline_model_heads_match_reference_expressions():
     assert abs(float(l2) - float(ref2)) <= 1e-5 * abs(float(ref2))
 
 
+@pytest.mark.parametrize("with_bias", [False, True])
+def test_sharded_ce_wrapper_single_rank_matches_fused_ce(with_bias):
+    """sharded.sharded_cross_entropy without a process group (world 1) = ops.fullsort_cross_entropy: same loss and
+    gradients (the multi-rank exchange itself is covered by the gloo tests and tests/dist_check.py)."""
+    from datamining_recblr_b200 import ops, sharded
+    g = torch.Generator(device="cuda").manual_seed(9)
+    B, N, D = 200, 2500, 64
+    q0 = torch.randn(B, D, device="cuda", generator=g)
+    e0 = torch.randn(N, D, device="cuda", generator=g) * 0.3
+    b0 = torch.randn(N, device="cuda", generator=g) if with_bias else None
+    pos = torch.randint(0, N, (B,), device="cuda", generator=g)
+    outs = []
+    for fn in (lambda q, e, b: ops.fullsort_cross_entropy(q, e, pos, item_bias=b),
+               lambda q, e, b: sharded.sharded_cross_entropy(q, e, pos, id_offset=0, item_bias=b)):
+        q, e = q0.clone().requires_grad_(True), e0.clone().requires_grad_(True)
+        b = b0.clone().requires_grad_(True) if with_bias else None
+        loss = fn(q, e, b)
+        loss.backward()
+        outs.append((loss.detach(), q.grad, e.grad, None if b is None else b.grad))
+    assert torch.equal(outs[0][0], outs[1][0])
+    for a, c in zip(outs[0][1:], outs[1][1:]):
+        assert (a is None and c is None) or torch.equal(a, c)
+
+
 def test_item_bias_unsupported_width_raises():
     from datamining_recblr_b200 import ops
     assert ops.fullsort_bias_supported(64) and ops.fullsort_bias_supported(192) and not ops.fullsort_bias_supported(256)
