@@ -29,6 +29,7 @@ SIGNATURES = {
     "bdlru_version": (_i, []),
     "bdlru_last_error": (ctypes.c_char_p, []),
     "bdlru_launch_count": (_u64, []),
+    "bdlru_build_info": (ctypes.c_char_p, []),
     "bdlru_scan_fwd": (_i, [_p, _p, _p, _i64, _i64, _p]),
     "bdlru_scan_bwd": (_i, [_p, _p, _p, _p, _p, _i64, _i64, _p]),
     "bdlru_gated_scan_fwd": (_i, [View, View, View, _p, _p, _i64, View, View, View, _i, _i, _i, _i, _p]),
@@ -131,6 +132,15 @@ def kernel_timer_stop():
     out = {n: [s.elapsed_time(e) for s, e in ev] for n, ev in TIMERS.items()}
     TIMERS.clear()
     return out
+
+
+def build_info():
+    """{'abi': int, 'digest': str, 'tuning': bool, 'matches_sources': bool} of the loaded library."""
+    from . import build as B
+    info = load().bdlru_build_info().decode()
+    dig = info.split("src=")[1].split()[0]
+    return {"abi": int(load().bdlru_version()), "digest": dig[:16], "tuning": info.endswith(" tuning"),
+            "matches_sources": dig == B.source_digest()}
 
 
 def check(rc):

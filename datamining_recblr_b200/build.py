@@ -23,6 +23,11 @@ def _sources():
     return sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
 
 
+def source_digest():
+    """sha256 over csrc/, include/ and the compile flags — also baked into the library (bdlru_build_info)."""
+    return _digest()
+
+
 def _digest():
     h = hashlib.sha256()
     for root in (CSRC, os.path.join(os.path.dirname(HERE), "include")):
@@ -44,7 +49,8 @@ def build(force=False, verbose=False):
 
     def compile_one(src):
         obj = os.path.join(OBJ, src[:-3] + ".o")
-        cmd = [NVCC, *FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        extra = [f'-DBDLRU_SOURCE_DIGEST="{dig}"'] if src == "api.cu" else []
+        cmd = [NVCC, *FLAGS, *extra, "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             print(" ".join(cmd), flush=True)
         r = subprocess.run(cmd, capture_output=True, text=True)

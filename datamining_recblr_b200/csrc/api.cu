@@ -77,3 +77,13 @@ int launch_colsum(const float* part, int n_rows, int row_stride, int n_cols, int
 extern "C" BDLRU_API int bdlru_version(void) { return 3; }
 extern "C" BDLRU_API const char* bdlru_last_error(void) { return bdlru::g_err; }
 extern "C" BDLRU_API uint64_t bdlru_launch_count(void) { return bdlru::g_launches.load(); }
+
+#ifndef BDLRU_SOURCE_DIGEST
+#define BDLRU_SOURCE_DIGEST "unknown"
+#endif
+#ifdef BDLRU_TUNING
+#define BDLRU_TUNING_TAG " tuning"
+#else
+#define BDLRU_TUNING_TAG ""
+#endif
+extern "C" BDLRU_API const char* bdlru_build_info(void) { return "src=" BDLRU_SOURCE_DIGEST BDLRU_TUNING_TAG; }

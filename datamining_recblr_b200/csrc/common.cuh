@@ -44,6 +44,23 @@ extern std::atomic<uint64_t> g_launches;
 
 int sm_count();  // SMs of the current device (cached)
 
+// Tuning switches (BDLRU_FS_DEBUG, BDLRU_FS_NT, BDLRU_CE_SETS, BDLRU_GSCAN_NS) and the clock64 phase counters exist only
+// in builds made with -DBDLRU_TUNING (tools/ce_variants.py); the shipped library ignores the environment, so a timed
+// kernel can never be told to skip its work.
+#ifdef BDLRU_TUNING
+#include <stdlib.h>
+inline int tuning_env(const char* name) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : 0;
+}
+#define FS_DBG(p) ((p).dbg)
+#define FS_CLOCK() clock64()
+#else
+inline int tuning_env(const char*) { return 0; }
+#define FS_DBG(p) 0
+#define FS_CLOCK() 0ll
+#endif
+
 // Deterministic second pass of every "per-CTA partials" reduction in this library:
 //     acc[c] = sum_{r < n_rows} part[r * row_stride + c],  c < n_cols
 // 32 columns x 32 row-lanes per CTA (coalesced 128-byte reads, fixed summation order), then an epilogue:

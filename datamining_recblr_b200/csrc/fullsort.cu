@@ -46,7 +46,8 @@ enum { MODE_TOPK = 0, MODE_CE = 1 };
 
 struct FsParams {
   int D, k, stages, splits, n_ug;
-  int dbg;  // BDLRU_FS_DEBUG (tuning only): 1 = epilogue skips loads+arithmetic, 2 = MMA warp skips the MMAs, 4 = no TMA loads
+  int dbg;  // BDLRU_FS_DEBUG, honoured ONLY in -DBDLRU_TUNING builds (never in the shipped library): 1 = epilogue skips
+            // loads+arithmetic, 2 = MMA warp skips the MMAs, 4 = no TMA loads, 8 = clock64 phase print, 16 = no threshold sharing
   const void* Q;              // [n_users, D] bf16 row-major
   long n_users, n_rows;       // rows of Q, rows of this E shard
   long id_offset, mask_local; // global id of E row 0; LOCAL row to exclude (-1: none)
@@ -77,7 +78,7 @@ static bool fs_plan(long n_users, long n_rows, int D, int k, int mode, FsPlan* p
   const int n_slab = D / 64;
   const int UB = n_users > kTile ? 2 : 1;
   // BDLRU_FS_NT=64 (tuning): 64-item tiles with 3 accumulator stages instead of 96-item tiles with 2
-  static const int force_nt = getenv("BDLRU_FS_NT") ? atoi(getenv("BDLRU_FS_NT")) : 0;
+  static const int force_nt = tuning_env("BDLRU_FS_NT");
   int NT = D <= 128 ? 96 : 64;
   if (force_nt == 64) NT = 64;
   int NSTG = 2;
@@ -248,7 +249,7 @@ fullsort_kernel(const __grid_constant__ CUtensorMap tmE, const FsParams p) {
       const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
       tc::mbar_wait(&e_empty[s], ph ^ 1u);
       if (tc::elect_one()) {
-        if (p.dbg & 4) {
+        if (FS_DBG(p) & 4) {
           tc::mbar_arrive(&e_full[s]);
         } else {
         tc::mbar_arrive_expect_tx(&e_full[s], (uint32_t)n_slab * kSlabB);
@@ -274,11 +275,11 @@ fullsort_kernel(const __grid_constant__ CUtensorMap tmE, const FsParams p) {
       const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
       const int b = it % NSTG;
       const uint32_t bph = (uint32_t)(it / NSTG) & 1u;
-      const long long c0 = clock64();
+      const long long c0 = FS_CLOCK();
       tc::mbar_wait(&acc_empty[b], bph ^ 1u);
-      const long long c1 = clock64();
+      const long long c1 = FS_CLOCK();
       tc::mbar_wait(&e_full[s], ph);
-      const long long c2 = clock64();
+      const long long c2 = FS_CLOCK();
       tc::fence_after_sync();
       if (tc::elect_one()) {
         const uint32_t e0 = tc::smem_u32(sE + (size_t)s * n_slab * kSlabB);
@@ -287,7 +288,7 @@ fullsort_kernel(const __grid_constant__ CUtensorMap tmE, const FsParams p) {
         const uint64_t bd0 = tc::smem_desc_sw128(e0, 16, 1024);
 #pragma unroll
         for (int ub = 0; ub < UB; ++ub) {
-          if (p.dbg & 2) break;
+          if (FS_DBG(p) & 2) break;
           const uint32_t d_tmem = tmem_base + acc_col0 + (uint32_t)((b * UB + ub) * NT);
           const uint32_t a_tmem = tmem_base + (uint32_t)ub * q_cols;
           for (int sl = 0; sl < n_slab; ++sl) {
@@ -304,10 +305,10 @@ fullsort_kernel(const __grid_constant__ CUtensorMap tmE, const FsParams p) {
         tc::umma_commit(&acc_full[b]);  // accumulators complete
       }
       __syncwarp();
-      const long long c3 = clock64();
+      const long long c3 = FS_CLOCK();
       t_acc += c1 - c0; t_ring += c2 - c1; t_issue += c3 - c2;
     }
-    if ((p.dbg & 8) && lane == 0 && blockIdx.x == 0 && n_iter > 1)
+    if ((FS_DBG(p) & 8) && lane == 0 && blockIdx.x == 0 && n_iter > 1)
       printf("[fs mma warp %d] tiles %d: wait acc_empty %lld, wait e_full %lld, issue %lld cycles/tile\n", warp, n_iter,
              t_acc / (n_iter / 2), t_ring / (n_iter / 2), t_issue / (n_iter / 2));
   } else {
@@ -361,15 +362,15 @@ fullsort_kernel(const __grid_constant__ CUtensorMap tmE, const FsParams p) {
     constexpr float kLog2e = 1.4426950408889634f;
     constexpr bool CLK = ES == 1;           // clock64 phase counters (BDLRU_FS_DEBUG & 8) only where registers allow
     long long te_wait = 0, te_ld = 0;
-    const long long te_begin = CLK ? clock64() : 0;
+    const long long te_begin = CLK ? FS_CLOCK() : 0;
     for (int it = (ES == 1 ? 0 : eset); it < n_iter; it += NSETS) {
       const int b = it % NSTG;
       const uint32_t bph = (uint32_t)(it / NSTG) & 1u;
       const long base = (t_begin + it) * NT;  // local row index of the tile's first item
       const bool special = (base + NT > p.n_rows) || (p.mask_local >= base && p.mask_local < base + NT);
-      const long long e0c = CLK ? clock64() : 0;
+      const long long e0c = CLK ? FS_CLOCK() : 0;
       tc::mbar_wait(&acc_full[b], bph);
-      const long long e1c = CLK ? clock64() : 0;
+      const long long e1c = CLK ? FS_CLOCK() : 0;
       te_wait += e1c - e0c;
       tc::fence_after_sync();
       if (share) {
@@ -381,7 +382,7 @@ fullsort_kernel(const __grid_constant__ CUtensorMap tmE, const FsParams p) {
       // landed the TMEM buffer is handed back to the MMA warp BEFORE the scores are processed, so the tensor pipe
       // only ever waits for the loads, not for the top-k / softmax arithmetic.
       constexpr int CH = ((MODE == MODE_TOPK && K > 16) || ES > 1) ? 1 : NCH;
-      if (p.dbg & 1) {
+      if (FS_DBG(p) & 1) {
         tc::fence_before_sync();
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&acc_empty[b]);
@@ -397,7 +398,7 @@ fullsort_kernel(const __grid_constant__ CUtensorMap tmE, const FsParams p) {
           tc::fence_before_sync();
           __syncwarp();
           if (lane == 0) tc::mbar_arrive(&acc_empty[b]);
-          if (CLK) te_ld += clock64() - e1c;
+          if (CLK) te_ld += FS_CLOCK() - e1c;
         }
         // all CH chunk maxima first (independent trees: ILP), one vote for the common case "nothing to insert"
         float v[CH][32];
@@ -467,9 +468,9 @@ fullsort_kernel(const __grid_constant__ CUtensorMap tmE, const FsParams p) {
         }
       }
     }
-    if (CLK && (p.dbg & 8) && lane == 0 && blockIdx.x == 0 && warp == 3 && n_iter > 0)
+    if (CLK && (FS_DBG(p) & 8) && lane == 0 && blockIdx.x == 0 && warp == 3 && n_iter > 0)
       printf("[fs epilogue warp] per tile: total %lld, wait acc_full %lld, ld+release %lld cycles\n",
-             (clock64() - te_begin) / n_iter, te_wait / n_iter, te_ld / n_iter);
+             (FS_CLOCK() - te_begin) / n_iter, te_wait / n_iter, te_ld / n_iter);
     if (user < p.n_users) {
       if (MODE == MODE_TOPK) {
         float* os = p.part_scores + ((size_t)user * p.splits + split) * p.k;
@@ -557,11 +558,7 @@ __global__ void ce_merge_kernel(const float* __restrict__ pm, const float* __res
 
 // ----------------------------------------------------------------------------- host side
 static int fs_debug() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("BDLRU_FS_DEBUG");
-    v = e ? atoi(e) : 0;
-  }
+  static const int v = tuning_env("BDLRU_FS_DEBUG");
   return v;
 }
 
@@ -576,7 +573,7 @@ static int fs_check(const void* Q, const void* E, long n_users, long n_rows, int
 
 // Softmax warp sets of the CE forward (see fullsort_kernel).  BDLRU_CE_SETS=1 selects the single-set kernel (A/B runs).
 static int ce_sets() {
-  static const int v = (getenv("BDLRU_CE_SETS") && atoi(getenv("BDLRU_CE_SETS")) == 1) ? 1 : 2;
+  static const int v = tuning_env("BDLRU_CE_SETS") == 1 ? 1 : 2;
   return v;
 }
 

@@ -215,7 +215,7 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const BwdParams p) {
     long g = 0;
     uint32_t wi = 0;
     long long tq_wait_s = 0, tq_math = 0, tq_wait_p = 0, tq_st = 0, tq_n = 0;
-    const long long tq_begin = clock64();
+    const long long tq_begin = FS_CLOCK();
     const int xj_per_grp = (p.D >> 4) / NG;  // 8-column groups of X handled by this warp group
     for (long w = blockIdx.x; w < n_work; w += gridDim.x, ++wi) {
       const long rb = w % p.row_blocks;
@@ -296,10 +296,10 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const BwdParams p) {
         }
         const bool tail = !TRANSPOSED && (cbase + NT > p.n_y);  // last tile: columns beyond the table contribute 0
         uint32_t packed[NT / 2];
-        const long long k0 = clock64();
+        const long long k0 = FS_CLOCK();
         tc::mbar_wait(&s_full[b], bph);
         tc::fence_after_sync();
-        const long long k1 = clock64();
+        const long long k1 = FS_CLOCK();
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
           uint32_t raw[32];
@@ -337,10 +337,10 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const BwdParams p) {
           if (TRANSPOSED ? onehot_here : tail) chunk_math(std::true_type{});
           else chunk_math(std::false_type{});
         }
-        const long long k2 = clock64();
+        const long long k2 = FS_CLOCK();
         tc::mbar_wait(&p_empty[b], bph ^ 1u);   // GEMM2 of the tile that used this P stage has completed
         tc::fence_after_sync();
-        const long long k3 = clock64();
+        const long long k3 = FS_CLOCK();
 #pragma unroll
         for (int j = 0; j < NT / 16; ++j) {
           const uint32_t wv[8] = {packed[8 * j], packed[8 * j + 1], packed[8 * j + 2], packed[8 * j + 3],
@@ -351,7 +351,7 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const BwdParams p) {
         tc::fence_before_sync();
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&p_full[b]);
-        const long long k4 = clock64();
+        const long long k4 = FS_CLOCK();
         tq_wait_s += k1 - k0; tq_math += k2 - k1; tq_wait_p += k3 - k2; tq_st += k4 - k3; ++tq_n;
       }
       // row block finished: dX accumulator -> global (scaled); 32-column chunks split over the groups
@@ -381,9 +381,9 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const BwdParams p) {
       }
       tc::fence_before_sync();
     }
-    if ((p.dbg & 8) && blockIdx.x == 0 && warp == 3 && lane == 0 && tq_n > 0)
+    if ((FS_DBG(p) & 8) && blockIdx.x == 0 && warp == 3 && lane == 0 && tq_n > 0)
       printf("[ce_bwd softmax warp, transposed=%d] own tiles %lld: total/own-tile %lld = wait s_full %lld + ld+math %lld + "
-             "wait p_empty %lld + st+arrive %lld cycles\n", (int)TRANSPOSED, tq_n, (clock64() - tq_begin) / tq_n,
+             "wait p_empty %lld + st+arrive %lld cycles\n", (int)TRANSPOSED, tq_n, (FS_CLOCK() - tq_begin) / tq_n,
              tq_wait_s / tq_n, tq_math / tq_n, tq_wait_p / tq_n, tq_st / tq_n);
   }
   tc::fence_before_sync();
@@ -468,7 +468,7 @@ static int bwd_one(const void* X, long n_x, const void* Y, long n_y, int D, cons
   p.X = X; p.Y = Y; p.n_x = n_x; p.n_y = n_y; p.D = D; p.stages = pl.stages; p.splits = pl.splits;
   p.row_blocks = pl.row_blocks; p.tiles_total = pl.tiles;
   p.lse = lse; p.pos = pos; p.n_users = n_users; p.id_offset = id_offset; p.scale = scale;
-  p.dbg = getenv("BDLRU_FS_DEBUG") ? atoi(getenv("BDLRU_FS_DEBUG")) : 0;
+  p.dbg = tuning_env("BDLRU_FS_DEBUG");
   p.out = pl.splits > 1 ? scratch : grad;
   if ((rc = bwd_launch<TR>(pl, my, p, st))) return rc;
   if (pl.splits > 1) {

@@ -446,7 +446,7 @@ static Tiling make_tiling(int B, int T, int C) {
   // time slices per CTA: enough to cover T when it is short, at most 256 threads / 32 slices
   int ns = 256 / t.tcn;
   if (ns > 32) ns = 32;  // tcn < 8 (C/4 not a multiple of 8): fewer threads rather than a long combine loop
-  static const int force_ns = getenv("BDLRU_GSCAN_NS") ? atoi(getenv("BDLRU_GSCAN_NS")) : 0;  // tuning
+  static const int force_ns = tuning_env("BDLRU_GSCAN_NS");
   if (force_ns > 0 && force_ns < ns) ns = force_ns;
   t.NS = ns;
   (void)T;

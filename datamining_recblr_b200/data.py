@@ -118,6 +118,7 @@ class PinnedBatchLoader:
             self.stage = [(torch.empty((batch_size, L), dtype=torch.int32).pin_memory(),
                            torch.empty(batch_size, dtype=torch.int32).pin_memory(),
                            torch.empty(batch_size, dtype=torch.int32).pin_memory()) for _ in range(2)]
+            self.slot_done = [None, None]   # event of the last H2D copy issued FROM each staging slot
 
     def __len__(self):
         n = len(self.a)
@@ -138,6 +139,8 @@ class PinnedBatchLoader:
         if not self.cuda:
             return (self.hist[idx].long(), self.length[idx].long(), self.target[idx].long()), None
         h, l, t = self.stage[slot]
+        if self.slot_done[slot] is not None:
+            self.slot_done[slot].synchronize()   # the copy that last read this pinned slot must be over before regathering
         torch.index_select(self.hist, 0, idx, out=h[:n])
         torch.index_select(self.length, 0, idx, out=l[:n])
         torch.index_select(self.target, 0, idx, out=t[:n])
@@ -145,6 +148,7 @@ class PinnedBatchLoader:
             dev = tuple(x[:n].to(self.device, non_blocking=True).long() for x in (h, l, t))
             ev = torch.cuda.Event()
             ev.record(self.stream)
+        self.slot_done[slot] = ev
         return dev, ev
 
     def __iter__(self):

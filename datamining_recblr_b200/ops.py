@@ -43,16 +43,12 @@ def parallel_scan(gates, tokens):
     return _ScanBCT.apply(gates, tokens)
 
 
-_WS = {}
-
-
 def _workspace(device, nbytes):
-    key = (device.type, device.index)
-    buf = _WS.get(key)
-    if buf is None or buf.numel() < nbytes:
-        buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
-        _WS[key] = buf
-    return buf
+    """Scratch for ONE kernel call, owned by the caching allocator (or, under capture, by the CUDA graph's private pool):
+    its lifetime follows stream order like any other tensor, so a captured graph can never be left pointing at a buffer
+    that a later, larger eager call replaced (a cached grow-on-demand buffer had exactly that hazard), and two streams
+    never share scratch."""
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
 
 
 class _GatedScan(torch.autograd.Function):
@@ -710,10 +706,20 @@ def topk_merge(cand_scores, cand_ids, k):
     return out_s, out_i
 
 
+def _check_pos(pos, n_users):
+    """The kernels read the positives as `const int64_t*`: anything else would be read out of bounds."""
+    assert pos.dim() == 1 and pos.shape[0] == n_users, f"pos must be [{n_users}], got {tuple(pos.shape)}"
+    if pos.dtype != torch.int64:
+        assert not pos.dtype.is_floating_point, f"pos must hold integer item ids, got {pos.dtype}"
+        pos = pos.long()
+    return pos.contiguous()
+
+
 def fullsort_ce_stats(q, table, pos, id_offset=0, item_bias=None):
     """Per-user (row_max, row_sumexp, pos_logit) of the logits q @ table^T (+ item_bias) over this table (shard), never
     materialised.  pos_logit is written only for users whose positive row lives in this shard (others keep 0)."""
     L.require_cuda(q, table, pos)
+    pos = _check_pos(pos, q.shape[0])
     qb, eb = _bf16_rows(q), _bf16_rows(table)
     if item_bias is not None:
         qb, eb = _augment_with_bias(qb, eb, item_bias)
@@ -734,6 +740,7 @@ def fullsort_ce_grads(qb, eb, pos, lse, scale, id_offset=0):
     """(dQ [B, D], dE [rows, D]) fp32 of scale * sum_b(lse_b - logit_{b,pos_b}) for bf16 qb, eb and the GLOBAL lse;
     the logits are recomputed tile by tile on the tensor cores and never stored."""
     L.require_cuda(qb, eb, pos, lse)
+    pos = _check_pos(pos, qb.shape[0])
     B, D = qb.shape
     N = eb.shape[0]
     lib = L.load()
@@ -779,4 +786,4 @@ def fullsort_cross_entropy(q, table, pos, item_bias=None):
     `item_bias` [n_rows] adds BERT4Rec's `output_bias` to the logits (bert4rec.py:200-213; select the masked positions
     before the call — the reference's `sum(loss * targets) / sum(targets)` is the mean over the rows with target 1)."""
     L.require_cuda(q, table, pos)
-    return _FullsortCE.apply(q, table, pos.contiguous(), item_bias)
+    return _FullsortCE.apply(q, table, _check_pos(pos, q.shape[0]), item_bias)

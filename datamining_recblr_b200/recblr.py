@@ -55,7 +55,7 @@ except ImportError:  # the attributes RecBLR.py:20,37-38,83,87-92 rely on (SURVE
 
 
 def softplus_inverse(x):
-    return torch.log(torch.expm1(x))
+    return torch.log(torch.exp(x) - 1)  # the reference's exact expression (RecBLR.py:14-15): bit-identical fresh inits
 
 
 def _autocast_bf16():
@@ -133,10 +133,7 @@ class RecBLR(SequentialRecommender):
         p = self.dropout_prob if self.training else 0.0
         D = self.hidden_size
         if self.fused_front and D % 4 == 0 and D <= 512:
-            seed_dev = None
-            if p > 0.0:
-                self._dropout_step.add_(1)
-                seed_dev = self._dropout_step
+            seed_dev = self._dropout_step if p > 0.0 else None   # advanced once per training forward (RecBLR.forward)
             seed = self._seed_base()
             return ops.embed_layernorm(item_seq, self.item_embedding.weight, self.layer_norm.weight,
                                        self.layer_norm.bias, eps=self.layer_norm.eps, dropout_p=p, seed=seed,
@@ -145,8 +142,13 @@ class RecBLR(SequentialRecommender):
         return self.layer_norm(self.dropout(self.item_embedding(item_seq)))
 
     def forward(self, item_seq, item_seq_len):
+        dropping = self.training and self.dropout_prob > 0
+        if dropping:
+            # one tick per training forward, whichever front-end path runs: every fused dropout site of this step
+            # (front end, residual LayerNorms, FFN) derives its mask from (seed, this counter, site)
+            self._dropout_step.add_(1)
         item_emb = self._front(item_seq)
-        ctx = (self._seed_base(), self._dropout_step if self.training and self.dropout_prob > 0 else None)
+        ctx = (self._seed_base(), self._dropout_step if dropping else None)
         for i, layer in enumerate(self.recurrent_layers):
             item_emb = layer(item_emb, dropout_ctx=(ctx[0] + 7919 * (i + 1), ctx[1]))
         return self.gather_indexes(item_emb, item_seq_len - 1)

@@ -90,7 +90,8 @@ def sharded_cross_entropy(q, table_shard, pos, id_offset, group=None, reduce_dq=
     reduce_dq=False, in which case it is this shard's partial and the caller sums it (e.g. the reduce-scatter in the
     backward of an autograd-aware all-gather).  `item_bias` = this rank's slice of a per-item logit bias
     (bert4rec.py:200-213); its gradient is shard-local like the table's."""
-    return _ShardedCE.apply(q, table_shard, pos.contiguous(), int(id_offset), group, bool(reduce_dq), item_bias)
+    return _ShardedCE.apply(q, table_shard, ops._check_pos(pos, q.shape[0]), int(id_offset), group, bool(reduce_dq),
+                            item_bias)
 
 
 # ----------------------------------------------------------------------------- data parallel + sharded CE (configs[4])

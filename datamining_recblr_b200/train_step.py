@@ -41,7 +41,18 @@ class GraphedTrainStep:
         return loss.detach()
 
     def __call__(self, interaction):
+        """Replays the captured step when the batch has the captured shapes; any other batch (the ragged last batch of
+        a RecBole epoch) runs the same body eagerly — same kernels, same optimizer state, no graph."""
+        if any(tuple(interaction[k].shape) != tuple(v.shape) for k, v in self.static.items()):
+            return self._eager(interaction)
         for k, v in self.static.items():
             v.copy_(interaction[k], non_blocking=True)
         self.graph.replay()
         return self.loss
+
+    def _eager(self, interaction):
+        static, self.static = self.static, {k: interaction[k] for k in self.static}
+        try:
+            return self._body()
+        finally:
+            self.static = static

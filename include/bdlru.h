@@ -44,6 +44,9 @@ int bdlru_version(void);
 const char* bdlru_last_error(void);
 /* Number of kernel launches enqueued by this library since process start (bench.py's gpu_launches). */
 uint64_t bdlru_launch_count(void);
+/* "src=<sha256 of csrc/ + include/ + flags>[ tuning]": which sources this binary was built from, and whether it is a
+ * -DBDLRU_TUNING build (the only kind that reads BDLRU_* environment switches).  bench.py refuses tuning builds. */
+const char* bdlru_build_info(void);
 
 /* ---------------------------------------------------------------------------------------------
  * S0 — raw first-order scan on [B, C, T] contiguous fp32, T contiguous.

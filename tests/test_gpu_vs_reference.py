@@ -1,0 +1,123 @@
+"""GPU parity against the REFERENCE'S OWN implementation launched on the B200 (What's missing #3): the
+unmodified `parallel_scan.py` Triton kernels (parallel_scan.py:44-118, JIT-compiled for sm_100a by the image's triton)
+and the unmodified `RecBLR.py` modules on top of them — literal left pad to a power of two, F.conv1d fallback (the
+causal-conv1d wheel is absent), separate gate ops, two transposes, Triton scan.
+
+The sources are not in the repository: `oracle/build_ref.py` packs them from /root/reference into the git-ignored
+`oracle/_ref/reference_py.tar.gz`, which travels to the GPU box; without the blob these tests skip (and say so).
+Tolerances: both sides compute in fp32, so each is also held to the float64 oracle; ours-vs-reference <= 1e-4 max-norm
+(north_star) on outputs and input gradients."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import build_ref
+from tests.util import rel_err
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(not build_ref.available(), reason="oracle/_ref/reference_py.tar.gz not built")]
+TOL = 1e-4
+
+
+@pytest.mark.parametrize("T", [64, 256, 1024, 4096])
+@pytest.mark.parametrize("regime", ["model", "near_one"])
+def test_parallel_scan_matches_reference_triton_kernel(T, regime):
+    """ops.parallel_scan (csrc/scan_bct.cu) vs the reference's Triton `parallel_scan` on the same fp32 [B, C, T] inputs,
+    forward and both gradients; and both against the float64 sequential scan."""
+    from datamining_recblr_b200 import ops
+    from oracle import bdlru_oracle as O
+    _, ps = build_ref.load_gpu_reference()
+    B, C = 6, 32
+    g = torch.Generator(device="cuda").manual_seed(T)
+    lo, hi = {"model": (0.3, 0.999), "near_one": (0.999, 1.0)}[regime]
+    gates = torch.rand(B, C, T, device="cuda", generator=g) * (hi - lo) + lo
+    tokens = torch.randn(B, C, T, device="cuda", generator=g)
+    gy = torch.randn(B, C, T, device="cuda", generator=g)
+    outs = []
+    for fn in (ops.parallel_scan, ps.parallel_scan):
+        a, b = gates.clone().requires_grad_(True), tokens.clone().requires_grad_(True)
+        h = fn(a, b)
+        h.backward(gy)
+        outs.append((h.detach(), a.grad, b.grad))
+    h64 = O.scan_fwd(gates.double().cpu().numpy(), tokens.double().cpu().numpy())
+    da64, db64, _ = O.scan_bwd(gates.double().cpu().numpy(), h64, gy.double().cpu().numpy())
+    for ours, theirs, ref in zip(outs[0], outs[1], (h64, da64, db64)):
+        assert rel_err(ours, theirs.double().cpu().numpy()) <= TOL
+        assert rel_err(ours, ref) <= TOL
+        assert rel_err(theirs, ref) <= TOL       # the reference kernel itself meets the bar it sets
+
+
+def _copy_layer_weights(dst, src):
+    dst.load_state_dict(src.state_dict())
+
+
+@pytest.mark.parametrize("T", [5, 50, 64, 200])
+def test_gated_recurrent_layer_matches_reference_on_gpu(T):
+    """Our GatedRecurrentLayer (h0 instead of the left pad, fused conv / gate+scan / z-gate kernels) vs the reference's
+    (literal pad + Triton scan) with the same weights on the same input: output and every gradient."""
+    from datamining_recblr_b200.recblr import GatedRecurrentLayer
+    mod, _ = build_ref.load_gpu_reference()
+    torch.manual_seed(T)
+    ref = mod.GatedRecurrentLayer(d_model=64, expansion_factor=2, kernel_size=4).cuda()
+    with torch.no_grad():
+        for p in ref.parameters():
+            if p.dim() >= 2:
+                p.mul_(3.0)
+        ref.gates.bias.normal_(std=0.5)
+        ref.conv1d.bias.normal_(std=0.5)
+    ours = GatedRecurrentLayer(d_model=64, expansion_factor=2, kernel_size=4).cuda()
+    _copy_layer_weights(ours, ref)
+    x = torch.randn(7, T, 64, device="cuda")
+    gy = torch.randn(7, T, 64, device="cuda")
+    res = []
+    for m in (ours, ref):
+        xi = x.clone().requires_grad_(True)
+        y = m(xi)
+        y.backward(gy)
+        res.append((y.detach(), xi.grad, {n: p.grad.clone() for n, p in m.named_parameters()}))
+        m.zero_grad()
+    assert rel_err(res[0][0], res[1][0].double().cpu().numpy()) <= TOL
+    assert rel_err(res[0][1], res[1][1].double().cpu().numpy()) <= TOL
+    for n, gr in res[1][2].items():
+        assert rel_err(res[0][2][n], gr.double().cpu().numpy()) <= 5e-4, n   # fp32 reductions over B*T in different orders
+
+
+def test_model_loss_and_scores_match_reference_on_gpu():
+    """Whole model, reference checkpoint loaded unchanged: CE loss (fused tcgen05 CE, bf16 operands: 2e-3; dense fp32:
+    1e-4), seq_output and full_sort_predict scores vs the reference model running its Triton scan on the same GPU."""
+    from datamining_recblr_b200.recblr import RecBLR
+    from oracle import torch_port as TP
+    from oracle.reference_loader import FakeDataset, make_config
+    mod, _ = build_ref.load_gpu_reference()
+    n_items, L, B = 700, 50, 48
+    cfg = make_config(hidden_size=64, num_layers=2, dropout_prob=0.0, max_len=L)
+    cfg["device"] = "cuda"
+    torch.manual_seed(1)
+    ref = mod.RecBLR(cfg, FakeDataset(n_items)).cuda().eval()
+    ours = RecBLR(cfg, FakeDataset(n_items)).cuda().eval()
+    ours.load_state_dict(ref.state_dict())
+    seq, lens, pos = TP.synthetic_batch(B, L, n_items, seed=4)
+    inter = {"item_id_list": seq.cuda(), "item_length": lens.cuda(), "item_id": pos.cuda()}
+    with torch.no_grad():
+        q_ref = ref.forward(inter["item_id_list"], inter["item_length"])
+        q = ours.forward(inter["item_id_list"], inter["item_length"])
+        assert rel_err(q, q_ref.double().cpu().numpy()) <= TOL
+        s_ref, s = ref.full_sort_predict(inter), ours.full_sort_predict(inter)
+        assert rel_err(s, s_ref.double().cpu().numpy()) <= TOL
+        l_ref = float(ref.calculate_loss(inter))
+        ours.ce_impl = "dense"
+        assert abs(float(ours.calculate_loss(inter)) - l_ref) <= TOL * abs(l_ref)
+        ours.ce_impl = "fused"
+        assert abs(float(ours.calculate_loss(inter)) - l_ref) <= 2e-3 * abs(l_ref)
+        # ranking: (a) our fp32 dense scores rank like the reference's (fp32 near-ties aside); (b) the fused scorer fed the
+        # REFERENCE's seq_output returns exactly the ids of RecBole's dense procedure on the same bf16-rounded operands
+        from datamining_recblr_b200 import ops
+        top = lambda m: torch.sort(m, dim=1, descending=True, stable=True).indices[:, :10]
+        sd, so = s_ref.double().clone(), s.double().clone()
+        sd[:, 0] = so[:, 0] = float("-inf")
+        assert float((top(sd) == top(so)).all(1).double().mean()) >= 0.95
+        table = ref.item_embedding.weight.detach()
+        _, ids = ops.fullsort_topk(q_ref, table, 10, mask_id=0)
+        dense = q_ref.bfloat16().double() @ table.bfloat16().double().T
+        dense[:, 0] = float("-inf")
+        assert torch.equal(ids.long(), top(dense))

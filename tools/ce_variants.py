@@ -25,7 +25,7 @@ def build_all():
     for name, (mq, me, mf) in VARIANTS.items():
         objdir = os.path.join(OUT, "obj_" + name)
         os.makedirs(objdir, exist_ok=True)
-        defs = [f"-DBDLRU_CE_DQ_POLY_MASK={mq:#x}u", f"-DBDLRU_CE_DE_POLY_MASK={me:#x}u", f"-DBDLRU_CE_FWD_POLY_MASK={mf:#x}u"]
+        defs = ["-DBDLRU_TUNING", f"-DBDLRU_CE_DQ_POLY_MASK={mq:#x}u", f"-DBDLRU_CE_DE_POLY_MASK={me:#x}u", f"-DBDLRU_CE_FWD_POLY_MASK={mf:#x}u"]
         objs = []
         for src in B._sources():
             obj = os.path.join(objdir, src[:-3] + ".o")
