@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("BDLRU_LIB") or os.path.join(_HERE, "libbdlru.so")
 
 F32, BF16 = 0, 1
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 
 class View(ctypes.Structure):
@@ -46,6 +46,8 @@ SIGNATURES = {
     "bdlru_embed_ln_fwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i, _f, _f, _u64, _p, _i, _i, _p]),
     "bdlru_embed_ln_bwd_workspace_bytes": (_sz, [_i64, _i]),
     "bdlru_embed_ln_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _i64, _i64, _i, _f, _u64, _p, _i64, _i, _i, _p]),
+    "bdlru_embed_ln_bwd_rows": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _i64, _i64, _i, _f, _u64, _p, _i64, _i, _i, _p]),
+    "bdlru_scatter_add_rows": (_i, [_p, _p, _i64, _i, _i, _i64, _i64, _i64, _p, _p]),
     "bdlru_add_ln_fwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _i64, _i, _f, _f, _u64, _p, _i, _p]),
     "bdlru_add_ln_bwd_workspace_bytes": (_sz, [_i64, _i]),
     "bdlru_add_ln_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _i64, _i, _f, _u64, _p, _i, _p]),
@@ -57,9 +59,10 @@ SIGNATURES = {
     "bdlru_fullsort_topk_workspace_bytes": (_sz, [_i64, _i64, _i, _i]),
     "bdlru_fullsort_topk": (_i, [_p, _p, _i64, _i64, _i, _i, _i64, _i64, _p, _p, _p, _sz, _p]),
     "bdlru_topk_merge": (_i, [_p, _p, _i64, _i, _i, _p, _p, _p]),
+    "bdlru_topk_merge_strided": (_i, [_p, _p, _i64, _i, _i, _i64, _i64, _p, _p, _p]),
     "bdlru_fullsort_ce_workspace_bytes": (_sz, [_i64, _i64, _i]),
     "bdlru_fullsort_ce_fwd": (_i, [_p, _p, _p, _i64, _i64, _i, _i64, _p, _p, _p, _p, _sz, _p]),
-    "bdlru_fullsort_ce_bwd": (_i, [_p, _p, _p, _p, _f, _i64, _i64, _i, _i64, _p, _p, _p, _sz, _p]),
+    "bdlru_fullsort_ce_bwd": (_i, [_p, _p, _p, _p, _f, _p, _i64, _i64, _i, _i64, _p, _p, _p, _sz, _p]),
 }
 
 _lib = None

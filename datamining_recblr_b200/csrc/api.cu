@@ -74,7 +74,7 @@ int launch_colsum(const float* part, int n_rows, int row_stride, int n_cols, int
 
 }  // namespace bdlru
 
-extern "C" BDLRU_API int bdlru_version(void) { return 3; }
+extern "C" BDLRU_API int bdlru_version(void) { return 4; }
 extern "C" BDLRU_API const char* bdlru_last_error(void) { return bdlru::g_err; }
 extern "C" BDLRU_API uint64_t bdlru_launch_count(void) { return bdlru::g_launches.load(); }
 

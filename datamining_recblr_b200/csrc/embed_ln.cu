@@ -109,7 +109,8 @@ __global__ void __launch_bounds__(256) embed_ln_bwd_kernel(const int64_t* __rest
                                                            const float* __restrict__ rstd_in, float* __restrict__ dtable,
                                                            float* __restrict__ part /* [grid][2][D] */, long n_tokens,
                                                            long n_items, int D, float p, uint64_t seed,
-                                                           const uint64_t* __restrict__ seed_dev, long padding_idx) {
+                                                           const uint64_t* __restrict__ seed_dev, long padding_idx,
+                                                           TO* __restrict__ drows /* nullable: [n_tokens][D] */) {
   extern __shared__ float red[];  // [warps * RPW][2][D]
   if (seed_dev) seed += *seed_dev;
   constexpr int RPW = 32 / LPR;
@@ -158,7 +159,8 @@ __global__ void __launch_bounds__(256) embed_ln_bwd_kernel(const int64_t* __rest
     }
     s1 = group_sum<LPR>(s1) / (float)D;
     s2 = group_sum<LPR>(s2) / (float)D;
-    if (live && id != padding_idx) {
+    if (live && (drows || id != padding_idx)) {
+      const bool pad = id == padding_idx;   // row-gradient mode keeps the slot (zeros): the exchange is dense per token
 #pragma unroll
       for (int v = 0; v < VPL; ++v) {
         const int vec = sl + LPR * v;
@@ -168,7 +170,12 @@ __global__ void __launch_bounds__(256) embed_ln_bwd_kernel(const int64_t* __rest
           d.y = rstd * (dxh[v][1] - s1 - xh[v][1] * s2) * msk[v][1];
           d.z = rstd * (dxh[v][2] - s1 - xh[v][2] * s2) * msk[v][2];
           d.w = rstd * (dxh[v][3] - s1 - xh[v][3] * s2) * msk[v][3];
-          atomicAdd(reinterpret_cast<float4*>(dtable + id * D + vec * 4), d);
+          if (drows) {
+            const float o[4] = {pad ? 0.f : d.x, pad ? 0.f : d.y, pad ? 0.f : d.z, pad ? 0.f : d.w};
+            IO<TO>::store(drows + n * D + vec * 4, o);
+          } else {
+            atomicAdd(reinterpret_cast<float4*>(dtable + id * D + vec * 4), d);
+          }
         }
       }
     }
@@ -190,6 +197,26 @@ __global__ void __launch_bounds__(256) embed_ln_bwd_kernel(const int64_t* __rest
     float s = 0.f;
     for (int w = 0; w < nwarp * RPW; ++w) s += red[(size_t)w * 2 * D + idx];
     part[(size_t)blockIdx.x * 2 * D + idx] = s;
+  }
+}
+
+// dst[(id - row_lo) * D + :] += rows[n * D + :] for every token n whose id lies in [row_lo, row_hi) and is not
+// padding_idx: the owner-side half of the sharded embedding gradient (the rows arrive by all-gather from every rank;
+// a rank adds only what it owns).  One lane per 4-channel vector, vector red.global.add.
+template <typename TO>
+__global__ void __launch_bounds__(256) scatter_rows_kernel(const int64_t* __restrict__ ids, const TO* __restrict__ rows,
+                                                           long n_tokens, int D, long row_lo, long row_hi,
+                                                           long padding_idx, float* __restrict__ dst) {
+  const int nvec = D / 4;
+  const long total = n_tokens * nvec;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long n = i / nvec;
+    const int vec = (int)(i - n * nvec);
+    const long id = ids[n];
+    if (id < row_lo || id >= row_hi || id == padding_idx) continue;
+    float v[4];
+    IO<TO>::load(rows + n * D + vec * 4, v);
+    atomicAdd(reinterpret_cast<float4*>(dst + (id - row_lo) * D + vec * 4), make_float4(v[0], v[1], v[2], v[3]));
   }
 }
 
@@ -266,19 +293,19 @@ extern "C" BDLRU_API size_t bdlru_embed_ln_bwd_workspace_bytes(int64_t n_tokens,
   return (size_t)sm_count() * 8 * 2 * (size_t)D * sizeof(float);
 }
 
-extern "C" BDLRU_API int bdlru_embed_ln_bwd(const int64_t* ids, const void* table, const float* gamma,
-                                            const void* grad_out, const float* mean, const float* rstd, float* dtable,
-                                            float* dgamma, float* dbeta, void* workspace, size_t workspace_bytes,
-                                            int64_t n_tokens, int64_t n_items, int D, float dropout_p, uint64_t seed,
-                                            const uint64_t* seed_device, int64_t padding_idx, int dtype, int out_dtype,
-                                            void* stream) {
+static int embed_bwd_impl(const int64_t* ids, const void* table, const float* gamma, const void* grad_out,
+                          const float* mean, const float* rstd, float* dtable, void* drows, float* dgamma, float* dbeta,
+                          void* workspace, size_t workspace_bytes, int64_t n_tokens, int64_t n_items, int D,
+                          float dropout_p, uint64_t seed, const uint64_t* seed_device, int64_t padding_idx, int dtype,
+                          int out_dtype, void* stream) {
   int rc = embed_check(n_tokens, n_items, D, dtype, dropout_p);
   if (rc) return rc;
   BDLRU_REQUIRE(out_dtype == dtype || (dtype == BDLRU_F32 && out_dtype == BDLRU_BF16),
                 "embed_ln_bwd: out_dtype must equal the table dtype, or be bf16 for an fp32 table");
-  BDLRU_REQUIRE(ids && table && gamma && grad_out && mean && rstd && dtable && dgamma && dbeta,
+  BDLRU_REQUIRE(ids && table && gamma && grad_out && mean && rstd && (dtable || drows) && dgamma && dbeta,
                 "embed_ln_bwd: null pointer");
-  BDLRU_REQUIRE(aligned(table, 16) && aligned(grad_out, 16) && aligned(dtable, 16) && aligned(gamma, 16),
+  BDLRU_REQUIRE(aligned(table, 16) && aligned(grad_out, 16) && aligned(dtable, 16) && aligned(gamma, 16) &&
+                    aligned(drows, 16),
                 "embed_ln_bwd: pointers must be 16-byte aligned");
   const int grid = embed_grid(n_tokens, D);
   const size_t need = (size_t)grid * 2 * D * sizeof(float);
@@ -290,7 +317,7 @@ extern "C" BDLRU_API int bdlru_embed_ln_bwd(const int64_t* ids, const void* tabl
 #define EBWD(TT, TTO, LPR, VPL)                                                                                       \
   embed_ln_bwd_kernel<TT, TTO, LPR, VPL><<<grid, 256, smem, st>>>(ids, (const TT*)table, gamma, (const TTO*)grad_out, mean, \
                                                                   rstd, dtable, part, n_tokens, n_items, D, dropout_p,      \
-                                                                  seed, seed_device, padding_idx)
+                                                                  seed, seed_device, padding_idx, (TTO*)drows)
 #define EBWD_FF(LPR, VPL) EBWD(float, float, LPR, VPL)
 #define EBWD_BB(LPR, VPL) EBWD(__nv_bfloat16, __nv_bfloat16, LPR, VPL)
 #define EBWD_FB(LPR, VPL) EBWD(float, __nv_bfloat16, LPR, VPL)
@@ -307,4 +334,51 @@ extern "C" BDLRU_API int bdlru_embed_ln_bwd(const int64_t* ids, const void* tabl
 #undef EBWD
   BDLRU_LAUNCHED();
   return launch_colsum(part, grid, 2 * D, 2 * D, COLSUM_SPLIT, dgamma, dbeta, D, nullptr, st);
+}
+
+extern "C" BDLRU_API int bdlru_embed_ln_bwd(const int64_t* ids, const void* table, const float* gamma,
+                                            const void* grad_out, const float* mean, const float* rstd, float* dtable,
+                                            float* dgamma, float* dbeta, void* workspace, size_t workspace_bytes,
+                                            int64_t n_tokens, int64_t n_items, int D, float dropout_p, uint64_t seed,
+                                            const uint64_t* seed_device, int64_t padding_idx, int dtype, int out_dtype,
+                                            void* stream) {
+  BDLRU_REQUIRE(dtable, "embed_ln_bwd: null dtable");
+  return embed_bwd_impl(ids, table, gamma, grad_out, mean, rstd, dtable, nullptr, dgamma, dbeta, workspace,
+                        workspace_bytes, n_tokens, n_items, D, dropout_p, seed, seed_device, padding_idx, dtype, out_dtype,
+                        stream);
+}
+
+extern "C" BDLRU_API int bdlru_embed_ln_bwd_rows(const int64_t* ids, const void* table, const float* gamma,
+                                                 const void* grad_out, const float* mean, const float* rstd,
+                                                 void* drows, float* dgamma, float* dbeta, void* workspace,
+                                                 size_t workspace_bytes, int64_t n_tokens, int64_t n_items, int D,
+                                                 float dropout_p, uint64_t seed, const uint64_t* seed_device,
+                                                 int64_t padding_idx, int dtype, int out_dtype, void* stream) {
+  BDLRU_REQUIRE(drows, "embed_ln_bwd_rows: null drows");
+  return embed_bwd_impl(ids, table, gamma, grad_out, mean, rstd, nullptr, drows, dgamma, dbeta, workspace,
+                        workspace_bytes, n_tokens, n_items, D, dropout_p, seed, seed_device, padding_idx, dtype, out_dtype,
+                        stream);
+}
+
+extern "C" BDLRU_API int bdlru_scatter_add_rows(const int64_t* ids, const void* rows, int64_t n_tokens, int D,
+                                                int rows_dtype, int64_t row_lo, int64_t row_hi, int64_t padding_idx,
+                                                float* dst, void* stream) {
+  BDLRU_REQUIRE(ids && rows && dst, "scatter_add_rows: null pointer");
+  BDLRU_REQUIRE(n_tokens >= 1 && D >= 4 && D % 4 == 0, "scatter_add_rows: bad sizes n_tokens=%ld D=%d", (long)n_tokens, D);
+  BDLRU_REQUIRE(rows_dtype == BDLRU_F32 || rows_dtype == BDLRU_BF16, "scatter_add_rows: bad dtype %d", rows_dtype);
+  BDLRU_REQUIRE(row_lo >= 0 && row_hi >= row_lo, "scatter_add_rows: bad row range");
+  BDLRU_REQUIRE(aligned(rows, 16) && aligned(dst, 16), "scatter_add_rows: pointers must be 16-byte aligned");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const long total = n_tokens * (D / 4);
+  long blocks = (total + 255) / 256;
+  const long cap = (long)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  if (rows_dtype == BDLRU_F32)
+    scatter_rows_kernel<float><<<(unsigned)blocks, 256, 0, st>>>(ids, (const float*)rows, n_tokens, D, row_lo, row_hi,
+                                                                 padding_idx, dst);
+  else
+    scatter_rows_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>(ids, (const __nv_bfloat16*)rows, n_tokens, D,
+                                                                         row_lo, row_hi, padding_idx, dst);
+  BDLRU_LAUNCHED();
+  return BDLRU_OK;
 }

@@ -498,8 +498,12 @@ fullsort_kernel(const __grid_constant__ CUtensorMap tmE, const FsParams p) {
 // ----------------------------------------------------------------------------- merges
 // One warp per user: k rounds of "best remaining candidate" by (score desc, id asc) over n_cand candidates staged in
 // shared memory.  Used for the S per-CTA lists of one GPU and for the G per-shard lists of the NCCL merge.
+// Candidate (list l, user u, slot j) lives at l * list_stride + u * user_stride + j (elements): user-major lists
+// ([n_users][n_lists][k]: list_stride = k, user_stride = n_lists * k) and the rank-major layout an NCCL all-gather
+// leaves behind ([n_lists][...][n_users][k]) are both read in place, no permute copy.
 __global__ void __launch_bounds__(128) topk_merge_kernel(const float* __restrict__ cs, const int* __restrict__ ci,
-                                                         long n_users, int n_cand, int k, float* __restrict__ os,
+                                                         long n_users, int n_cand, int k, long list_stride,
+                                                         long user_stride, float* __restrict__ os,
                                                          int* __restrict__ oi) {
   extern __shared__ uint8_t msm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -508,8 +512,9 @@ __global__ void __launch_bounds__(128) topk_merge_kernel(const float* __restrict
   float* s = reinterpret_cast<float*>(msm) + (size_t)warp * n_cand;
   int* id = reinterpret_cast<int*>(msm + (size_t)4 * n_cand * sizeof(float)) + (size_t)warp * n_cand;
   for (int j = lane; j < n_cand; j += 32) {
-    s[j] = cs[user * n_cand + j];
-    id[j] = ci[user * n_cand + j];
+    const long src = (long)(j / k) * list_stride + user * user_stride + (j % k);
+    s[j] = cs[src];
+    id[j] = ci[src];
   }
   __syncwarp();
   for (int r = 0; r < k; ++r) {
@@ -651,24 +656,36 @@ extern "C" BDLRU_API int bdlru_fullsort_topk(const void* Q, const void* E, int64
   const size_t msmem = (size_t)4 * n_cand * 8;
   BDLRU_REQUIRE(msmem <= 200 * 1024, "fullsort_topk: merge of %d candidates per user does not fit", n_cand);
   BDLRU_CUDA(cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
-  topk_merge_kernel<<<(unsigned)((n_users + 3) / 4), 128, msmem, st>>>(p.part_scores, p.part_ids, n_users, n_cand, k,
-                                                                      out_scores, out_ids);
+  topk_merge_kernel<<<(unsigned)((n_users + 3) / 4), 128, msmem, st>>>(p.part_scores, p.part_ids, n_users, n_cand, k, k,
+                                                                      (long)n_cand, out_scores, out_ids);
+  BDLRU_LAUNCHED();
+  return BDLRU_OK;
+}
+
+static int merge_impl(const float* cand_scores, const int32_t* cand_ids, int64_t n_users, int n_lists, int k,
+                      int64_t list_stride, int64_t user_stride, float* out_scores, int32_t* out_ids, void* stream) {
+  BDLRU_REQUIRE(cand_scores && cand_ids && out_scores && out_ids, "topk_merge: null pointer");
+  BDLRU_REQUIRE(n_users >= 1 && n_lists >= 1 && k >= 1 && k <= 32, "topk_merge: bad sizes");
+  BDLRU_REQUIRE(list_stride >= 1 && user_stride >= k, "topk_merge: bad strides");
+  const int n_cand = n_lists * k;
+  const size_t msmem = (size_t)4 * n_cand * 8;
+  BDLRU_REQUIRE(msmem <= 200 * 1024, "topk_merge: %d candidates per user do not fit", n_cand);
+  BDLRU_CUDA(cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
+  topk_merge_kernel<<<(unsigned)((n_users + 3) / 4), 128, msmem, reinterpret_cast<cudaStream_t>(stream)>>>(
+      cand_scores, cand_ids, n_users, n_cand, k, list_stride, user_stride, out_scores, out_ids);
   BDLRU_LAUNCHED();
   return BDLRU_OK;
 }
 
 extern "C" BDLRU_API int bdlru_topk_merge(const float* cand_scores, const int32_t* cand_ids, int64_t n_users,
                                           int n_lists, int k, float* out_scores, int32_t* out_ids, void* stream) {
-  BDLRU_REQUIRE(cand_scores && cand_ids && out_scores && out_ids, "topk_merge: null pointer");
-  BDLRU_REQUIRE(n_users >= 1 && n_lists >= 1 && k >= 1 && k <= 32, "topk_merge: bad sizes");
-  const int n_cand = n_lists * k;
-  const size_t msmem = (size_t)4 * n_cand * 8;
-  BDLRU_REQUIRE(msmem <= 200 * 1024, "topk_merge: %d candidates per user do not fit", n_cand);
-  BDLRU_CUDA(cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
-  topk_merge_kernel<<<(unsigned)((n_users + 3) / 4), 128, msmem, reinterpret_cast<cudaStream_t>(stream)>>>(
-      cand_scores, cand_ids, n_users, n_cand, k, out_scores, out_ids);
-  BDLRU_LAUNCHED();
-  return BDLRU_OK;
+  return merge_impl(cand_scores, cand_ids, n_users, n_lists, k, k, (int64_t)n_lists * k, out_scores, out_ids, stream);
+}
+
+extern "C" BDLRU_API int bdlru_topk_merge_strided(const float* cand_scores, const int32_t* cand_ids, int64_t n_users,
+                                                  int n_lists, int k, int64_t list_stride, int64_t user_stride,
+                                                  float* out_scores, int32_t* out_ids, void* stream) {
+  return merge_impl(cand_scores, cand_ids, n_users, n_lists, k, list_stride, user_stride, out_scores, out_ids, stream);
 }
 
 namespace bdlru { size_t ce_bwd_workspace_bytes(long n_users, long n_rows, int D); }

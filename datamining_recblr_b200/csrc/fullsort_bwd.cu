@@ -57,6 +57,7 @@ struct BwdParams {
   long n_users;
   long id_offset;       // global id of item row 0 of this shard
   float scale;
+  const float* scale_dev;  // optional device scalar multiplied into `scale` (the upstream dL/dloss: no host sync, no extra pass)
   int dbg;              // BDLRU_FS_DEBUG & 8: print per-tile phase timings of one softmax warp
   float* out;           // [splits][n_x][D] fp32 (splits == 1: the final gradient)
 };
@@ -358,6 +359,7 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const BwdParams p) {
       tc::mbar_wait(dx_full, wi & 1u);
       tc::fence_after_sync();
       float* orow = p.out + ((size_t)split * p.n_x + xrow) * p.D;
+      const float out_scale = p.scale * (p.scale_dev ? __ldg(p.scale_dev) : 1.f);
       // dQ pass: "- onehot" = minus the positive item's row of Y, applied once, by the split that owns that column
       const bool sub_pos = !TRANSPOSED && xrow < p.n_x && row_pos >= t0 * NT && row_pos < t1 * NT && row_pos < p.n_y;
       const __nv_bfloat16* yrow = reinterpret_cast<const __nv_bfloat16*>(p.Y) + (sub_pos ? row_pos : 0) * p.D;
@@ -373,7 +375,7 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const BwdParams p) {
             for (int e = 0; e < 4; ++e) {
               o[e] = __uint_as_float(acc[i + e]);
               if (sub_pos) o[e] -= __bfloat162float(yrow[c * 32 + i + e]);
-              o[e] *= p.scale;
+              o[e] *= out_scale;
             }
             *reinterpret_cast<float4*>(orow + c * 32 + i) = make_float4(o[0], o[1], o[2], o[3]);
           }
@@ -458,7 +460,8 @@ static int bwd_launch(const BwdPlan& pl, const CUtensorMap& my, const BwdParams&
 // one gradient: X rows against Y columns; result (scaled) in `grad` [n_x, D]
 template <bool TR>
 static int bwd_one(const void* X, long n_x, const void* Y, long n_y, int D, const float* lse, const int64_t* pos,
-                   long n_users, long id_offset, float scale, float* grad, float* scratch, cudaStream_t st) {
+                   long n_users, long id_offset, float scale, const float* scale_dev, float* grad, float* scratch,
+                   cudaStream_t st) {
   BwdPlan pl;
   bwd_plan(n_x, n_y, D, &pl);
   CUtensorMap my;
@@ -467,7 +470,7 @@ static int bwd_one(const void* X, long n_x, const void* Y, long n_y, int D, cons
   BwdParams p = {};
   p.X = X; p.Y = Y; p.n_x = n_x; p.n_y = n_y; p.D = D; p.stages = pl.stages; p.splits = pl.splits;
   p.row_blocks = pl.row_blocks; p.tiles_total = pl.tiles;
-  p.lse = lse; p.pos = pos; p.n_users = n_users; p.id_offset = id_offset; p.scale = scale;
+  p.lse = lse; p.pos = pos; p.n_users = n_users; p.id_offset = id_offset; p.scale = scale; p.scale_dev = scale_dev;
   p.dbg = tuning_env("BDLRU_FS_DEBUG");
   p.out = pl.splits > 1 ? scratch : grad;
   if ((rc = bwd_launch<TR>(pl, my, p, st))) return rc;
@@ -494,7 +497,8 @@ size_t ce_bwd_workspace_bytes(long n_users, long n_rows, int D) {
 using namespace bdlru;
 
 extern "C" BDLRU_API int bdlru_fullsort_ce_bwd(const void* Q, const void* E, const int64_t* pos, const float* lse,
-                                               float scale, int64_t n_users, int64_t n_rows, int D, int64_t id_offset,
+                                               float scale, const float* scale_dev, int64_t n_users, int64_t n_rows, int D,
+                                               int64_t id_offset,
                                                float* dQ, float* dE, void* workspace, size_t workspace_bytes,
                                                void* stream) {
   BDLRU_REQUIRE(Q && E && pos && lse, "fullsort_ce_bwd: null input");
@@ -508,10 +512,10 @@ extern "C" BDLRU_API int bdlru_fullsort_ce_bwd(const void* Q, const void* E, con
                 workspace_bytes, need);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   int rc;
-  if (dQ && (rc = bwd_one<false>(Q, n_users, E, n_rows, D, lse, pos, n_users, id_offset, scale, dQ,
+  if (dQ && (rc = bwd_one<false>(Q, n_users, E, n_rows, D, lse, pos, n_users, id_offset, scale, scale_dev, dQ,
                                  reinterpret_cast<float*>(workspace), st)))
     return rc;
-  if (dE && (rc = bwd_one<true>(E, n_rows, Q, n_users, D, lse, pos, n_users, id_offset, scale, dE,
+  if (dE && (rc = bwd_one<true>(E, n_rows, Q, n_users, D, lse, pos, n_users, id_offset, scale, scale_dev, dE,
                                 reinterpret_cast<float*>(workspace), st)))
     return rc;
   return BDLRU_OK;

@@ -5,6 +5,8 @@
     scan_channel_last(a, b, h0=None)                   raw scan, [B, T, C]
     causal_conv1d_channel_last(x, weight, bias, silu)  [B, T, C]          RecBLR.py:185 / 188-193
 """
+import ctypes
+
 import torch
 
 from . import _lib as L
@@ -439,6 +441,21 @@ def embed_layernorm(ids, table, gamma, beta, eps=1e-12, dropout_p=0.0, seed=0, p
     return _EmbedLN.apply(ids, table, gamma, beta, eps, dropout_p, seed, padding_idx, seed_dev, out_dtype)
 
 
+def scatter_add_rows(ids, rows, dst, row_lo, row_hi, padding_idx=-1):
+    """dst[(id - row_lo)] += rows[n] for every token n with row_lo <= ids[n] < row_hi and ids[n] != padding_idx
+    (dst fp32 [row_hi - row_lo or more, D]; rows fp32/bf16 [n, D]) — the owner-side half of the sharded embedding
+    gradient."""
+    L.require_cuda(ids, rows, dst)
+    assert ids.dtype == torch.int64 and rows.dim() == 2 and dst.dtype == torch.float32
+    ids_c, rows_c = ids.reshape(-1).contiguous(), rows.contiguous()
+    assert rows_c.shape[0] == ids_c.numel() and dst.is_contiguous() and dst.shape[1] == rows_c.shape[1]
+    assert dst.shape[0] >= row_hi - row_lo
+    L.check(L.load().bdlru_scatter_add_rows(L.ptr(ids_c), L.ptr(rows_c), ids_c.numel(), rows_c.shape[1],
+                                            L.dtype_tag(rows_c), int(row_lo), int(row_hi), int(padding_idx), L.ptr(dst),
+                                            L.stream_ptr(dst)))
+    return dst
+
+
 def colsum(x2d):
     """fp32 column sums of a row-major [rows, cols] fp32/bf16 matrix (one streaming pass + deterministic reduce)."""
     L.require_cuda(x2d)
@@ -671,7 +688,7 @@ def _augment_with_bias(qb, eb, item_bias):
     return qa, ea
 
 
-def fullsort_topk(q, table, k, mask_id=0, id_offset=0, item_bias=None):
+def fullsort_topk(q, table, k, mask_id=0, id_offset=0, item_bias=None, out=None):
     """Fused full-sort scoring + top-k (RecBLR.py:114-122 + RecBole's `scores[:, 0] = -inf; torch.topk`): returns
     (scores fp32 [B, k], ids int32 [B, k]) of q @ table^T (+ item_bias [n_rows], bert4rec.py:230-242) without forming
     [B, n_rows].  Operands are rounded to bf16, accumulated in fp32 on the tcgen05 tensor cores; ordering is score
@@ -685,8 +702,13 @@ def fullsort_topk(q, table, k, mask_id=0, id_offset=0, item_bias=None):
     B, D = qb.shape
     N = table.shape[0]
     lib = L.load()
-    out_s = torch.empty((B, k), dtype=torch.float32, device=q.device)
-    out_i = torch.empty((B, k), dtype=torch.int32, device=q.device)
+    if out is not None:   # caller-owned contiguous [B, k] fp32 / int32 buffers (e.g. halves of one exchange buffer)
+        out_s, out_i = out
+        assert out_s.shape == (B, k) and out_s.dtype == torch.float32 and out_s.is_contiguous()
+        assert out_i.shape == (B, k) and out_i.dtype == torch.int32 and out_i.is_contiguous()
+    else:
+        out_s = torch.empty((B, k), dtype=torch.float32, device=q.device)
+        out_i = torch.empty((B, k), dtype=torch.int32, device=q.device)
     nws = lib.bdlru_fullsort_topk_workspace_bytes(B, N, D, k)
     ws = _workspace(q.device, nws)
     L.check(lib.bdlru_fullsort_topk(L.ptr(qb), L.ptr(eb), B, N, D, k, id_offset, mask_id, L.ptr(out_s), L.ptr(out_i),
@@ -715,6 +737,20 @@ def _check_pos(pos, n_users):
     return pos.contiguous()
 
 
+def topk_merge_gathered(packed, k):
+    """Merge of the buffer `all_gather_into_tensor` leaves behind when every rank contributes one packed
+    [2, B, k] tensor (row 0: fp32 scores, row 1: the int32 ids' bits): packed fp32 [world, 2, B, k], read in place."""
+    L.require_cuda(packed)
+    world, two, B, kk = packed.shape
+    assert two == 2 and kk == k and packed.dtype == torch.float32 and packed.is_contiguous()
+    out_s = torch.empty((B, k), dtype=torch.float32, device=packed.device)
+    out_i = torch.empty((B, k), dtype=torch.int32, device=packed.device)
+    ids_ptr = ctypes.c_void_p(packed.data_ptr() + B * k * 4)
+    L.check(L.load().bdlru_topk_merge_strided(L.ptr(packed), ids_ptr, B, world, k, 2 * B * k, k, L.ptr(out_s), L.ptr(out_i),
+                                              L.stream_ptr(packed)))
+    return out_s, out_i
+
+
 def fullsort_ce_stats(q, table, pos, id_offset=0, item_bias=None):
     """Per-user (row_max, row_sumexp, pos_logit) of the logits q @ table^T (+ item_bias) over this table (shard), never
     materialised.  pos_logit is written only for users whose positive row lives in this shard (others keep 0)."""
@@ -736,20 +772,31 @@ def fullsort_ce_stats(q, table, pos, id_offset=0, item_bias=None):
     return row_max, row_sum, pos_logit
 
 
-def fullsort_ce_grads(qb, eb, pos, lse, scale, id_offset=0):
+def fullsort_ce_grads(qb, eb, pos, lse, scale, id_offset=0, scale_dev=None, out_dq=None, out_de=None, want_dq=True,
+                      want_de=True):
     """(dQ [B, D], dE [rows, D]) fp32 of scale * sum_b(lse_b - logit_{b,pos_b}) for bf16 qb, eb and the GLOBAL lse;
-    the logits are recomputed tile by tile on the tensor cores and never stored."""
+    the logits are recomputed tile by tile on the tensor cores and never stored.  `scale_dev` (fp32 CUDA scalar) is
+    multiplied in on the device (the upstream gradient of the loss: no sync, no extra pass over dE); `out_dq` / `out_de`
+    let the caller have the kernel write straight into its own fp32 buffers (e.g. the optimizer's gradient of the table)."""
     L.require_cuda(qb, eb, pos, lse)
     pos = _check_pos(pos, qb.shape[0])
     B, D = qb.shape
     N = eb.shape[0]
     lib = L.load()
-    dQ = torch.empty((B, D), dtype=torch.float32, device=qb.device)
-    dE = torch.empty((N, D), dtype=torch.float32, device=qb.device)
+    dQ = dE = None
+    if want_dq:
+        dQ = out_dq if out_dq is not None else torch.empty((B, D), dtype=torch.float32, device=qb.device)
+        assert dQ.shape == (B, D) and dQ.dtype == torch.float32 and dQ.is_contiguous()
+    if want_de:
+        dE = out_de if out_de is not None else torch.empty((N, D), dtype=torch.float32, device=qb.device)
+        assert dE.shape == (N, D) and dE.dtype == torch.float32 and dE.is_contiguous()
+    if scale_dev is not None:
+        scale_dev = scale_dev.detach().reshape(()).float().contiguous()
     nws = lib.bdlru_fullsort_ce_workspace_bytes(B, N, D)
     ws = _workspace(qb.device, nws)
-    L.check(lib.bdlru_fullsort_ce_bwd(L.ptr(qb), L.ptr(eb), L.ptr(pos), L.ptr(lse.float().contiguous()), float(scale), B,
-                                      N, D, id_offset, L.ptr(dQ), L.ptr(dE), L.ptr(ws), nws, L.stream_ptr(qb)))
+    L.check(lib.bdlru_fullsort_ce_bwd(L.ptr(qb), L.ptr(eb), L.ptr(pos), L.ptr(lse.float().contiguous()), float(scale),
+                                      L.ptr(scale_dev), B, N, D, id_offset, L.ptr(dQ), L.ptr(dE), L.ptr(ws), nws,
+                                      L.stream_ptr(qb)))
     return dQ, dE
 
 
@@ -771,13 +818,13 @@ class _FullsortCE(torch.autograd.Function):
     def backward(ctx, grad_loss):
         qb, eb, pos, lse = ctx.saved_tensors
         qd, ed, D, bd = ctx.meta
-        # dloss/dlogit = (softmax - onehot) / B, times the upstream scalar (kept on the device: no sync)
-        dQ, dE = fullsort_ce_grads(qb, eb, pos, lse, 1.0 / qb.shape[0])
-        g = grad_loss.float()
+        # dloss/dlogit = (softmax - onehot) / B, times the upstream scalar (read by the kernel on the device: no sync and
+        # no extra pass over the [n_items, D] gradient)
+        dQ, dE = fullsort_ce_grads(qb, eb, pos, lse, 1.0 / qb.shape[0], scale_dev=grad_loss)
         if bd is None:
-            return (dQ * g).to(qd), (dE * g).to(ed), None, None
+            return dQ.to(qd), dE.to(ed), None, None
         # augmented operands: the bias gradient is the column of d(table') that multiplies q' = 1
-        return (dQ[:, :D] * g).to(qd), (dE[:, :D] * g).to(ed), None, (dE[:, D] * g).to(bd)
+        return dQ[:, :D].to(qd), dE[:, :D].to(ed), None, dE[:, D].to(bd)
 
 
 def fullsort_cross_entropy(q, table, pos, item_bias=None):

@@ -118,6 +118,8 @@ class RecBLR(SequentialRecommender):
         # step counter of the fused front end's dropout stream, ON THE DEVICE so that a training step captured in a
         # CUDA graph draws a new mask at every replay (not a parameter, not saved in checkpoints)
         self.register_buffer("_dropout_step", torch.zeros(1, dtype=torch.int64), persistent=False)
+        # set by sharded.shard_item_table(model): the tied table row-sharded over a process group
+        self.table_shard = None
 
     def _init_weights(self, module):  # RecBLR.py:66-73 (the pad row 0 is re-randomised too: SURVEY quirk 2)
         if isinstance(module, (nn.Linear, nn.Embedding)):
@@ -132,6 +134,11 @@ class RecBLR(SequentialRecommender):
     def _front(self, item_seq):
         p = self.dropout_prob if self.training else 0.0
         D = self.hidden_size
+        if self.table_shard is not None:   # gather from the replicated bf16 copy; row gradients go to the row owners
+            out = self.table_shard.embed_layernorm(item_seq, self.layer_norm.weight, self.layer_norm.bias,
+                                                   self.layer_norm.eps, p, self._seed_base(),
+                                                   self._dropout_step if p > 0.0 else None)
+            return out if _autocast_bf16() is not None else out.float()
         if self.fused_front and D % 4 == 0 and D <= 512:
             seed_dev = self._dropout_step if p > 0.0 else None   # advanced once per training forward (RecBLR.forward)
             seed = self._seed_base()
@@ -168,6 +175,10 @@ class RecBLR(SequentialRecommender):
         item_seq_len = interaction[self.ITEM_SEQ_LEN]
         seq_output = self.forward(item_seq, item_seq_len)
         pos_items = interaction[self.POS_ITEM_ID]
+        if self.table_shard is not None:
+            if self.loss_type != "CE":
+                raise NotImplementedError("the row-sharded item table supports loss_type 'CE' only")
+            return self.table_shard.cross_entropy(seq_output, pos_items)   # GLOBAL-mean loss: sum dense grads over ranks
         if self.loss_type == "BPR":
             neg_items = interaction[self.NEG_ITEM_ID]
             pos_score = torch.sum(seq_output * self.item_embedding(pos_items), dim=-1)
@@ -184,11 +195,15 @@ class RecBLR(SequentialRecommender):
 
     # ------------------------------------------------------------------ RecBLR.py:105-122
     def predict(self, interaction):
+        if self.table_shard is not None:
+            raise NotImplementedError("predict() needs the whole table: use full_sort_topk with the sharded table")
         seq_output = self.forward(interaction[self.ITEM_SEQ], interaction[self.ITEM_SEQ_LEN])
         test_item_emb = self.item_embedding(interaction[self.ITEM_ID])
         return torch.mul(seq_output, test_item_emb).sum(dim=1)
 
     def full_sort_predict(self, interaction):
+        if self.table_shard is not None:
+            raise NotImplementedError("the dense [B, n_items] scores do not exist with a sharded table: use full_sort_topk")
         seq_output = self.forward(interaction[self.ITEM_SEQ], interaction[self.ITEM_SEQ_LEN])
         return torch.matmul(seq_output, self.item_embedding.weight.transpose(0, 1))
 
@@ -198,6 +213,9 @@ class RecBLR(SequentialRecommender):
         (SURVEY §3.5): returns (scores [B, k] fp32, ids [B, k] int64) ordered by score descending with the
         LOWEST item id first among ties, without materialising [B, n_items]."""
         seq_output = self.forward(interaction[self.ITEM_SEQ], interaction[self.ITEM_SEQ_LEN])
+        if self.table_shard is not None:
+            scores, ids = self.table_shard.full_sort_topk(seq_output, k, mask_id=0 if mask_padding_item else -1)
+            return scores, ids.long()
         scores, ids = ops.fullsort_topk(seq_output, self.item_embedding.weight, k,
                                         mask_id=0 if mask_padding_item else -1)
         return scores, ids.long()

@@ -24,24 +24,38 @@ def _world(group):
     return dist.get_world_size(group) if dist.is_initialized() else 1
 
 
-def sharded_topk(q, table_shard, k, id_offset, mask_id=0, group=None, local_topk=None, local_merge=None, item_bias=None):
+def sharded_topk(q, table_shard, k, id_offset, mask_id=0, group=None, local_topk=None, local_merge=None, item_bias=None,
+                 gathered_merge=None):
     """Top-k of q @ table^T (+ item_bias) over the whole (sharded) table.  q [B, D] must be identical on every rank;
     `item_bias` is this rank's slice [rows of table_shard] of the bias vector (bert4rec.py:230-242).
-    Returns (scores [B, k] fp32, ids [B, k] int32), identical on every rank and to the single-table result."""
+    Returns (scores [B, k] fp32, ids [B, k] int32), identical on every rank and to the single-table result.
+
+    Exchange: the local kernel writes its (scores | ids) lists into the two halves of ONE packed [2, B, k] buffer, a
+    single all-gather moves them, and the merge kernel reads the rank-major result in place (no second collective, no
+    permute / contiguous copies); every call in the sequence is capturable in a CUDA graph."""
     local_topk = local_topk or ops.fullsort_topk
-    local_merge = local_merge or ops.topk_merge
     kw = {} if item_bias is None else {"item_bias": item_bias}
-    s, i = local_topk(q, table_shard, k, mask_id=mask_id, id_offset=id_offset, **kw)
     world = _world(group)
     if world == 1:
-        return s, i
+        return local_topk(q, table_shard, k, mask_id=mask_id, id_offset=id_offset, **kw)
     B = q.shape[0]
-    cs = torch.empty((world * B, k), dtype=torch.float32, device=s.device)   # rank-major concatenation
-    ci = torch.empty((world * B, k), dtype=torch.int32, device=s.device)
-    dist.all_gather_into_tensor(cs, s.contiguous(), group=group)
-    dist.all_gather_into_tensor(ci, i.contiguous(), group=group)
-    cs = cs.view(world, B, k).permute(1, 0, 2).reshape(B, world * k).contiguous()
-    ci = ci.view(world, B, k).permute(1, 0, 2).reshape(B, world * k).contiguous()
+    packed = torch.empty((2, B, k), dtype=torch.float32, device=q.device)
+    out = (packed[0], packed[1].view(torch.int32))
+    if local_topk is ops.fullsort_topk:
+        local_topk(q, table_shard, k, mask_id=mask_id, id_offset=id_offset, out=out, **kw)
+    else:   # test stand-ins return fresh tensors
+        s, i = local_topk(q, table_shard, k, mask_id=mask_id, id_offset=id_offset, **kw)
+        out[0].copy_(s)
+        out[1].copy_(i)
+    gathered = torch.empty((world * 2, B, k), dtype=torch.float32, device=q.device)   # concatenation along dim 0
+    dist.all_gather_into_tensor(gathered, packed, group=group)
+    gathered = gathered.view(world, 2, B, k)
+    if local_merge is None and gathered_merge is None:
+        return ops.topk_merge_gathered(gathered, k)
+    if gathered_merge is not None:
+        return gathered_merge(gathered, k)
+    cs = gathered[:, 0].permute(1, 0, 2).reshape(B, world * k).contiguous()           # CPU test path
+    ci = gathered[:, 1].view(torch.int32).permute(1, 0, 2).reshape(B, world * k).contiguous()
     return local_merge(cs, ci, k)
 
 
@@ -75,13 +89,12 @@ class _ShardedCE(torch.autograd.Function):
     def backward(ctx, grad_loss):
         qb, eb, pos, lse = ctx.saved_tensors
         id_offset, group, qd, ed, reduce_dq, D, bd = ctx.meta
-        dQ, dE = ops.fullsort_ce_grads(qb, eb, pos, lse, 1.0 / qb.shape[0], id_offset=id_offset)
+        dQ, dE = ops.fullsort_ce_grads(qb, eb, pos, lse, 1.0 / qb.shape[0], id_offset=id_offset, scale_dev=grad_loss)
         dQ = dQ[:, :D].contiguous()          # no-op without a bias; drops the gradient of the constant 1-columns
         if reduce_dq and _world(group) > 1:  # every shard contributes P_shard E_shard to dQ; dE is shard-local
             dist.all_reduce(dQ, op=dist.ReduceOp.SUM, group=group)
-        g = grad_loss.float()
-        dbias = None if bd is None else (dE[:, D] * g).to(bd)
-        return (dQ * g).to(qd), (dE[:, :D] * g).to(ed), None, None, None, None, dbias
+        dbias = None if bd is None else dE[:, D].to(bd)
+        return dQ.to(qd), dE[:, :D].to(ed), None, None, None, None, dbias
 
 
 def sharded_cross_entropy(q, table_shard, pos, id_offset, group=None, reduce_dq=True, item_bias=None):
@@ -131,3 +144,264 @@ def allreduce_gradients(params, group=None, average=True):
     for p in ps:  # the reduced gradients are handed back as VIEWS of the flat buffer: no copy-back kernels
         p.grad = flat[off:off + p.numel()].view_as(p)
         off += p.numel()
+
+
+# ----------------------------------------------------------------------------- row-sharded TIED item table (training)
+def _reduce_scatter_rows(full, group):
+    """Sum of `full` [world * n, ...] over ranks, this rank keeping its n rows (reduce-scatter; gloo, which has no
+    reduce-scatter, all-reduces and slices — CPU tests only)."""
+    world, rank = _world(group), dist.get_rank(group)
+    n = full.shape[0] // world
+    if dist.get_backend(group) == "nccl":
+        out = torch.empty((n, *full.shape[1:]), dtype=full.dtype, device=full.device)
+        dist.reduce_scatter_tensor(out, full.contiguous(), op=dist.ReduceOp.SUM, group=group)
+        return out
+    full = full.clone()
+    dist.all_reduce(full, op=dist.ReduceOp.SUM, group=group)
+    return full[rank * n:(rank + 1) * n].clone()
+
+
+class _Kernels:
+    """The per-shard CUDA entry points the sharded table calls; the gloo CPU tests substitute oracle stand-ins."""
+    embed_fwd = None   # filled lazily (ops needs the library)
+
+
+class _TiedEmbedLN(torch.autograd.Function):
+    """LayerNorm(dropout(table[ids])) reading the REPLICATED bf16 copy; its backward does not return a table gradient
+    but routes the per-token row gradients to the row owners' fp32 gradient shards (ShardedItemTable.add_row_grads)."""
+
+    @staticmethod
+    def forward(ctx, ids, gamma, beta, sit, eps, p, seed, seed_dev):
+        out, saved = sit.k.embed_fwd(ids, sit.table_bf16, gamma, beta, eps, p, seed, seed_dev)
+        ctx.sit, ctx.saved, ctx.args = sit, saved, (ids, gamma, eps, p, seed, seed_dev)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        sit = ctx.sit
+        ids, gamma, eps, p, seed, seed_dev = ctx.args
+        dgamma, dbeta = sit.k.embed_bwd(sit, ids, gamma, grad_out, ctx.saved, p, seed, seed_dev)
+        return None, dgamma.to(gamma.dtype), dbeta.to(gamma.dtype), None, None, None, None, None
+
+
+class _TiedCE(torch.autograd.Function):
+    """Global-mean full-softmax CE of a data-parallel batch against the row-sharded table: all-gather the queries,
+    per-shard statistics, tiny all-reduces, and in the backward dE written STRAIGHT into the owner's gradient shard while
+    the dQ partials are reduce-scattered back to the users' ranks."""
+
+    @staticmethod
+    def forward(ctx, q, pos, sit):
+        world, group = sit.world, sit.group
+        qb = q.detach().to(torch.bfloat16).contiguous()
+        pos = pos.contiguous()
+        if world > 1:
+            q_all = torch.empty((world * qb.shape[0], qb.shape[1]), dtype=qb.dtype, device=qb.device)
+            dist.all_gather_into_tensor(q_all, qb, group=group)
+            pos_all = torch.empty(world * pos.shape[0], dtype=pos.dtype, device=pos.device)
+            dist.all_gather_into_tensor(pos_all, pos, group=group)
+        else:
+            q_all, pos_all = qb, pos
+        m, s, pl = sit.k.ce_stats(q_all, sit.shard_bf16(), pos_all, sit.lo)
+        lse, pl = combine_ce_stats(m, s, pl, group)
+        ctx.sit, ctx.q_dtype = sit, q.dtype
+        ctx.save_for_backward(q_all, pos_all, lse)
+        return (lse - pl).mean()
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        sit = ctx.sit
+        q_all, pos_all, lse = ctx.saved_tensors
+        de = sit.grad_buffer()                       # fp32 [rows_per, D]; rows [0, n_local) are OVERWRITTEN by the kernel
+        dq_part = sit.k.ce_grads(q_all, sit.shard_bf16(), pos_all, lse, 1.0 / q_all.shape[0], sit.lo, grad_loss,
+                                 de[:sit.n_local])
+        sit.master.grad = de
+        sit._ce_written = True
+        dq = _reduce_scatter_rows(dq_part, sit.group) if sit.world > 1 else dq_part
+        return dq.to(ctx.q_dtype), None, None
+
+
+class ShardedItemTable:
+    """The tied item-embedding table of RecBLR (RecBLR.py:39, used by the input gather :76 AND the CE :99-103) ROW-SHARDED
+    over the ranks of a process group for training at configs[4] scale:
+
+      master      fp32 [rows_per, D] nn.Parameter — this rank's rows [lo, hi) (+ zero pad rows up to rows_per, so that every
+                  shard has the same size); the optimizer and its state exist for these rows only
+      table_bf16  bf16 [world * rows_per, D], replicated — what the input gather and the tensor-core CE read; refreshed
+                  after every optimizer step from the masters (one cast of the shard + one in-place all-gather)
+
+    Per step nothing of size [n_items, D] is all-reduced: the CE's dE is complete on the owner (every rank scores ALL
+    users of the global batch against its rows) and is written by the kernel directly into `master.grad`; the input
+    gather's row gradients travel as (ids, bf16 rows) of the local tokens, all-gathered and scatter-added by each owner
+    for its id range; the loss is the GLOBAL mean, so dense parameters are afterwards SUMMED over ranks
+    (`allreduce_gradients(dense, average=False)`).  world == 1 degenerates to the same code without collectives."""
+
+    def __init__(self, full_weight, group=None, padding_idx=0, kernels=None):
+        self.group = group
+        self.world = _world(group)
+        self.rank = dist.get_rank(group) if self.world > 1 else 0
+        n_items, D = full_weight.shape
+        self.n_items, self.D, self.padding_idx = n_items, D, padding_idx
+        self.rows_per = -(-n_items // self.world)
+        self.lo = min(self.rank * self.rows_per, n_items)
+        self.hi = min(self.lo + self.rows_per, n_items)
+        self.n_local = self.hi - self.lo
+        dev = full_weight.device
+        master = torch.zeros((self.rows_per, D), dtype=torch.float32, device=dev)
+        master[:self.n_local] = full_weight.detach()[self.lo:self.hi].float()
+        self.master = torch.nn.Parameter(master)
+        self.table_bf16 = torch.zeros((self.world * self.rows_per, D), dtype=torch.bfloat16, device=dev)
+        self._grad = None
+        self._ce_written = False
+        assert self.n_local >= 1, f"item table of {n_items} rows cannot be sharded {self.world} ways"
+        self.k = kernels or _cuda_kernels()
+        self.refresh()
+
+    # ---- views
+    def shard_bf16(self):
+        return self.table_bf16[self.lo:self.lo + self.n_local]   # lo == rank * rows_per: global id == row of the copy
+
+    def grad_buffer(self):
+        if self._grad is None:
+            self._grad = torch.zeros_like(self.master)   # pad rows stay zero for ever
+        return self._grad
+
+    # ---- the two uses of the table
+    def embed_layernorm(self, ids, gamma, beta, eps, dropout_p, seed, seed_dev):
+        return _TiedEmbedLN.apply(ids, gamma, beta, self, float(eps), float(dropout_p), int(seed), seed_dev)
+
+    def cross_entropy(self, q, pos):
+        return _TiedCE.apply(q, pos, self)
+
+    def add_row_grads(self, ids, drows):
+        """Owner-side accumulation of the input gather's gradient: ids int64 [n], drows [n, D] of THIS rank's tokens."""
+        assert self._ce_written, "sharded table: the CE backward must run before the embedding backward (same loss)"
+        de = self.master.grad
+        if self.world > 1:
+            ids_all = torch.empty(self.world * ids.numel(), dtype=ids.dtype, device=ids.device)
+            dist.all_gather_into_tensor(ids_all, ids.reshape(-1).contiguous(), group=self.group)
+            rows_all = torch.empty((self.world * drows.shape[0], drows.shape[1]), dtype=drows.dtype, device=drows.device)
+            dist.all_gather_into_tensor(rows_all, drows.contiguous(), group=self.group)
+        else:
+            ids_all, rows_all = ids.reshape(-1), drows
+        self.k.scatter_rows(ids_all, rows_all, de, self.lo, self.hi, self.padding_idx)
+        self._ce_written = False
+
+    # ---- after the optimizer step
+    @torch.no_grad()
+    def refresh(self):
+        """bf16 copy <- masters: cast this rank's rows into its slice, then one in-place all-gather of the slices."""
+        mine = self.table_bf16[self.rank * self.rows_per:(self.rank + 1) * self.rows_per]
+        mine.copy_(self.master)
+        if self.world > 1:
+            dist.all_gather_into_tensor(self.table_bf16, mine, group=self.group)
+
+    def attach(self, optimizer):
+        """Refresh the replicated copy automatically after every `optimizer.step()`."""
+        optimizer.register_step_post_hook(lambda *_: self.refresh())
+        return self
+
+    @torch.no_grad()
+    def full_weight(self):
+        """fp32 [n_items, D] assembled from the masters (checkpointing; one all-gather)."""
+        if self.world == 1:
+            return self.master.detach()[:self.n_items].clone()
+        out = torch.empty((self.world * self.rows_per, self.D), dtype=torch.float32, device=self.master.device)
+        dist.all_gather_into_tensor(out, self.master.detach().contiguous(), group=self.group)
+        return out[:self.n_items].clone()
+
+    @torch.no_grad()
+    def full_sort_topk(self, q, k, mask_id=0):
+        """Data-parallel eval: every rank holds different users; gather them, score all against the local rows, merge
+        the per-shard lists, keep this rank's users."""
+        qb = q.detach().to(torch.bfloat16).contiguous()
+        if self.world > 1:
+            q_all = torch.empty((self.world * qb.shape[0], qb.shape[1]), dtype=qb.dtype, device=qb.device)
+            dist.all_gather_into_tensor(q_all, qb, group=self.group)
+        else:
+            q_all = qb
+        s, i = sharded_topk(q_all, self.shard_bf16(), k, id_offset=self.lo, mask_id=mask_id, group=self.group)
+        n = qb.shape[0]
+        return s[self.rank * n:(self.rank + 1) * n], i[self.rank * n:(self.rank + 1) * n]
+
+
+def _cuda_kernels():
+    """The CUDA entry points behind ShardedItemTable (bf16 table, bf16 activations)."""
+    from . import _lib as L
+
+    class K:
+        @staticmethod
+        def embed_fwd(ids, table, gamma, beta, eps, p, seed, seed_dev):
+            n_items, D = table.shape
+            ids_c = ids.contiguous()
+            gf, bf = gamma.detach().float().contiguous(), beta.detach().float().contiguous()
+            n = ids_c.numel()
+            out = torch.empty((*ids.shape, D), dtype=table.dtype, device=table.device)
+            mean = torch.empty(n, dtype=torch.float32, device=table.device)
+            rstd = torch.empty_like(mean)
+            L.check(L.load().bdlru_embed_ln_fwd(L.ptr(ids_c), L.ptr(table), L.ptr(gf), L.ptr(bf), L.ptr(out), L.ptr(mean),
+                                                L.ptr(rstd), n, n_items, D, eps, p, seed, L.ptr(seed_dev),
+                                                L.dtype_tag(table), L.dtype_tag(out), L.stream_ptr(table)))
+            return out, (ids_c, gf, mean, rstd)
+
+        @staticmethod
+        def embed_bwd(sit, ids, gamma, grad_out, saved, p, seed, seed_dev):
+            ids_c, gf, mean, rstd = saved
+            table = sit.table_bf16
+            n_items, D = table.shape
+            n = ids_c.numel()
+            grad_out = grad_out.to(table.dtype).contiguous()
+            dgamma = torch.empty(D, dtype=torch.float32, device=table.device)
+            dbeta = torch.empty_like(dgamma)
+            lib = L.load()
+            nws = lib.bdlru_embed_ln_bwd_workspace_bytes(n, D)
+            ws = ops._workspace(table.device, nws)
+            tail = (n, n_items, D, p, seed, L.ptr(seed_dev), sit.padding_idx, L.dtype_tag(table), L.dtype_tag(grad_out),
+                    L.stream_ptr(table))
+            if sit.world == 1:   # the owner is this rank: scatter straight into the gradient shard the CE already wrote
+                assert sit._ce_written, "sharded table: the CE backward must run before the embedding backward"
+                L.check(lib.bdlru_embed_ln_bwd(L.ptr(ids_c), L.ptr(table), L.ptr(gf), L.ptr(grad_out), L.ptr(mean),
+                                               L.ptr(rstd), L.ptr(sit.master.grad), L.ptr(dgamma), L.ptr(dbeta), L.ptr(ws),
+                                               nws, *tail))
+                sit._ce_written = False
+            else:
+                drows = torch.empty((n, D), dtype=table.dtype, device=table.device)
+                L.check(lib.bdlru_embed_ln_bwd_rows(L.ptr(ids_c), L.ptr(table), L.ptr(gf), L.ptr(grad_out), L.ptr(mean),
+                                                    L.ptr(rstd), L.ptr(drows), L.ptr(dgamma), L.ptr(dbeta), L.ptr(ws), nws,
+                                                    *tail))
+                sit.add_row_grads(ids_c, drows)
+            return dgamma, dbeta
+
+        @staticmethod
+        def ce_stats(q_all, shard, pos_all, lo):
+            return ops.fullsort_ce_stats(q_all, shard, pos_all, id_offset=lo)
+
+        @staticmethod
+        def ce_grads(q_all, shard, pos_all, lse, scale, lo, grad_loss, out_de):
+            dq, _ = ops.fullsort_ce_grads(q_all, shard, pos_all, lse, scale, id_offset=lo, scale_dev=grad_loss,
+                                          out_de=out_de)
+            return dq
+
+        @staticmethod
+        def scatter_rows(ids_all, rows_all, dst, lo, hi, padding_idx):
+            ops.scatter_add_rows(ids_all, rows_all, dst, lo, hi, padding_idx)
+
+    return K
+
+
+def shard_item_table(model, group=None):
+    """Switches a constructed RecBLR (identical full table on every rank: same seed, or a loaded checkpoint) to the
+    row-sharded tied table: `model.item_embedding.weight` becomes this rank's fp32 master shard (what the optimizer
+    sees), `model.table_shard` the ShardedItemTable that `_front` / `calculate_loss` / `full_sort_topk` go through.
+    Call before building the optimizer, then `model.table_shard.attach(optimizer)`."""
+    full = model.item_embedding.weight
+    sit = ShardedItemTable(full.data, group=group, padding_idx=0)
+    del model.item_embedding.weight
+    model.item_embedding.weight = sit.master        # registered as the module's parameter again (nn.Parameter)
+    model.table_shard = sit
+    return sit
+
+
+def dense_parameters(model):
+    """Parameters replicated on every rank (everything but the sharded table): the ones to all-reduce."""
+    sit = getattr(model, "table_shard", None)
+    return [p for p in model.parameters() if sit is None or p is not sit.master]

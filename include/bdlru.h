@@ -148,6 +148,18 @@ int bdlru_embed_ln_bwd(const int64_t* ids, const void* table, const float* gamma
                        void* workspace, size_t workspace_bytes, int64_t n_tokens, int64_t n_items, int D,
                        float dropout_p, uint64_t seed, const uint64_t* seed_device, int64_t padding_idx, int dtype,
                        int out_dtype, void* stream);
+/* Row-sharded item table (SURVEY §8e "input gather with a sharded tied table"): the same backward, but instead of
+ * scattering it writes the per-token row gradients drows [n_tokens, D] in `out_dtype` (zeros at ids == padding_idx) —
+ * the payload of the exchange to the row owners — and bdlru_scatter_add_rows is the owner-side half:
+ * dst[(id - row_lo) * D + :] += rows[n, :] for every token with row_lo <= id < row_hi and id != padding_idx
+ * (dst = this rank's fp32 gradient shard, NOT zeroed here; vector red.global.add). */
+int bdlru_embed_ln_bwd_rows(const int64_t* ids, const void* table, const float* gamma, const void* grad_out,
+                            const float* mean, const float* rstd, void* drows, float* dgamma, float* dbeta,
+                            void* workspace, size_t workspace_bytes, int64_t n_tokens, int64_t n_items, int D,
+                            float dropout_p, uint64_t seed, const uint64_t* seed_device, int64_t padding_idx, int dtype,
+                            int out_dtype, void* stream);
+int bdlru_scatter_add_rows(const int64_t* ids, const void* rows, int64_t n_tokens, int D, int rows_dtype,
+                           int64_t row_lo, int64_t row_hi, int64_t padding_idx, float* dst, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Residual epilogue: out[n,:] = LayerNorm(dropout(x[n,:]) + residual[n,:]) * gamma + beta
@@ -199,6 +211,13 @@ int bdlru_fullsort_topk(const void* Q, const void* E, int64_t n_users, int64_t n
  * [n_users, n_lists * k] (any order inside); keeps the k best by (score desc, id asc). */
 int bdlru_topk_merge(const float* cand_scores, const int32_t* cand_ids, int64_t n_users, int n_lists, int k,
                      float* out_scores, int32_t* out_ids, void* stream);
+/* Same merge reading the candidate lists IN PLACE from any regular layout: candidate (list l, user u, slot j) is element
+ * l * list_stride + u * user_stride + j of cand_scores / cand_ids.  With list_stride = 2 * n_users * k, user_stride = k
+ * and cand_ids = cand_scores + n_users * k it consumes the buffer an NCCL all-gather of per-rank packed
+ * [2][n_users][k] (scores | ids) lists leaves behind — one collective, no permute/contiguous copies. */
+int bdlru_topk_merge_strided(const float* cand_scores, const int32_t* cand_ids, int64_t n_users, int n_lists, int k,
+                             int64_t list_stride, int64_t user_stride, float* out_scores, int32_t* out_ids,
+                             void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Full-softmax cross-entropy over all item rows (RecBLR.py:99-103) without materialising the logits.
@@ -208,6 +227,9 @@ int bdlru_topk_merge(const float* cand_scores, const int32_t* cand_ids, int64_t 
  * bwd: given the global lse[b] and the upstream scale (dloss / n_users_total), recomputes the logits
  *      tile by tile and writes dQ (fp32 [n_users, D], overwritten) and dE (fp32 [n_rows, D],
  *      overwritten):  P = exp(l - lse) - onehot;  dQ = scale * P E;  dE = scale * P^T Q.
+ *      scale_dev (may be NULL): DEVICE fp32 scalar multiplied into `scale` inside the kernel — the upstream gradient
+ *      of the loss stays on the device and dE can be written straight into the optimizer's gradient buffer.
+ *      Either of dQ / dE may be NULL (that gradient is skipped).
  * pos int64 [n_users] holds GLOBAL item ids.
  * ------------------------------------------------------------------------------------------- */
 size_t bdlru_fullsort_ce_workspace_bytes(int64_t n_users, int64_t n_rows, int D);
@@ -215,7 +237,7 @@ int bdlru_fullsort_ce_fwd(const void* Q, const void* E, const int64_t* pos, int6
                           int D, int64_t id_offset, float* row_max, float* row_sumexp, float* pos_logit,
                           void* workspace, size_t workspace_bytes, void* stream);
 int bdlru_fullsort_ce_bwd(const void* Q, const void* E, const int64_t* pos, const float* lse, float scale,
-                          int64_t n_users, int64_t n_rows, int D, int64_t id_offset,
+                          const float* scale_dev, int64_t n_users, int64_t n_rows, int D, int64_t id_offset,
                           float* dQ, float* dE, void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus

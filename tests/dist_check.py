@@ -67,9 +67,62 @@ def main():
     for (n1, p1), (n2, p2) in zip(ref_model.named_parameters(), dp_model.named_parameters()):
         den = p1.grad.abs().max().clamp_min(1e-12)
         assert (p1.grad - p2.grad).abs().max() <= 3e-2 * den, (n1, float((p1.grad - p2.grad).abs().max()), float(den))
+    # H7: the tied table itself row-sharded (fp32 master shard + replicated bf16 copy): TWO optimizer steps on `world`
+    # ranks == two steps of one process on the concatenated batches (table rounded to bf16 so both read the same values)
+    import copy
+    torch.manual_seed(5)
+    cfg = make_config(hidden_size=64, num_layers=2, dropout_prob=0.0, max_len=L)
+    cfg["device"] = dev
+    one = RecBLR(cfg, FakeDataset(n_items)).to(dev)
+    with torch.no_grad():
+        one.item_embedding.weight.copy_(one.item_embedding.weight.to(torch.bfloat16).float())
+    shd = copy.deepcopy(one)
+    sit = sharded.shard_item_table(shd)
+    opt1 = torch.optim.SGD(one.parameters(), lr=0.5)
+    opt2 = torch.optim.SGD(shd.parameters(), lr=0.5)
+    sit.attach(opt2)
+    for step in range(2):
+        seq, lens, tgt = TP.synthetic_batch(Bl * world, L, n_items, seed=20 + step)
+        full = {"item_id_list": seq.to(dev), "item_length": lens.to(dev), "item_id": tgt.to(dev)}
+        mine = {k: v[rank * Bl:(rank + 1) * Bl] for k, v in full.items()}
+        opt1.zero_grad(set_to_none=True)
+        opt2.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            l_one = one.calculate_loss(full)
+            l_shd = shd.calculate_loss(mine)
+        l_one.backward()
+        l_shd.backward()
+        sharded.allreduce_gradients(sharded.dense_parameters(shd), average=False)
+        assert abs(float(l_one) - float(l_shd)) <= 2e-3 * abs(float(l_one)), (step, float(l_one), float(l_shd))
+        g1 = one.item_embedding.weight.grad[sit.lo:sit.hi]
+        g2 = sit.master.grad[:sit.n_local]
+        den = one.item_embedding.weight.grad.abs().max()
+        assert (g1 - g2).abs().max() <= 3e-2 * den, ("table grad", step, float((g1 - g2).abs().max()), float(den))
+        d1 = {n: p.grad for n, p in one.named_parameters() if n != "item_embedding.weight"}
+        d2 = {n: p.grad for n, p in shd.named_parameters() if n != "item_embedding.weight"}
+        for n in d1:
+            den = d1[n].abs().max().clamp_min(1e-12)
+            assert (d1[n] - d2[n]).abs().max() <= 5e-2 * den, (n, step, float((d1[n] - d2[n]).abs().max()), float(den))
+        opt1.step()
+        opt2.step()            # post-hook: refresh of the replicated bf16 copy (cast + in-place all-gather)
+        with torch.no_grad():  # keep the single-process table bf16-representable like the sharded copy
+            full_w = sit.full_weight()
+            assert (full_w - one.item_embedding.weight).abs().max() <= 3e-2 * 0.5 * float(den) + 1e-3
+            one.item_embedding.weight.copy_(full_w.to(torch.bfloat16).float())
+            sit.master[:sit.n_local].copy_(one.item_embedding.weight[sit.lo:sit.hi])
+            sit.refresh()
+    # data-parallel eval through the sharded table: this rank's users, ids == the single-table fused top-k
+    one.eval()
+    shd.eval()
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        _, i_one = one.full_sort_topk(full, 10)
+        _, i_shd = shd.full_sort_topk(mine, 10)
+    agree = (i_one[rank * Bl:(rank + 1) * Bl] == i_shd).all(1).float().mean()
+    assert float(agree) >= 0.98, float(agree)     # the two models' seq_outputs differ by fp32 reduction order only
     dist.barrier()
     if rank == 0:
-        print(f"dist_check ok: world={world} loss={float(l1):.6f} dp_sharded_ce_loss={float(dp_loss):.6f}")
+        print(f"dist_check ok: world={world} loss={float(l1):.6f} dp_sharded_ce_loss={float(dp_loss):.6f} "
+              f"sharded_table_loss={float(l_shd):.6f}")
     dist.destroy_process_group()
 
 

@@ -97,14 +97,19 @@ def _cpu_ce_stats(qb, eb, pos, id_offset=0, item_bias=None):
     return m.float(), ssum.float(), pl.float()
 
 
-def _cpu_ce_grads(qb, eb, pos, lse, scale, id_offset=0):
+def _cpu_ce_grads(qb, eb, pos, lse, scale, id_offset=0, scale_dev=None, out_dq=None, out_de=None, want_dq=True,
+                  want_de=True):
     """Oracle stand-in for ops.fullsort_ce_grads: scale * (softmax - onehot) applied to both operands, GLOBAL lse."""
     p = torch.exp(qb.double() @ eb.double().T - lse.double()[:, None])
     loc = pos - id_offset
     own = (loc >= 0) & (loc < eb.shape[0])
     p[torch.arange(len(pos))[own], loc[own]] -= 1.0
-    p *= scale
-    return (p @ eb.double()).float(), (p.T @ qb.double()).float()
+    p *= scale * (1.0 if scale_dev is None else float(scale_dev))
+    dq, de = (p @ eb.double()).float(), (p.T @ qb.double()).float()
+    if out_de is not None:
+        out_de.copy_(de)
+        de = out_de
+    return dq, de
 
 
 def _ce_worker(rank, world, port, outdir, with_bias):
@@ -184,3 +189,112 @@ def test_shard_bounds_cover_table():
     for n, g in ((10, 3), (1000003, 8), (5, 8)):
         b = sharded.shard_bounds(n, g)
         assert b[0] == 0 and b[-1] == n and all(x <= y for x, y in zip(b, b[1:]))
+
+
+# ----------------------------------------------------------------------------- row-sharded TIED table (training, H7)
+class _CpuTableKernels:
+    """Oracle stand-ins (torch float64 on CPU) for the five CUDA entry points behind sharded.ShardedItemTable."""
+
+    @staticmethod
+    def embed_fwd(ids, table, gamma, beta, eps, p, seed, seed_dev):
+        assert p == 0.0
+        with torch.enable_grad():     # Function.forward runs under no_grad; the stand-in differentiates with autograd
+            rows = table[ids.reshape(-1)].double().requires_grad_(True)
+            g, b = gamma.detach().double().requires_grad_(True), beta.detach().double().requires_grad_(True)
+            out = torch.nn.functional.layer_norm(rows, (table.shape[1],), g, b, eps)
+        return out.detach().float().view(*ids.shape, -1), (ids, rows, g, b, out)
+
+    @staticmethod
+    def embed_bwd(sit, ids, gamma, grad_out, saved, p, seed, seed_dev):
+        ids, rows, g, b, out = saved
+        drows, dg, db = torch.autograd.grad(out, (rows, g, b), grad_out.double().reshape(out.shape))
+        drows[ids.reshape(-1) == sit.padding_idx] = 0
+        sit.add_row_grads(ids.reshape(-1), drows.float())
+        return dg.float(), db.float()
+
+    @staticmethod
+    def ce_stats(q_all, shard, pos_all, lo):
+        return _cpu_ce_stats(q_all, shard, pos_all, id_offset=lo)
+
+    @staticmethod
+    def ce_grads(q_all, shard, pos_all, lse, scale, lo, grad_loss, out_de):
+        dq, _ = _cpu_ce_grads(q_all, shard, pos_all, lse, scale, id_offset=lo, scale_dev=grad_loss, out_de=out_de)
+        return dq
+
+    @staticmethod
+    def scatter_rows(ids_all, rows_all, dst, lo, hi, padding_idx):
+        own = (ids_all >= lo) & (ids_all < hi) & (ids_all != padding_idx)
+        dst.index_add_(0, ids_all[own] - lo, rows_all[own].float())
+
+
+def _tied_data(world, N=53, D=16, B=6, Lq=5):
+    rng = np.random.default_rng(4)
+    table = torch.tensor(rng.integers(-4, 5, size=(N, D)) * 0.125, dtype=torch.float32)     # exact in bf16
+    gamma = torch.tensor(1.0 + rng.integers(-2, 3, size=D) * 0.125, dtype=torch.float32)
+    beta = torch.tensor(rng.integers(-2, 3, size=D) * 0.125, dtype=torch.float32)
+    ids = [torch.tensor(rng.integers(0, N, size=(B, Lq))) for _ in range(world)]           # includes padding id 0
+    pos = [torch.tensor(rng.integers(1, N, size=B)) for _ in range(world)]
+    return table, gamma, beta, ids, pos
+
+
+def _tied_worker(rank, world, port, outdir):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    if world > 1:
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    from datamining_recblr_b200 import sharded
+    table, gamma, beta, ids, pos = _tied_data(world)
+    sit = sharded.ShardedItemTable(table, padding_idx=0, kernels=_CpuTableKernels)
+    g, b = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    x = sit.embed_layernorm(ids[rank], g, b, 1e-12, 0.0, 0, None)          # [B, Lq, D]
+    q = torch.tanh(x.double()).mean(1).float()                             # stand-in for the recurrent layers
+    q = q + (q.to(torch.bfloat16).float() - q).detach()                    # the CE rounds q to bf16 (a real cast would also
+                                                                           # round the GRADIENT to bf16 on the way back)
+    loss = sit.cross_entropy(q, pos[rank])
+    (loss * 3.0).backward()
+    dgb = torch.stack([g.grad, b.grad])
+    if world > 1:
+        dist.all_reduce(dgb)                                               # dense parameters: summed over ranks
+    grad = sit.master.grad.clone()
+    with torch.no_grad():
+        sit.master -= 0.25 * sit.master.grad                               # a "step", then refresh the replicated copy
+    sit.refresh()
+    torch.save(dict(loss=loss.detach(), grad=grad, dgb=dgb, lo=sit.lo, hi=sit.hi, n_local=sit.n_local,
+                    copy=sit.table_bf16.clone(), full=sit.full_weight()), os.path.join(outdir, f"r{rank}.pt"))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [1, 2, 3])
+def test_sharded_tied_table_step_equals_single_table_autograd(tmp_path, world):
+    """ShardedItemTable on `world` gloo ranks (different users per rank), the oracle standing in for the kernels: the
+    GLOBAL-mean loss, the per-owner gradient shards (CE part written in place + input-gather rows exchanged and
+    scatter-added, padding id skipped), the summed dense gradients and the refreshed replicated bf16 copy all equal plain
+    float64 autograd over ONE tied table with the concatenated batch."""
+    if world == 1:
+        _tied_worker(0, 1, 0, str(tmp_path))
+    else:
+        mp.spawn(_tied_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    rs = [torch.load(str(tmp_path / f"r{r}.pt")) for r in range(world)]
+    table, gamma, beta, ids, pos = _tied_data(world)
+    T = table.double().requires_grad_(True)
+    g, b = gamma.double().requires_grad_(True), beta.double().requires_grad_(True)
+    all_ids, all_pos = torch.cat(ids), torch.cat(pos)
+    emb = torch.nn.functional.embedding(all_ids, T, padding_idx=0)
+    x = torch.nn.functional.layer_norm(emb, (T.shape[1],), g, b, 1e-12)
+    q = torch.tanh(x.float().double()).mean(1)
+    q = q + (q.float().to(torch.bfloat16).double() - q).detach()           # same bf16 rounding, identity gradient
+    loss = torch.nn.functional.cross_entropy(q @ T.T, all_pos)
+    (loss * 3.0).backward()
+    for r in rs:
+        assert abs(float(r["loss"]) - float(loss)) < 1e-5 * abs(float(loss))
+        want = T.grad[r["lo"]:r["hi"]]
+        got = r["grad"][:r["n_local"]].double()
+        assert (got - want).abs().max() < 2e-5 * T.grad.abs().max(), (r["lo"], (got - want).abs().max())
+        assert float(r["grad"][r["n_local"]:].abs().sum()) == 0.0         # pad rows of the last shard stay zero
+        assert (r["dgb"][0].double() - g.grad).abs().max() < 1e-4 * g.grad.abs().max()
+        assert (r["dgb"][1].double() - b.grad).abs().max() < 1e-4 * b.grad.abs().max()
+        new_full = (table.double() - 0.25 * T.grad).float()
+        assert (r["full"] - new_full).abs().max() < 1e-5
+        assert torch.equal(r["copy"][:table.shape[0]], r["full"].to(torch.bfloat16))
+        assert torch.equal(r["copy"], rs[0]["copy"])                       # replicated copy identical on every rank
