@@ -1,17 +1,25 @@
 #!/usr/bin/env python
 """bench.py — the hot path of BASELINE.json on N B200s of one node; prints ONE JSON line (rank 0).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload beauty|ml1m|score1m|score10m]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload north_star|strain10m|strain1m|beauty|ml1m|score1m|score10m]
 
 Workloads (BASELINE.json `configs`):
-  beauty   (default) configs[1]: RecBLR at the Amazon-Beauty shape — n_items 12 102, L = 50, D = 64 (C = 128),
-           2 layers, train batch 2 048 per GPU.  A step is RecBole's `_train_epoch` body for one batch:
-           zero_grad -> calculate_loss (front end, 2 x (BD-LRU + FFN), CE over all items) -> backward -> Adam.
-           metric = BD-LRU fwd+bwd seq-tokens/s = B*L*N / step time.  A `fullsort` sub-object reports the other half
-           of the metric (full-sort scored users/s, eval batch 4 096) measured the same way.
-  ml1m     configs[0]'s shape (n_items 3 417, L = 200) through the same step.
-  score1m / score10m   configs[3]: synthetic full-sort scoring, D = 128, 4 096 users, item table row-sharded over
-           the N ranks with an NCCL top-k merge; metric = full-sort scored users/s.
+  north_star (default) = the largest single-GPU configuration, configs[4] "synthetic large-scale training": RecBLR with
+           10 M items, L = 200, D = 128 (C = 256), 2 layers, batch 8 192 per GPU, bf16 autocast.  A step is RecBole's
+           `_train_epoch` body for one batch: zero_grad -> calculate_loss (front end, 2 x (BD-LRU + FFN), full-softmax CE
+           over all 10 M items) -> backward -> Adam.  The tied item table is ROW-SHARDED over the N ranks (fp32 master
+           shard + optimizer state on the owner, replicated bf16 copy refreshed by an all-gather; sharded.ShardedItemTable),
+           the layers are data parallel.  metric = BD-LRU fwd+bwd seq-tokens/s = N*B*L / step time (weak scaling).
+           Sub-objects on the same line: `fullsort` = configs[3], 4 096 users scored against the SAME 10 M-row table,
+           row-sharded over the N ranks with the NCCL list merge (users/s, strong scaling); `sweep` = configs[2] corners of
+           the fused gate+scan fwd+bwd against the HBM roofline, fp32 and bf16 (N = 1 only); `vs_triton` = the reference's
+           own Triton-scan layer timed on the same GPU (N = 1 only); `parity_check` = in-run assertion that the sharded
+           path equals the single-table kernels; `cpu_baseline` (N = 1 only).
+  strain10m / strain1m   the training line alone (1 M items = the 10x smaller probe).
+  beauty   configs[1]: Amazon-Beauty shape — n_items 12 102, L = 50, D = 64, B = 2 048/GPU, table replicated, whole step
+           as one CUDA graph, data-parallel gradient all-reduce.    ml1m: configs[0]'s shape through the same step.
+  score1m / score10m   configs[3] alone: synthetic full-sort scoring, D = 128, 4 096 users, table row-sharded.
 
 `--impl reference` times the CPU restatement of the reference (oracle/torch_port.py: literal pad, F.conv1d,
 separate gate ops, sequential scan) with all host threads on a bounded sample of the same workload.
@@ -124,10 +132,30 @@ def finish_distributed(world):
 
 def ncu_traffic(workload, kernel):
     """dram bytes per launch of `kernel` from the committed ncu capture of this workload (None if there is none)."""
-    try:
-        return json.load(open(os.path.join(ROOT, "profiles", "r1_dram_traffic.json")))[workload][kernel]
-    except Exception:
-        return None
+    for name in ("r2_dram_traffic.json", "r1_dram_traffic.json"):
+        try:
+            return json.load(open(os.path.join(ROOT, "profiles", name)))[workload][kernel]
+        except Exception:
+            continue
+    return None
+
+
+def refuse_tuning_environment():
+    """A timed kernel must not be steerable from the environment: refuse to run with any BDLRU_* variable set or with a
+    -DBDLRU_TUNING build of the library (the only kind that reads them)."""
+    bad = sorted(k for k in os.environ if k.startswith("BDLRU_"))
+    if bad:
+        raise SystemExit(f"bench.py refuses to run with tuning variables set: {bad}")
+
+
+def bench_header():
+    """Which binary produced the numbers: ABI version, source digest baked into libbdlru.so, and whether that digest
+    matches the sources lying next to it."""
+    from datamining_recblr_b200 import _lib
+    info = _lib.build_info()
+    if info["tuning"]:
+        raise SystemExit("bench.py refuses to time a -DBDLRU_TUNING build of libbdlru.so")
+    return {"library": info}
 
 
 def dist_env():
@@ -219,12 +247,18 @@ def run_reference(args):
     rank, world, _ = dist_env()
     if rank != 0:
         return
-    if args.workload in WORKLOADS:
-        w = WORKLOADS[args.workload]
-        base, t = cpu_train_baseline(w, args.steps, max(1, min(args.warmup, 2)), sample_B=args.cpu_sample or (16 if w.get("big") else 1024))
+    wname = "strain10m" if args.workload == "north_star" else args.workload
+    if wname in WORKLOADS:
+        w = WORKLOADS[wname]
+        # bounded: each CPU step costs seconds (10 M-row table: CE over all items, dense dE, Adam), so at most 5 timed steps
+        args.steps = min(args.steps, 5 if w.get("big") else 20)
+        base, t = cpu_train_baseline(w, args.steps, 1 if w.get("big") else max(1, min(args.warmup, 2)),
+                                     sample_B=args.cpu_sample or (32 if w.get("big") else 1024))
         line = dict(metric="bdlru_fwd_bwd_seq_tokens_per_s", value=base["value"], unit="seq-tokens/s",
-                    config=dict(workload=f"{args.workload}: n_items={w['n_items']} L={w['L']} D={w['D']} "
-                                         f"layers={w['layers']} train step (CE over all items + Adam)"),
+                    config=dict(workload=f"{wname}: RecBLR n_items={w['n_items']} L={w['L']} D={w['D']} C={2 * w['D']} "
+                                         f"layers={w['layers']} batch {w['B']}/GPU, train step = zero_grad + calculate_loss "
+                                         f"(CE over all items) + backward + Adam",
+                                sample=base["sample"]),
                     dtype="f32")
     else:
         n = SCORE_WORKLOADS[args.workload]
@@ -239,6 +273,23 @@ def run_reference(args):
 
 
 # ----------------------------------------------------------------------------- our arm: training step
+def parity_check_sharded_ce(sit, dev, n=512):
+    """ASSERTS, before any timing, that the row-sharded CE statistics (per-shard kernel + NCCL combine) equal the
+    single-table kernel run on the replicated copy: global LSE and positive logit of n seeded users."""
+    from datamining_recblr_b200 import ops, sharded
+    g = torch.Generator().manual_seed(77)
+    q = torch.randn(n, sit.D, generator=g).to(torch.bfloat16).to(dev)
+    pos = torch.randint(1, sit.n_items, (n,), generator=g).to(dev)
+    m, s, pl = ops.fullsort_ce_stats(q, sit.shard_bf16(), pos, id_offset=sit.lo)
+    lse, pl = sharded.combine_ce_stats(m, s, pl, sit.group)
+    m1, s1, pl1 = ops.fullsort_ce_stats(q, sit.table_bf16[:sit.n_items], pos)
+    lse1 = m1 + torch.log(s1)
+    e_lse = float(((lse - lse1).abs() / lse1.abs().clamp_min(1e-6)).max())
+    e_pl = float((pl - pl1).abs().max() / pl1.abs().max().clamp_min(1e-6))
+    assert e_lse <= 1e-6 and e_pl <= 1e-6, f"parity_check: sharded CE differs from the single table (lse {e_lse}, pos {e_pl})"
+    return {"ce_lse_max_rel": e_lse, "ce_pos_logit_max_rel": e_pl, "ce_users": n}
+
+
 def run_train(args):
     import torch.distributed as dist
     from datamining_recblr_b200 import _lib, sharded
@@ -251,26 +302,37 @@ def run_train(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    w = WORKLOADS[args.workload]
+    north = args.workload == "north_star"
+    wname = "strain10m" if north else args.workload
+    w = WORKLOADS[wname]
     B, L, D = w["B"], w["L"], w["D"]
     torch.manual_seed(2020)
     big = bool(w.get("big"))
     cfg = make_config(w, dev)
-    if big and world > 1:
-        cfg["ce_impl"] = "sharded"   # global-mean loss: gradients are SUMMED over ranks
-    model = RecBLR(cfg, _DS(w["n_items"])).to(dev)
+    with torch.device(dev):   # parameters are created on the GPU (same seed => identical on every rank)
+        model = RecBLR(cfg, _DS(w["n_items"]))
+    sit = None
+    if big:   # tied item table row-sharded over the ranks (world 1: same code, no collectives)
+        sit = sharded.shard_item_table(model)
+        torch.cuda.empty_cache()
     opt = torch.optim.Adam(model.parameters(), lr=1e-3, fused=True, capturable=True)
-    params = [p for p in model.parameters()]
+    if sit is not None:
+        sit.attach(opt)   # refresh of the replicated bf16 copy after every optimizer step
+    dense = sharded.dense_parameters(model)
     amp = args.dtype == "bf16"
+    assert amp or sit is None, "the sharded-table workloads run in bf16"
 
-    # distinct batches per step (and per rank): > L2 is not reachable at this shape, so L2 is flushed between steps
-    n_batches = 2 if w.get("big") else 4
+    # distinct batches per step (and per rank)
+    n_batches = 2 if big else 4
     host = [synthetic_batch(B, L, w["n_items"], seed=2020 + 97 * rank + i) for i in range(n_batches)]
     host = [tuple(t.pin_memory() for t in b) for b in host]
     devb = [tuple(t.to(dev) for t in b) for b in host]
 
     def allreduce_grads(ps):
-        sharded.allreduce_gradients(ps, average=model.ce_impl != "sharded")   # one flat NCCL call, grads become views
+        if sit is not None:   # loss is the GLOBAL mean: dense gradients are summed; the table gradient is owner-local
+            sharded.allreduce_gradients(dense, average=False)
+        else:
+            sharded.allreduce_gradients(ps, average=True)   # one flat NCCL call, grads become views
 
     def eager_step(batch):
         inter = {"item_id_list": batch[0], "item_length": batch[1], "item_id": batch[2]}
@@ -279,9 +341,13 @@ def run_train(args):
             loss = model.calculate_loss(inter)
         loss.backward()
         if world > 1:
-            allreduce_grads(params)
+            allreduce_grads([p for p in model.parameters()])
         opt.step()
         return loss.detach()
+
+    parity = None
+    if sit is not None:
+        parity = parity_check_sharded_ce(sit, dev)
 
     model.train()
     graphed = None
@@ -309,8 +375,9 @@ def run_train(args):
 
     # ---- timed region: K steps, inputs resident in HBM, CUDA events per step, L2 flushed between steps
     timed = ["bdlru_gated_scan_fwd", "bdlru_gated_scan_bwd", "bdlru_conv1d_fwd", "bdlru_conv1d_bwd",
-             "bdlru_embed_ln_fwd", "bdlru_embed_ln_bwd", "bdlru_fullsort_ce_fwd", "bdlru_fullsort_ce_bwd",
-             "bdlru_add_ln_fwd", "bdlru_add_ln_bwd", "bdlru_colsum"]
+             "bdlru_embed_ln_fwd", "bdlru_embed_ln_bwd", "bdlru_embed_ln_bwd_rows", "bdlru_scatter_add_rows",
+             "bdlru_fullsort_ce_fwd", "bdlru_fullsort_ce_bwd", "bdlru_add_ln_fwd", "bdlru_add_ln_bwd", "bdlru_colsum",
+             "bdlru_silu_dropout_fwd", "bdlru_silu_dropout_bwd"]
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -350,11 +417,11 @@ def run_train(args):
         launches = graphed_launches * args.steps
     if world > 1:
         dist.barrier()
-    total_ms = sum(s.elapsed_time(e) for s, e in evs)
-    tt = torch.tensor([total_ms], device=dev)
+    per_step = [s.elapsed_time(e) for s, e in evs]
+    tt = torch.tensor([sum(per_step), statistics.median(per_step), min(per_step)], device=dev)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    total_ms = float(tt)
+    total_ms, med_ms, min_ms = (float(x) for x in tt)
     ms_per_step = total_ms / args.steps
     value = world * B * L / (ms_per_step * 1e-3)
 
@@ -373,40 +440,18 @@ def run_train(args):
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_s = float(te)
-    clocks = sampler.stop() if rank == 0 else None
     h2d = sum(t.numel() * t.element_size() for t in host[0])
 
-    # ---- the other half of the metric: full-sort scored users/s at the eval batch (forward + scoring + top-k)
+    # ---- the other half of the metric: full-sort scored users/s
     fullsort = None
-    if rank == 0:
-        model.eval()
-        EB = w["eval_B"]
-        eb = tuple(t.to(dev) for t in synthetic_batch(EB, L, w["n_items"], seed=7))
-        inter = {"item_id_list": eb[0], "item_length": eb[1], "item_id": eb[2]}
-        from datamining_recblr_b200 import ops
-
-        def score():
-            with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
-                if ops.fullsort_supported(D):
-                    return model.full_sort_topk(inter, 10)
-                s = model.full_sort_predict(inter)  # dense fallback of the stock trainer until the fused kernel lands
-                s[:, 0] = float("-inf")
-                return torch.topk(s, 10)
-        for _ in range(3):
-            score()
-        ts = []
-        for _ in range(max(args.steps, 5)):
-            flush_l2(dev)
-            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s.record()
-            score()
-            e.record()
-            e.synchronize()
-            ts.append(s.elapsed_time(e))
-        fullsort = dict(metric="fullsort_scored_users_per_s", value=EB / (statistics.median(ts) * 1e-3), unit="users/s",
-                        users=EB, n_items=w["n_items"], k=10, ms=statistics.median(ts),
-                        fused_topk=bool(ops.fullsort_supported(D)))
-        model.train()
+    if sit is not None:
+        # configs[3] on the table just trained: 4 096 users against all n_items rows, row-sharded over the ranks
+        from bench_score import score_leg
+        fullsort = score_leg(sit.shard_bf16(), sit.lo, sit.n_items, steps=20 if north else 10, warmup=3,
+                             full_table=sit.table_bf16[:sit.n_items])
+    elif rank == 0:
+        fullsort = model_fullsort_leg(model, w, dev, amp, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
 
     if rank != 0:
         del graphed
@@ -418,79 +463,140 @@ def run_train(args):
     es = 2 if amp else 4
     C = 2 * D
     E_l = B * L * C  # elements of one [B, L, C] activation
-    # algorithmic bytes per launch (DESIGN.md §Kernels): z-fused gated scan fwd reads x', r, i, z and writes h, y;
+    # algorithmic bytes per launch (DESIGN.md §2): z-fused gated scan fwd reads x', r, i, z and writes h, y;
     # bwd reads x', r, i, z, h, g and writes dx', dr, di, dz
+    tab_es = 2 if sit is not None else 4
     alg = {"bdlru_gated_scan_fwd": 6 * E_l * es, "bdlru_gated_scan_bwd": 10 * E_l * es,
            "bdlru_conv1d_fwd": 2 * E_l * es, "bdlru_conv1d_bwd": 4 * E_l * es,
-           "bdlru_embed_ln_fwd": B * L * (8 + 2 * D * 4), "bdlru_embed_ln_bwd": B * L * (8 + 3 * D * 4),
-           "bdlru_add_ln_fwd": 3 * B * L * D * es, "bdlru_add_ln_bwd": 5 * B * L * D * es}
+           "bdlru_embed_ln_fwd": B * L * (8 + D * tab_es + D * es), "bdlru_embed_ln_bwd": B * L * (8 + D * tab_es + D * es + D * 4),
+           "bdlru_embed_ln_bwd_rows": B * L * (8 + D * tab_es + 2 * D * es),
+           "bdlru_add_ln_fwd": 3 * B * L * D * es, "bdlru_add_ln_bwd": 5 * B * L * D * es,
+           "bdlru_silu_dropout_fwd": 2 * B * L * 4 * D * es, "bdlru_silu_dropout_bwd": 3 * B * L * 4 * D * es}
     per_kernel = {}
     for name, ts in ktimes.items():
         if ts:
             per_kernel[name] = dict(calls_per_step=len(ts) / eager_steps, avg_ms=sum(ts) / len(ts),
-                                    share_of_step=(sum(ts) / eager_steps) / ms_per_step if world == 1 else None,
+                                    share_of_step=(sum(ts) / eager_steps) / ms_per_step,
                                     gbs=(alg[name] / (sum(ts) / len(ts)) / 1e6) if name in alg else None)
-    Bce = B * world if model.ce_impl == "sharded" else B
-    Nce = w["n_items"] // world if model.ce_impl == "sharded" else w["n_items"]
+            if name in alg:
+                per_kernel[name]["hbm_frac"] = per_kernel[name]["gbs"] / P["hbm"]
+    Bce = B * world if sit is not None else B
+    Nce = sit.n_local if sit is not None else w["n_items"]
     flops = {"bdlru_fullsort_ce_fwd": 2.0 * Bce * Nce * D, "bdlru_fullsort_ce_bwd": 4.0 * Bce * Nce * D}
     for name, f in flops.items():
         if name in per_kernel:
             per_kernel[name]["tflops"] = f / (per_kernel[name]["avg_ms"] * 1e-3) / 1e12
+            per_kernel[name]["tensor_frac"] = per_kernel[name]["tflops"] / P["tf_sustained"]
+    if "bdlru_fullsort_ce_bwd" in per_kernel:   # both gradients recompute the logits: 8*B*N*D executed, 4*B*N*D credited
+        per_kernel["bdlru_fullsort_ce_bwd"]["tflops_executed"] = 2 * per_kernel["bdlru_fullsort_ce_bwd"]["tflops"]
     cand = [n for n in per_kernel if n in alg or n in flops]
     dom = max(cand, key=lambda n: per_kernel[n]["avg_ms"] * per_kernel[n]["calls_per_step"])
     if dom in flops:
         roofline = dict(bound="tensor", kernel=dom, achieved=per_kernel[dom]["tflops"], peak=P["tf_sustained"],
-                        unit="TFLOP/s", frac=per_kernel[dom]["tflops"] / P["tf_sustained"], traffic=None,
-                        peak_source=P["src"] + " (sustained bf16 cuBLAS)", algorithmic_flops_per_launch=flops[dom],
+                        unit="TFLOP/s", frac=per_kernel[dom]["tflops"] / P["tf_sustained"],
+                        traffic=ncu_traffic(wname, dom),
+                        peak_source=P["src"] + " (sustained bf16 cuBLAS: the kernel is timed inside a long step)",
+                        algorithmic_flops_per_launch=flops[dom],
                         avg_launch_ms=per_kernel[dom]["avg_ms"],
-                        note="credited flops: 2*B*N*D forward, 4*B*N*D backward (dQ and dE; the recompute GEMMs are not credited)")
+                        executed_frac=per_kernel[dom].get("tflops_executed", per_kernel[dom]["tflops"]) / P["tf_sustained"],
+                        note="credited flops (SURVEY §8d): 2*B*N*D forward, 4*B*N*D backward (dQ and dE); each gradient pass "
+                             "recomputes the logits on the tensor cores, which is executed but not credited")
     else:
         roofline = dict(bound="hbm", kernel=dom, achieved=per_kernel[dom]["gbs"], peak=P["hbm"], unit="GB/s",
-                        frac=per_kernel[dom]["gbs"] / P["hbm"], traffic=ncu_traffic(args.workload, dom),
+                        frac=per_kernel[dom]["gbs"] / P["hbm"], traffic=ncu_traffic(wname, dom),
                         peak_source=P["src"],
                         algorithmic_bytes_per_launch=alg[dom], avg_launch_ms=per_kernel[dom]["avg_ms"],
                         note="events bracket the C-ABI call on the launching stream (includes its dLambda/dh0 reduction "
-                             "launch); working set is L2-resident at this shape, see DESIGN.md")
+                             "launch)" + ("" if big else "; working set is L2-resident at this shape, see DESIGN.md"))
 
-    base, _ = (cpu_train_baseline(w, steps=3 if big else 6, warmup=1, sample_B=args.cpu_sample or (16 if big else 1024))
+    sweep = vs_triton = None
+    if north and world == 1:
+        import gc
+        del opt
+        if sit is not None:
+            sit._grad = None
+        gc.collect()
+        torch.cuda.empty_cache()
+        from bench_legs import sweep_leg, triton_leg
+        sweep = sweep_leg(P["hbm"])
+        vs_triton = triton_leg()
+    base, _ = (cpu_train_baseline(w, steps=2 if big else 6, warmup=1, sample_B=args.cpu_sample or (32 if big else 1024))
                if not args.no_cpu and world == 1 else (None, 0))   # cpu_baseline: rank 0 at N = 1 only
+    par = (f"dp{world} layers + item table row-sharded x{world} (fp32 master + Adam state on the owner, replicated bf16 "
+           f"copy all-gathered per step; CE dE owner-local, dQ reduce-scatter, embedding rows all-gather + owner scatter)"
+           if sit is not None and world > 1 else (f"dp{world}" if world > 1 else "single"))
     line = dict(metric="bdlru_fwd_bwd_seq_tokens_per_s", value=value, unit="seq-tokens/s", n_gpus=world,
-                steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=ms_per_step, higher_is_better=True,
-                scaling="weak", vs_baseline=None, dtype="bf16" if amp else "f32", data="synthetic",
-                config=dict(workload=f"{args.workload}: RecBLR n_items={w['n_items']} L={L} D={D} C={C} "
+                steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=ms_per_step, ms_median=med_ms, ms_min=min_ms,
+                higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16" if amp else "f32", data="synthetic",
+                config=dict(workload=f"{wname}: RecBLR n_items={w['n_items']} L={L} D={D} C={C} "
                                      f"layers={w['layers']} batch {B}/GPU, train step = zero_grad + calculate_loss "
                                      f"(CE over all items) + backward + Adam",
-                            l2="flushed between steps (256 MB write); per-step working set < L2",
-                            parallelism=f"dp{world}" if world > 1 else "single",
-                            ce_impl=model.ce_impl, scan_state="fp32",
+                            l2="flushed between steps (256 MB write)" + ("" if big else "; per-step working set < L2"),
+                            parallelism=par, ce_impl="sharded-table" if sit is not None else model.ce_impl,
+                            scan_state="fp32", table="fp32 master + bf16 compute copy" if sit is not None else "fp32",
                             launch="CUDA graph replay of the whole step" if graphed is not None else "eager"),
                 e2e=dict(value=world * B * L * args.steps / e2e_s, unit="seq-tokens/s", h2d_bytes_per_step=h2d,
                          d2h_bytes_per_step=4, ms_per_step=e2e_s / args.steps * 1e3),
                 gpu_launches=launches, clocks=clocks, roofline=roofline, kernels=per_kernel, fullsort=fullsort,
-                cpu_baseline=base)
+                parity_check=(dict(status="ok", **parity, **(fullsort or {}).get("parity_check", {}))
+                              if parity is not None else None),
+                sweep=sweep, vs_triton=vs_triton, cpu_baseline=base, **bench_header())
     print(json.dumps(line), flush=True)
     del graphed
     finish_distributed(world)
 
 
+def model_fullsort_leg(model, w, dev, amp, steps):
+    """Small-catalog workloads: users/s of model forward + fused scoring + top-10 at the eval batch (rank 0)."""
+    from datamining_recblr_b200 import ops
+    from datamining_recblr_b200.timing import flush_l2
+    model.eval()
+    EB, L, D = w["eval_B"], w["L"], w["D"]
+    eb = tuple(t.to(dev) for t in synthetic_batch(EB, L, w["n_items"], seed=7))
+    inter = {"item_id_list": eb[0], "item_length": eb[1], "item_id": eb[2]}
+
+    def score():
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
+            return model.full_sort_topk(inter, 10)
+    assert ops.fullsort_supported(D)
+    for _ in range(3):
+        score()
+    ts = []
+    for _ in range(max(steps, 5)):
+        flush_l2(dev)
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        score()
+        e.record()
+        e.synchronize()
+        ts.append(s.elapsed_time(e))
+    model.train()
+    return dict(metric="fullsort_scored_users_per_s", value=EB / (statistics.median(ts) * 1e-3), unit="users/s",
+                users=EB, n_items=w["n_items"], k=10, ms=statistics.median(ts), ms_min=min(ts), fused_topk=True,
+                includes="model forward + fused scoring + top-10")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=0, help="timed steps (default: 200 training / 50 scoring)")
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=0, help="timed steps (default: 10 large-catalog / 200 small / 50 scoring)")
+    ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="beauty", choices=list(WORKLOADS) + list(SCORE_WORKLOADS))
+    ap.add_argument("--workload", default="north_star", choices=["north_star"] + list(WORKLOADS) + list(SCORE_WORKLOADS))
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
     ap.add_argument("--cpu-sample", type=int, default=0, help="sequences (train) / users (scoring) per CPU step")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-graph", action="store_true", help="run the training step eagerly instead of as a CUDA graph")
     args = ap.parse_args()
+    train_name = "strain10m" if args.workload == "north_star" else args.workload
     if args.steps <= 0:
-        big_w = args.workload in WORKLOADS and WORKLOADS[args.workload].get("big")
-        args.steps = (5 if args.impl == "reference" else (20 if big_w else (200 if args.workload in WORKLOADS else 50)))
+        big_w = train_name in WORKLOADS and WORKLOADS[train_name].get("big")
+        args.steps = (3 if args.impl == "reference" and big_w else 5 if args.impl == "reference"
+                      else (10 if big_w else (200 if train_name in WORKLOADS else 50)))
     if args.impl == "reference":
         return run_reference(args)
-    if args.workload in WORKLOADS:
+    refuse_tuning_environment()
+    if train_name in WORKLOADS:
         return run_train(args)
     from bench_score import run_score  # noqa: WPS433  (kept separate: needs the tcgen05 kernels)
     return run_score(args)

@@ -37,3 +37,38 @@ def time_cuda(fn, warmup=3, iters=10, flush=True):
 
 def summarize(times):
     return {"median_ms": statistics.median(times), "min_ms": min(times), "n": len(times)}
+
+
+L2_BYTES = 126 << 20
+
+
+def time_graph(make_set, run, set_bytes, iters=7):
+    """HBM-resident timing of one op without flushes inside the timed region: the op is captured into a CUDA graph that
+    runs it on R rotating input sets whose total footprint exceeds 2x the L2 (every instance reads from HBM), and the
+    replay is bracketed by CUDA events — host launch latency is not in the number.  make_set() -> one set of inputs;
+    run(set) runs the op (fwd, or fwd+bwd).  Returns (median ms per op instance, min ms, R)."""
+    R = max(2, min(48, -(-2 * L2_BYTES // max(set_bytes, 1))))
+    sets = [make_set() for _ in range(R)]
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for s in sets[:2]:
+            run(s)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for s in sets:
+            run(s)
+    g.replay()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        g.replay()
+        b.record()
+        b.synchronize()
+        ts.append(a.elapsed_time(b) / R)
+    del g
+    return statistics.median(ts), min(ts), R

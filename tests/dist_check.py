@@ -96,8 +96,8 @@ def main():
         assert abs(float(l_one) - float(l_shd)) <= 2e-3 * abs(float(l_one)), (step, float(l_one), float(l_shd))
         g1 = one.item_embedding.weight.grad[sit.lo:sit.hi]
         g2 = sit.master.grad[:sit.n_local]
-        den = one.item_embedding.weight.grad.abs().max()
-        assert (g1 - g2).abs().max() <= 3e-2 * den, ("table grad", step, float((g1 - g2).abs().max()), float(den))
+        den_t = one.item_embedding.weight.grad.abs().max()
+        assert (g1 - g2).abs().max() <= 3e-2 * den_t, ("table grad", step, float((g1 - g2).abs().max()), float(den_t))
         d1 = {n: p.grad for n, p in one.named_parameters() if n != "item_embedding.weight"}
         d2 = {n: p.grad for n, p in shd.named_parameters() if n != "item_embedding.weight"}
         for n in d1:
@@ -107,7 +107,7 @@ def main():
         opt2.step()            # post-hook: refresh of the replicated bf16 copy (cast + in-place all-gather)
         with torch.no_grad():  # keep the single-process table bf16-representable like the sharded copy
             full_w = sit.full_weight()
-            assert (full_w - one.item_embedding.weight).abs().max() <= 3e-2 * 0.5 * float(den) + 1e-3
+            assert (full_w - one.item_embedding.weight).abs().max() <= 0.5 * 3e-2 * float(den_t) + 1e-6
             one.item_embedding.weight.copy_(full_w.to(torch.bfloat16).float())
             sit.master[:sit.n_local].copy_(one.item_embedding.weight[sit.lo:sit.hi])
             sit.refresh()

@@ -31,31 +31,9 @@ def peak_gbs():
 
 
 def time_graph(make_set, run, set_bytes, iters=7):
-    """make_set() -> one set of inputs; run(set) runs the op (fwd, or fwd+bwd).  Returns median ms per op instance."""
-    R = max(2, min(48, -(-2 * L2_BYTES // max(set_bytes, 1))))
-    sets = [make_set() for _ in range(R)]
-    side = torch.cuda.Stream()
-    side.wait_stream(torch.cuda.current_stream())
-    with torch.cuda.stream(side):
-        for s in sets[:2]:
-            run(s)
-    torch.cuda.current_stream().wait_stream(side)
-    torch.cuda.synchronize()
-    g = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(g):
-        for s in sets:
-            run(s)
-    g.replay()
-    torch.cuda.synchronize()
-    ts = []
-    for _ in range(iters):
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        g.replay()
-        b.record()
-        b.synchronize()
-        ts.append(a.elapsed_time(b) / R)
-    return statistics.median(ts), R
+    from datamining_recblr_b200.timing import time_graph as tg
+    med, _, R = tg(make_set, run, set_bytes, iters)
+    return med, R
 
 
 def main():
