@@ -538,7 +538,7 @@ def run_train(args):
                 e2e=dict(value=world * B * L * args.steps / e2e_s, unit="seq-tokens/s", h2d_bytes_per_step=h2d,
                          d2h_bytes_per_step=4, ms_per_step=e2e_s / args.steps * 1e3),
                 gpu_launches=launches, clocks=clocks, roofline=roofline, kernels=per_kernel, fullsort=fullsort,
-                parity_check=(dict(status="ok", **parity, **(fullsort or {}).get("parity_check", {}))
+                parity_check=({**(fullsort or {}).get("parity_check", {}), **parity, "status": "ok"}
                               if parity is not None else None),
                 sweep=sweep, vs_triton=vs_triton, cpu_baseline=base, **bench_header())
     print(json.dumps(line), flush=True)

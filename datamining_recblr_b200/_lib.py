@@ -62,6 +62,10 @@ SIGNATURES = {
     "bdlru_topk_merge_strided": (_i, [_p, _p, _i64, _i, _i, _i64, _i64, _p, _p, _p]),
     "bdlru_fullsort_ce_workspace_bytes": (_sz, [_i64, _i64, _i]),
     "bdlru_fullsort_ce_fwd": (_i, [_p, _p, _p, _i64, _i64, _i, _i64, _p, _p, _p, _p, _sz, _p]),
+    "bdlru_fullsort_rowmax_workspace_bytes": (_sz, [_i64, _i64, _i]),
+    "bdlru_fullsort_rowmax": (_i, [_p, _p, _i64, _i64, _i, _i, _p, _p, _sz, _p]),
+    "bdlru_fullsort_ce_fwd_dq_workspace_bytes": (_sz, [_i64, _i64, _i]),
+    "bdlru_fullsort_ce_fwd_dq": (_i, [_p, _p, _p, _i64, _i64, _i, _p, _p, _p, _sz, _p]),
     "bdlru_fullsort_ce_bwd": (_i, [_p, _p, _p, _p, _f, _p, _i64, _i64, _i, _i64, _p, _p, _p, _sz, _p]),
 }
 

@@ -42,7 +42,7 @@ constexpr int kMaxStages = 8;
 #endif
 constexpr uint32_t kPolyMaskFwd = BDLRU_CE_FWD_POLY_MASK;
 
-enum { MODE_TOPK = 0, MODE_CE = 1 };
+enum { MODE_TOPK = 0, MODE_CE = 1, MODE_MAX = 2 };  // MAX: row maxima only (the reference of the fused CE forward)
 
 struct FsParams {
   int D, k, stages, splits, n_ug;
@@ -52,6 +52,7 @@ struct FsParams {
   long n_users, n_rows;       // rows of Q, rows of this E shard
   long id_offset, mask_local; // global id of E row 0; LOCAL row to exclude (-1: none)
   long tiles_total;
+  int tile_stride;            // MODE_MAX: walk every tile_stride-th tile only (sampled maximum); 1 elsewhere
   // top-k partials [n_users][splits][k]
   float* part_scores;
   int* part_ids;
@@ -100,7 +101,7 @@ static bool fs_plan(long n_users, long n_rows, int D, int k, int mode, FsPlan* p
   long want = (long)sm_count() / pl->n_ug;
   if (want < 1) want = 1;
   pl->splits = (int)(want < max_s ? want : max_s);
-  if (mode == MODE_CE) {
+  if (mode == MODE_CE || mode == MODE_MAX) {
     // The softmax statistics have no per-stream cost that grows with the split count (a (max, sum) pair per split), so
     // the CE grid need not be one wave: with 32 user groups one wave is 128 CTAs on 148 SMs (ncu: SMs active 85 % of
     // the time).  Take more, shorter streams (>= 32 tiles each) when that fills whole waves better.
@@ -193,6 +194,7 @@ template <int UB, int MODE, int K, int NT, int NSTG, int ES>
 __global__ void __launch_bounds__(96 + 128 * UB * ES, 1)
 fullsort_kernel(const __grid_constant__ CUtensorMap tmE, const FsParams p) {
   static_assert(ES == 1 || MODE == MODE_CE, "a second epilogue set exists for the CE statistics only");
+  static_assert(MODE != MODE_MAX || K == 1, "MODE_MAX keeps no list");
   constexpr int NSETS = ES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -255,7 +257,7 @@ fullsort_kernel(const __grid_constant__ CUtensorMap tmE, const FsParams p) {
         tc::mbar_arrive_expect_tx(&e_full[s], (uint32_t)n_slab * kSlabB);
         for (int sl = 0; sl < n_slab; ++sl)
           tc::tma_load_2d(sE + (size_t)(s * n_slab + sl) * kSlabB, &tmE, &e_full[s], sl * 64,
-                          (int)((t_begin + it) * NT));
+                          (int)((t_begin + it) * p.tile_stride * NT));
         }
       }
       __syncwarp();
@@ -366,7 +368,7 @@ fullsort_kernel(const __grid_constant__ CUtensorMap tmE, const FsParams p) {
     for (int it = (ES == 1 ? 0 : eset); it < n_iter; it += NSETS) {
       const int b = it % NSTG;
       const uint32_t bph = (uint32_t)(it / NSTG) & 1u;
-      const long base = (t_begin + it) * NT;  // local row index of the tile's first item
+      const long base = (t_begin + it) * p.tile_stride * NT;  // local row index of the tile's first item
       const bool special = (base + NT > p.n_rows) || (p.mask_local >= base && p.mask_local < base + NT);
       const long long e0c = CLK ? FS_CLOCK() : 0;
       tc::mbar_wait(&acc_full[b], bph);
@@ -437,6 +439,8 @@ fullsort_kernel(const __grid_constant__ CUtensorMap tmE, const FsParams p) {
             }
             if (share && ls[K - 1] > kth_before) atomicMax(p.shared_thr + user, thr_encode(ls[K - 1]));
           }
+        } else if (MODE == MODE_MAX) {
+          run_m = fmaxf(run_m, mt);
         } else {
           if (mt > run_m) {  // rescale the running sum to the new maximum (mt is finite here)
             run_s *= ex2_ftz((run_m - mt) * kLog2e);
@@ -483,7 +487,7 @@ fullsort_kernel(const __grid_constant__ CUtensorMap tmE, const FsParams p) {
           }
       } else {
         p.part_max[(size_t)user * p.ce_parts + split * NSETS + eset] = run_m;
-        p.part_sum[(size_t)user * p.ce_parts + split * NSETS + eset] = run_s;
+        if (MODE == MODE_CE) p.part_sum[(size_t)user * p.ce_parts + split * NSETS + eset] = run_s;
       }
     }
   }
@@ -561,6 +565,14 @@ __global__ void ce_merge_kernel(const float* __restrict__ pm, const float* __res
   row_sum[u] = s;
 }
 
+__global__ void max_merge_kernel(const float* __restrict__ pm, long n_users, int splits, float* __restrict__ row_max) {
+  const long u = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= n_users) return;
+  float m = -INFINITY;
+  for (int j = 0; j < splits; ++j) m = fmaxf(m, pm[u * splits + j]);
+  row_max[u] = m;
+}
+
 // ----------------------------------------------------------------------------- host side
 static int fs_debug() {
   static const int v = tuning_env("BDLRU_FS_DEBUG");
@@ -604,6 +616,7 @@ template <int MODE>
 static int fs_launch(const FsPlan& pl, const CUtensorMap& me, const FsParams& p, cudaStream_t st) {
   if (MODE == MODE_CE)
     return ce_sets() == 2 ? fs_launch_k<MODE_CE, 1, 2>(pl, me, p, st) : fs_launch_k<MODE_CE, 1, 1>(pl, me, p, st);
+  if (MODE == MODE_MAX) return fs_launch_k<MODE_MAX, 1, 1>(pl, me, p, st);
   if (p.k <= 10) return fs_launch_k<MODE_TOPK, 10, 1>(pl, me, p, st);
   if (p.k <= 16) return fs_launch_k<MODE_TOPK, 16, 1>(pl, me, p, st);
   if (p.k <= 20) return fs_launch_k<MODE_TOPK, 20, 1>(pl, me, p, st);
@@ -644,6 +657,7 @@ extern "C" BDLRU_API int bdlru_fullsort_topk(const void* Q, const void* E, int64
   p.n_users = n_users; p.n_rows = n_rows; p.id_offset = id_offset;
   p.mask_local = (mask_id >= id_offset && mask_id < id_offset + n_rows) ? mask_id - id_offset : -1;
   p.tiles_total = pl.tiles_total;
+  p.tile_stride = 1;
   p.part_scores = reinterpret_cast<float*>(workspace);
   p.part_ids = reinterpret_cast<int*>(p.part_scores + (size_t)n_users * pl.splits * k);
   p.shared_thr = nullptr;
@@ -719,6 +733,7 @@ extern "C" BDLRU_API int bdlru_fullsort_ce_fwd(const void* Q, const void* E, con
   p.D = D; p.k = 1; p.stages = pl.stages; p.splits = pl.splits; p.n_ug = pl.n_ug;
   p.n_users = n_users; p.n_rows = n_rows; p.id_offset = id_offset; p.mask_local = -1;
   p.tiles_total = pl.tiles_total;
+  p.tile_stride = 1;
   p.ce_parts = parts;
   p.part_max = reinterpret_cast<float*>(workspace);
   p.part_sum = p.part_max + (size_t)n_users * parts;
@@ -727,6 +742,52 @@ extern "C" BDLRU_API int bdlru_fullsort_ce_fwd(const void* Q, const void* E, con
   if ((rc = fs_launch<MODE_CE>(pl, me, p, st))) return rc;
   ce_merge_kernel<<<(unsigned)((n_users + 255) / 256), 256, 0, st>>>(p.part_max, p.part_sum, n_users, parts,
                                                                      row_max, row_sumexp);
+  BDLRU_LAUNCHED();
+  return BDLRU_OK;
+}
+
+// Row maxima of the logits Q E^T over this shard (no exponentials: tensor-bound), or over every tile_stride-th 96-item
+// tile only — a SAMPLED maximum, good enough as the softmax reference of bdlru_fullsort_ce_fwd_dq (any reference within
+// ~80 of the true maximum gives the same result; see the header).
+extern "C" BDLRU_API size_t bdlru_fullsort_rowmax_workspace_bytes(int64_t n_users, int64_t n_rows, int D) {
+  FsPlan pl;
+  if (D % 64 != 0 || D < 64 || D > 256 || !fs_plan(n_users, n_rows, D, 1, MODE_MAX, &pl)) return 0;
+  return (size_t)n_users * pl.splits * 4;
+}
+
+extern "C" BDLRU_API int bdlru_fullsort_rowmax(const void* Q, const void* E, int64_t n_users, int64_t n_rows, int D,
+                                               int tile_stride, float* row_max, void* workspace,
+                                               size_t workspace_bytes, void* stream) {
+  int rc = fs_check(Q, E, n_users, n_rows, D);
+  if (rc) return rc;
+  BDLRU_REQUIRE(row_max, "fullsort_rowmax: null output");
+  BDLRU_REQUIRE(tile_stride >= 1, "fullsort_rowmax: tile_stride=%d must be >= 1", tile_stride);
+  FsPlan pl;
+  BDLRU_REQUIRE(fs_plan(n_users, n_rows, D, 1, MODE_MAX, &pl), "fullsort_rowmax: no tiling fits shared memory (D=%d)", D);
+  const long tiles_eff = (pl.tiles_total + tile_stride - 1) / tile_stride;
+  // re-plan the splits for the tiles actually walked (same workspace bound: splits never grow)
+  FsPlan pe = pl;
+  if (tile_stride > 1) {
+    long max_s = tiles_eff / 4 > 0 ? tiles_eff / 4 : 1;
+    if (pe.splits > max_s) pe.splits = (int)max_s;
+  }
+  const size_t need = (size_t)n_users * pe.splits * 4;
+  BDLRU_REQUIRE(workspace && workspace_bytes >= need, "fullsort_rowmax: workspace %zu < %zu bytes", workspace_bytes, need);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  CUtensorMap me;
+  if ((rc = make_rows_map(&me, E, n_rows, D, pe.NT))) return rc;
+  FsParams p = {};
+  p.Q = Q;
+  p.dbg = fs_debug();
+  p.D = D; p.k = 1; p.stages = pe.stages; p.splits = pe.splits; p.n_ug = pe.n_ug;
+  p.n_users = n_users; p.n_rows = n_rows; p.id_offset = 0; p.mask_local = -1;
+  p.tiles_total = tiles_eff;
+  p.tile_stride = tile_stride;
+  p.ce_parts = pe.splits;
+  p.part_max = reinterpret_cast<float*>(workspace);
+  p.part_sum = nullptr;
+  if ((rc = fs_launch<MODE_MAX>(pe, me, p, st))) return rc;
+  max_merge_kernel<<<(unsigned)((n_users + 255) / 256), 256, 0, st>>>(p.part_max, n_users, pe.splits, row_max);
   BDLRU_LAUNCHED();
   return BDLRU_OK;
 }

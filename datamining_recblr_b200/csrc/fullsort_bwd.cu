@@ -3,7 +3,13 @@
 //
 //   P = exp(Q E^T - lse) - onehot(pos),   dQ = scale * P E,   dE = scale * P^T Q.
 //
-// One kernel template serves both gradients:  "X rows against a stream of Y tiles"
+// A third instantiation (MODE_FWD) is the FUSED FORWARD of the training step: with a per-user reference m_b (the row maximum,
+// or any value within ~80 of it: softmax is shift invariant and bf16 / fp32 keep their relative precision over that range)
+// it produces in ONE pass over the table both the softmax denominator s_b = sum_j exp(l_bj - m_b) and the unnormalised
+// A_b = sum_j exp(l_bj - m_b) E_j, from which  lse_b = m_b + log s_b  and  dQ_b = scale * (A_b / s_b - E_pos_b)  follow
+// without a separate dQ pass: one exponential pass over the [users, items] logits instead of two.
+//
+// One kernel template serves all of them:  "X rows against a stream of Y tiles"
 //   dX[128 rows, D] = sum over Y tiles  P_tile[128, NT] * Y_tile[NT, D],   P_tile from S = X Y_tile^T.
 //   dQ: X = Q (rows = users), Y = E (cols = items), softmax statistics per ROW   (TRANSPOSED = false)
 //   dE: X = E (rows = items), Y = Q (cols = users), softmax statistics per COLUMN (TRANSPOSED = true)
@@ -52,7 +58,8 @@ struct BwdParams {
   long n_x, n_y;        // rows of X, rows of Y (columns of S)
   int D, stages, splits;
   long row_blocks, tiles_total;
-  const float* lse;     // [n_users]
+  const float* lse;     // [n_users] global logsumexp (MODE_FWD: the per-user reference m_b)
+  float* sum_parts;     // MODE_FWD: [splits * NSTG][n_x] partial sums of exp(l - m) (one per column split and softmax group)
   const int64_t* pos;   // [n_users] global item ids
   long n_users;
   long id_offset;       // global id of item row 0 of this shard
@@ -62,9 +69,13 @@ struct BwdParams {
   float* out;           // [splits][n_x][D] fp32 (splits == 1: the final gradient)
 };
 
-template <bool TRANSPOSED, int NT, int NSTG>
+enum { MODE_DQ = 0, MODE_DE = 1, MODE_FWD = 2 };
+
+template <int MODE, int NT, int NSTG>
 __global__ void __launch_bounds__(96 + 128 * NSTG, 1)
 ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const BwdParams p) {
+  constexpr bool TRANSPOSED = MODE == MODE_DE;
+  constexpr bool FWD = MODE == MODE_FWD;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -245,7 +256,7 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const BwdParams p) {
       if (!TRANSPOSED) {
         if (xrow < p.n_x) {
           row_lse2 = p.lse[xrow] * kLog2e;
-          row_pos = p.pos[xrow] - p.id_offset;
+          if (!FWD) row_pos = p.pos[xrow] - p.id_offset;
         }
       } else {
         row_pos = xrow;
@@ -253,6 +264,7 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const BwdParams p) {
       float pre_lse[NCH];
       int pre_pos[NCH];
       bool pre_valid = false;
+      float rsum[2] = {0.f, 0.f};   // MODE_FWD: this thread's share of sum_j exp(l - m) (two chains for ILP)
       for (long t = t0; t < t1; ++t, ++g) {
         const int b = (int)(g % NSTG);
         if (b != grp) continue;
@@ -331,6 +343,10 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const BwdParams p) {
                   if (CHECK && cbase + col >= p.n_y) pr[u] = 0.f;
                 }
               }
+              if (FWD) {
+                rsum[0] += pr[0];
+                rsum[1] += pr[1];
+              }
               const __nv_bfloat162 h = __floats2bfloat162_rn(pr[0], pr[1]);
               packed[(c * 32 + i) >> 1] = *reinterpret_cast<const uint32_t*>(&h);
             }
@@ -359,9 +375,10 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const BwdParams p) {
       tc::mbar_wait(dx_full, wi & 1u);
       tc::fence_after_sync();
       float* orow = p.out + ((size_t)split * p.n_x + xrow) * p.D;
-      const float out_scale = p.scale * (p.scale_dev ? __ldg(p.scale_dev) : 1.f);
+      const float out_scale = FWD ? 1.f : p.scale * (p.scale_dev ? __ldg(p.scale_dev) : 1.f);
       // dQ pass: "- onehot" = minus the positive item's row of Y, applied once, by the split that owns that column
-      const bool sub_pos = !TRANSPOSED && xrow < p.n_x && row_pos >= t0 * NT && row_pos < t1 * NT && row_pos < p.n_y;
+      if (FWD && xrow < p.n_x) p.sum_parts[((size_t)split * NG + grp) * p.n_x + xrow] = rsum[0] + rsum[1];
+      const bool sub_pos = MODE == MODE_DQ && xrow < p.n_x && row_pos >= t0 * NT && row_pos < t1 * NT && row_pos < p.n_y;
       const __nv_bfloat16* yrow = reinterpret_cast<const __nv_bfloat16*>(p.Y) + (sub_pos ? row_pos : 0) * p.D;
       for (int c = grp; c < (p.D >> 5); c += NG) {
         uint32_t acc[32];
@@ -441,7 +458,7 @@ static void bwd_plan(long n_x, long n_y, int D, BwdPlan* pl) {
   pl->smem = 1024 + (size_t)pl->stages * stage + 16 * pl->NT * 4 + 512;
 }
 
-template <bool TR>
+template <int TR>
 static int bwd_launch(const BwdPlan& pl, const CUtensorMap& my, const BwdParams& p, cudaStream_t st) {
 #define BWD_CASE(NTv, NSv)                                                                                      \
   if (pl.NT == NTv && pl.NSTG == NSv) {                                                                         \
@@ -458,7 +475,7 @@ static int bwd_launch(const BwdPlan& pl, const CUtensorMap& my, const BwdParams&
 }
 
 // one gradient: X rows against Y columns; result (scaled) in `grad` [n_x, D]
-template <bool TR>
+template <int TR>
 static int bwd_one(const void* X, long n_x, const void* Y, long n_y, int D, const float* lse, const int64_t* pos,
                    long n_users, long id_offset, float scale, const float* scale_dev, float* grad, float* scratch,
                    cudaStream_t st) {
@@ -481,6 +498,15 @@ static int bwd_one(const void* X, long n_x, const void* Y, long n_y, int D, cons
     BDLRU_LAUNCHED();
   }
   return BDLRU_OK;
+}
+
+// out[u] = sum_j parts[j][u]
+__global__ void rowsum_merge_kernel(const float* __restrict__ parts, long n, int n_parts, float* __restrict__ out) {
+  const long u = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= n) return;
+  float a = 0.f;
+  for (int j = 0; j < n_parts; ++j) a += parts[(size_t)j * n + u];
+  out[u] = a;
 }
 
 size_t ce_bwd_workspace_bytes(long n_users, long n_rows, int D) {
@@ -512,11 +538,56 @@ extern "C" BDLRU_API int bdlru_fullsort_ce_bwd(const void* Q, const void* E, con
                 workspace_bytes, need);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   int rc;
-  if (dQ && (rc = bwd_one<false>(Q, n_users, E, n_rows, D, lse, pos, n_users, id_offset, scale, scale_dev, dQ,
+  if (dQ && (rc = bwd_one<MODE_DQ>(Q, n_users, E, n_rows, D, lse, pos, n_users, id_offset, scale, scale_dev, dQ,
                                  reinterpret_cast<float*>(workspace), st)))
     return rc;
-  if (dE && (rc = bwd_one<true>(E, n_rows, Q, n_users, D, lse, pos, n_users, id_offset, scale, scale_dev, dE,
+  if (dE && (rc = bwd_one<MODE_DE>(E, n_rows, Q, n_users, D, lse, pos, n_users, id_offset, scale, scale_dev, dE,
                                 reinterpret_cast<float*>(workspace), st)))
     return rc;
+  return BDLRU_OK;
+}
+
+extern "C" BDLRU_API size_t bdlru_fullsort_ce_fwd_dq_workspace_bytes(int64_t n_users, int64_t n_rows, int D) {
+  if (D % 64 != 0 || D < 64 || D > 256 || n_users < 1 || n_rows < 1) return 0;
+  BwdPlan a;
+  bwd_plan(n_users, n_rows, D, &a);
+  const size_t acc = a.splits > 1 ? (size_t)a.splits * n_users * D * 4 : 0;
+  return acc + (size_t)a.splits * a.NSTG * n_users * 4;
+}
+
+extern "C" BDLRU_API int bdlru_fullsort_ce_fwd_dq(const void* Q, const void* E, const float* ref, int64_t n_users,
+                                                  int64_t n_rows, int D, float* acc, float* row_sumexp, void* workspace,
+                                                  size_t workspace_bytes, void* stream) {
+  BDLRU_REQUIRE(Q && E && ref && acc && row_sumexp, "fullsort_ce_fwd_dq: null pointer");
+  BDLRU_REQUIRE(n_users >= 1 && n_rows >= 1, "fullsort_ce_fwd_dq: bad sizes n_users=%ld n_rows=%ld", (long)n_users, (long)n_rows);
+  BDLRU_REQUIRE(D % 64 == 0 && D >= 64 && D <= 256, "fullsort_ce_fwd_dq: D=%d must be a multiple of 64 in [64, 256]", D);
+  BDLRU_REQUIRE(aligned(Q, 16) && aligned(E, 16) && aligned(acc, 16), "fullsort_ce_fwd_dq: Q/E/acc must be 16-byte aligned");
+  const size_t need = bdlru_fullsort_ce_fwd_dq_workspace_bytes(n_users, n_rows, D);
+  BDLRU_REQUIRE(workspace && workspace_bytes >= need, "fullsort_ce_fwd_dq: workspace %zu < %zu bytes", workspace_bytes, need);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  BwdPlan pl;
+  bwd_plan(n_users, n_rows, D, &pl);
+  CUtensorMap my;
+  int rc = make_rows_map(&my, E, n_rows, D, pl.NT);
+  if (rc) return rc;
+  const size_t acc_bytes = pl.splits > 1 ? (size_t)pl.splits * n_users * D * 4 : 0;
+  float* scratch = reinterpret_cast<float*>(workspace);
+  BwdParams p = {};
+  p.X = Q; p.Y = E; p.n_x = n_users; p.n_y = n_rows; p.D = D; p.stages = pl.stages; p.splits = pl.splits;
+  p.row_blocks = pl.row_blocks; p.tiles_total = pl.tiles;
+  p.lse = ref; p.pos = nullptr; p.n_users = n_users; p.id_offset = 0; p.scale = 1.f; p.scale_dev = nullptr;
+  p.dbg = tuning_env("BDLRU_FS_DEBUG");
+  p.sum_parts = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + acc_bytes);
+  p.out = pl.splits > 1 ? scratch : acc;
+  if ((rc = bwd_launch<MODE_FWD>(pl, my, p, st))) return rc;
+  if (pl.splits > 1) {
+    const long n4 = n_users * D / 4;
+    sum_partials_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float4*>(scratch), n4,
+                                                                      pl.splits, reinterpret_cast<float4*>(acc));
+    BDLRU_LAUNCHED();
+  }
+  rowsum_merge_kernel<<<(unsigned)((n_users + 255) / 256), 256, 0, st>>>(p.sum_parts, n_users, pl.splits * pl.NSTG,
+                                                                        row_sumexp);
+  BDLRU_LAUNCHED();
   return BDLRU_OK;
 }

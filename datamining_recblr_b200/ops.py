@@ -800,29 +800,96 @@ def fullsort_ce_grads(qb, eb, pos, lse, scale, id_offset=0, scale_dev=None, out_
     return dQ, dE
 
 
+# Softmax reference of the fused CE forward: row maximum over every CE_REFERENCE_STRIDE-th 96-item tile (1 = exact row
+# maximum over all items, a full tensor-core pass).  Any reference within ~80 of the true maximum gives the same loss and
+# gradients (shift invariance; bf16 / fp32 keep their relative precision), and a sampled maximum over >= 1/16 of a catalog
+# is within a few units of the true one; if it ever were not, exp would overflow to inf and the device-side assert below
+# fires — the result can be slow (exact pass) or loud, never silently wrong.
+CE_REFERENCE_STRIDE = 16
+
+
+def fullsort_rowmax(qb, eb, tile_stride=1):
+    """Row maxima [B] fp32 of qb @ eb^T on the tensor cores, no exponentials (tile_stride > 1: sampled, see above)."""
+    L.require_cuda(qb, eb)
+    B, D = qb.shape
+    N = eb.shape[0]
+    lib = L.load()
+    out = torch.empty(B, dtype=torch.float32, device=qb.device)
+    nws = lib.bdlru_fullsort_rowmax_workspace_bytes(B, N, D)
+    ws = _workspace(qb.device, nws)
+    L.check(lib.bdlru_fullsort_rowmax(L.ptr(qb), L.ptr(eb), B, N, D, int(max(1, tile_stride)), L.ptr(out), L.ptr(ws), nws,
+                                      L.stream_ptr(qb)))
+    return out
+
+
+def fullsort_ce_fwd_dq(qb, eb, ref):
+    """Fused forward of the training CE for bf16 qb [B, D], eb [rows, D] and a per-user reference ref [B] fp32:
+    (acc [B, D], s [B]) with s_b = sum_j exp(l_bj - ref_b), acc_b = sum_j exp(l_bj - ref_b) eb_j  — one exponential pass
+    yields both the softmax denominator and the unnormalised dQ (include/bdlru.h)."""
+    L.require_cuda(qb, eb, ref)
+    B, D = qb.shape
+    N = eb.shape[0]
+    lib = L.load()
+    acc = torch.empty((B, D), dtype=torch.float32, device=qb.device)
+    s = torch.empty(B, dtype=torch.float32, device=qb.device)
+    nws = lib.bdlru_fullsort_ce_fwd_dq_workspace_bytes(B, N, D)
+    ws = _workspace(qb.device, nws)
+    L.check(lib.bdlru_fullsort_ce_fwd_dq(L.ptr(qb), L.ptr(eb), L.ptr(ref.float().contiguous()), B, N, D, L.ptr(acc),
+                                         L.ptr(s), L.ptr(ws), nws, L.stream_ptr(qb)))
+    return acc, s
+
+
+def pos_logits(qb, eb, pos, id_offset=0):
+    """q_b . E[pos_b] for the positives whose row lives in this (shard of the) table, 0 elsewhere; also the gathered rows
+    (zeros for foreign positives).  bf16 x bf16 products are exact in fp32; only the summation order differs from the GEMM."""
+    loc = pos - id_offset
+    own = (loc >= 0) & (loc < eb.shape[0])
+    rows = eb[loc.clamp(0, eb.shape[0] - 1)].float() * own[:, None]
+    return (qb.float() * rows).sum(1), rows
+
+
 class _FullsortCE(torch.autograd.Function):
-    """mean_b(logsumexp_n(q_b . E_n) - q_b . E_pos_b) over ALL rows of E (RecBLR.py:99-103), logits never stored."""
+    """mean_b(logsumexp_n(q_b . E_n) - q_b . E_pos_b) over ALL rows of E (RecBLR.py:99-103), logits never stored.
+    When q needs a gradient the forward is the FUSED pass (reference maximum -> one exponential pass giving the softmax
+    denominator and the unnormalised dQ), and the backward only runs the dE pass; otherwise the statistics-only kernel."""
 
     @staticmethod
     def forward(ctx, q, table, pos, item_bias):
         qb, eb = _bf16_rows(q), _bf16_rows(table)
         if item_bias is not None:
             qb, eb = _augment_with_bias(qb, eb, item_bias)
-        m, s, pl = fullsort_ce_stats(qb, eb, pos)
-        lse = m + torch.log(s)
-        ctx.save_for_backward(qb, eb, pos, lse)
         ctx.meta = (q.dtype, table.dtype, q.shape[1], None if item_bias is None else item_bias.dtype)
+        ctx.fused = bool(ctx.needs_input_grad[0])
+        if ctx.fused:
+            ref = fullsort_rowmax(qb, eb, CE_REFERENCE_STRIDE)
+            acc, s = fullsort_ce_fwd_dq(qb, eb, ref)
+            torch._assert_async(torch.isfinite(s).all(), "fused CE: the sampled softmax reference is > 80 below a row "
+                                "maximum (exp overflow): set ops.CE_REFERENCE_STRIDE = 1")
+            lse = ref + torch.log(s)
+            pl, prow = pos_logits(qb, eb, pos)
+            ctx.save_for_backward(qb, eb, pos, lse, acc, s, prow)
+        else:
+            m, s, pl = fullsort_ce_stats(qb, eb, pos)
+            lse = m + torch.log(s)
+            ctx.save_for_backward(qb, eb, pos, lse)
         return (lse - pl).mean()
 
     @staticmethod
     def backward(ctx, grad_loss):
-        qb, eb, pos, lse = ctx.saved_tensors
         qd, ed, D, bd = ctx.meta
-        # dloss/dlogit = (softmax - onehot) / B, times the upstream scalar (read by the kernel on the device: no sync and
+        # dloss/dlogit = (softmax - onehot) / B, times the upstream scalar (read by the kernels on the device: no sync and
         # no extra pass over the [n_items, D] gradient)
-        dQ, dE = fullsort_ce_grads(qb, eb, pos, lse, 1.0 / qb.shape[0], scale_dev=grad_loss)
+        if ctx.fused:
+            qb, eb, pos, lse, acc, s, prow = ctx.saved_tensors
+            dQ = (acc / s[:, None] - prow) * (grad_loss.float() / qb.shape[0])
+            dE = None
+            if ctx.needs_input_grad[1] or ctx.needs_input_grad[3]:
+                _, dE = fullsort_ce_grads(qb, eb, pos, lse, 1.0 / qb.shape[0], scale_dev=grad_loss, want_dq=False)
+        else:
+            qb, eb, pos, lse = ctx.saved_tensors
+            dQ, dE = fullsort_ce_grads(qb, eb, pos, lse, 1.0 / qb.shape[0], scale_dev=grad_loss)
         if bd is None:
-            return dQ.to(qd), dE.to(ed), None, None
+            return dQ.to(qd), (dE.to(ed) if dE is not None else None), None, None
         # augmented operands: the bias gradient is the column of d(table') that multiplies q' = 1
         return dQ[:, :D].to(qd), dE[:, :D].to(ed), None, dE[:, D].to(bd)
 

@@ -185,9 +185,11 @@ class _TiedEmbedLN(torch.autograd.Function):
 
 
 class _TiedCE(torch.autograd.Function):
-    """Global-mean full-softmax CE of a data-parallel batch against the row-sharded table: all-gather the queries,
-    per-shard statistics, tiny all-reduces, and in the backward dE written STRAIGHT into the owner's gradient shard while
-    the dQ partials are reduce-scattered back to the users' ranks."""
+    """Global-mean full-softmax CE of a data-parallel batch against the row-sharded table.  Forward: all-gather the
+    queries; per-shard reference maximum -> all-reduce MAX; ONE fused exponential pass per shard giving its share of the
+    softmax denominator and of the unnormalised dQ (ops.fullsort_ce_fwd_dq); tiny all-reduce SUM.  Backward: the dQ shares
+    are normalised and reduce-scattered back to the users' ranks, and the dE pass writes STRAIGHT into the owner's
+    gradient shard."""
 
     @staticmethod
     def forward(ctx, q, pos, sit):
@@ -201,19 +203,30 @@ class _TiedCE(torch.autograd.Function):
             dist.all_gather_into_tensor(pos_all, pos, group=group)
         else:
             q_all, pos_all = qb, pos
-        m, s, pl = sit.k.ce_stats(q_all, sit.shard_bf16(), pos_all, sit.lo)
-        lse, pl = combine_ce_stats(m, s, pl, group)
+        shard = sit.shard_bf16()
+        ref = sit.k.ce_rowmax(q_all, shard)
+        if world > 1:
+            dist.all_reduce(ref, op=dist.ReduceOp.MAX, group=group)
+        acc, s = sit.k.ce_fwd_dq(q_all, shard, ref)
+        pl, prow = ops.pos_logits(q_all, shard, pos_all, sit.lo)
+        if world > 1:
+            packed = torch.stack([s, pl])
+            dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
+            s, pl = packed[0], packed[1]
+        sit.k.assert_finite(s)
+        lse = ref + torch.log(s)
         ctx.sit, ctx.q_dtype = sit, q.dtype
-        ctx.save_for_backward(q_all, pos_all, lse)
+        ctx.save_for_backward(q_all, pos_all, lse, acc, s, prow)
         return (lse - pl).mean()
 
     @staticmethod
     def backward(ctx, grad_loss):
         sit = ctx.sit
-        q_all, pos_all, lse = ctx.saved_tensors
-        de = sit.grad_buffer()                       # fp32 [rows_per, D]; rows [0, n_local) are OVERWRITTEN by the kernel
-        dq_part = sit.k.ce_grads(q_all, sit.shard_bf16(), pos_all, lse, 1.0 / q_all.shape[0], sit.lo, grad_loss,
-                                 de[:sit.n_local])
+        q_all, pos_all, lse, acc, s, prow = ctx.saved_tensors
+        scale = grad_loss.float() / q_all.shape[0]
+        dq_part = (acc / s[:, None] - prow) * scale   # this shard's share of dL/dq for ALL users of the global batch
+        de = sit.grad_buffer()                        # fp32 [rows_per, D]; rows [0, n_local) are OVERWRITTEN by the kernel
+        sit.k.ce_de(q_all, sit.shard_bf16(), pos_all, lse, 1.0 / q_all.shape[0], sit.lo, grad_loss, de[:sit.n_local])
         sit.master.grad = de
         sit._ce_written = True
         dq = _reduce_scatter_rows(dq_part, sit.group) if sit.world > 1 else dq_part
@@ -372,14 +385,22 @@ def _cuda_kernels():
             return dgamma, dbeta
 
         @staticmethod
-        def ce_stats(q_all, shard, pos_all, lo):
-            return ops.fullsort_ce_stats(q_all, shard, pos_all, id_offset=lo)
+        def ce_rowmax(q_all, shard):
+            return ops.fullsort_rowmax(q_all, shard, ops.CE_REFERENCE_STRIDE)
 
         @staticmethod
-        def ce_grads(q_all, shard, pos_all, lse, scale, lo, grad_loss, out_de):
-            dq, _ = ops.fullsort_ce_grads(q_all, shard, pos_all, lse, scale, id_offset=lo, scale_dev=grad_loss,
-                                          out_de=out_de)
-            return dq
+        def ce_fwd_dq(q_all, shard, ref):
+            return ops.fullsort_ce_fwd_dq(q_all, shard, ref)
+
+        @staticmethod
+        def assert_finite(s):
+            torch._assert_async(torch.isfinite(s).all(), "sharded CE: the sampled softmax reference is > 80 below a row "
+                                "maximum (exp overflow): set ops.CE_REFERENCE_STRIDE = 1")
+
+        @staticmethod
+        def ce_de(q_all, shard, pos_all, lse, scale, lo, grad_loss, out_de):
+            ops.fullsort_ce_grads(q_all, shard, pos_all, lse, scale, id_offset=lo, scale_dev=grad_loss, out_de=out_de,
+                                  want_dq=False)
 
         @staticmethod
         def scatter_rows(ids_all, rows_all, dst, lo, hi, padding_idx):

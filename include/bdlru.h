@@ -240,6 +240,24 @@ int bdlru_fullsort_ce_bwd(const void* Q, const void* E, const int64_t* pos, cons
                           const float* scale_dev, int64_t n_users, int64_t n_rows, int D, int64_t id_offset,
                           float* dQ, float* dE, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Fused FORWARD of the training step (one exponential pass over the logits instead of two): softmax is shift invariant,
+ * so with a per-user reference m_b
+ *     row_sumexp[b] = sum_j exp(l_bj - m_b),      acc[b, :] = sum_j exp(l_bj - m_b) * E[j, :]        (fp32, this shard)
+ * give  lse_b = m_b + log(sum over shards of row_sumexp)  and  dL/dq_b = scale * (sum over shards of acc / s_b - E[pos_b])
+ * — the dQ half of bdlru_fullsort_ce_bwd comes out of the forward, and the backward only needs the dE pass (dQ = NULL).
+ * m_b must lie within ~80 of the true row maximum (fp32 / bf16 keep their relative precision over that range; beyond it
+ * exp overflows to inf, which the caller detects in row_sumexp).  bdlru_fullsort_rowmax computes it on the tensor cores
+ * without exponentials: exactly (tile_stride = 1) or over every tile_stride-th 96-item tile (a sampled maximum).
+ * Multi-GPU: all-reduce MAX the reference before the fused pass so that every shard uses the same m_b.
+ * ------------------------------------------------------------------------------------------- */
+size_t bdlru_fullsort_rowmax_workspace_bytes(int64_t n_users, int64_t n_rows, int D);
+int bdlru_fullsort_rowmax(const void* Q, const void* E, int64_t n_users, int64_t n_rows, int D, int tile_stride,
+                          float* row_max, void* workspace, size_t workspace_bytes, void* stream);
+size_t bdlru_fullsort_ce_fwd_dq_workspace_bytes(int64_t n_users, int64_t n_rows, int D);
+int bdlru_fullsort_ce_fwd_dq(const void* Q, const void* E, const float* ref, int64_t n_users, int64_t n_rows, int D,
+                             float* acc, float* row_sumexp, void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

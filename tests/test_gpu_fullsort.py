@@ -352,3 +352,65 @@ def test_fused_ce_many_row_blocks(B, N, D):
     ref_ids = torch.sort(logits, dim=1, descending=True, stable=True).indices[:, :10]
     agree = (ids.long() == ref_ids).all(dim=1).double().mean()
     assert float(agree) >= 0.999     # fp32 vs float64 near-ties only
+
+
+@pytest.mark.parametrize("B,N,D", [(130, 5000, 128), (300, 3417, 64), (64, 777, 256), (2048, 40000, 128)])
+def test_rowmax_exact_and_sampled(B, N, D):
+    """bdlru_fullsort_rowmax: exact row maxima (tile_stride 1) == max of the float64 logits of the same bf16 operands;
+    with tile_stride s it is exactly the maximum over the sampled 96-item tiles (never above the true maximum)."""
+    from datamining_recblr_b200 import ops
+    rng = np.random.default_rng(N)
+    qb, eb = _bf(rng.normal(size=(B, D))).cuda(), _bf(rng.normal(size=(N, D)) * 0.3).cuda()
+    logits = qb.double() @ eb.double().T
+    m = ops.fullsort_rowmax(qb, eb, 1)
+    ref = logits.max(1).values
+    assert float((m.double() - ref).abs().max()) <= 1e-5 * float(ref.abs().max())
+    NT = 96 if D <= 128 else 64
+    for s in (2, 7):
+        ms = ops.fullsort_rowmax(qb, eb, s)
+        cols = torch.cat([torch.arange(t * NT, min((t + 1) * NT, N)) for t in range(0, -(-N // NT), s)]).cuda()
+        want = logits[:, cols].max(1).values
+        assert float((ms.double() - want).abs().max()) <= 1e-5 * float(ref.abs().max())
+        assert bool((ms.double() <= ref + 1e-5 * ref.abs().max()).all())
+
+
+@pytest.mark.parametrize("B,N,D", [(130, 5000, 128), (300, 3417, 64), (64, 777, 256), (1000, 30000, 128)])
+@pytest.mark.parametrize("shift", [0.0, -25.0, 10.0])
+def test_ce_fwd_dq_is_shift_invariant_and_matches_float64(B, N, D, shift):
+    """bdlru_fullsort_ce_fwd_dq with reference = row maximum + shift: lse = ref + log s and acc / s = softmax(l) E do not
+    depend on the reference (the property the sampled maximum relies on), and match float64 on the same bf16 operands."""
+    from datamining_recblr_b200 import ops
+    rng = np.random.default_rng(B + N)
+    qb, eb = _bf(rng.normal(size=(B, D)) * 1.5).cuda(), _bf(rng.normal(size=(N, D)) * 0.3).cuda()
+    logits = qb.double() @ eb.double().T
+    ref = (logits.max(1).values + shift).float()
+    acc, s = ops.fullsort_ce_fwd_dq(qb, eb, ref)
+    lse = ref.double() + torch.log(s.double())
+    lse_ref = torch.logsumexp(logits, dim=1)
+    assert float((lse - lse_ref).abs().max()) <= 1e-5 * float(lse_ref.abs().max())
+    pe = torch.softmax(logits, dim=1) @ eb.double()
+    got = acc.double() / s.double()[:, None]
+    assert float((got - pe).abs().max()) <= 1e-2 * float(pe.abs().max())     # P is rounded to bf16 for the second GEMM
+
+
+def test_fused_ce_paths_agree():
+    """q needs a gradient -> fused forward (+ dE-only backward); q frozen -> statistics kernel + full backward: same loss,
+    same table gradient; and the exact (stride 1) and sampled (stride 16) references give the same result."""
+    from datamining_recblr_b200 import ops
+    rng = np.random.default_rng(3)
+    B, N, D = 500, 20000, 128
+    qb, eb = _bf(rng.normal(size=(B, D)) * 1.5), _bf(rng.normal(size=(N, D)) * 0.3)
+    pos = torch.tensor(rng.integers(0, N, size=B)).cuda()
+    res = []
+    for q_grad, stride in ((True, 16), (True, 1), (False, 16)):
+        ops.CE_REFERENCE_STRIDE = stride
+        q = qb.float().cuda().requires_grad_(q_grad)
+        e = eb.float().cuda().requires_grad_(True)
+        loss = ops.fullsort_cross_entropy(q, e, pos)
+        (loss * 1.5).backward()
+        res.append((float(loss), e.grad.clone(), q.grad.clone() if q_grad else None))
+    ops.CE_REFERENCE_STRIDE = 16
+    for r in res[1:]:
+        assert abs(r[0] - res[0][0]) <= 1e-6 * abs(res[0][0])
+        assert float((r[1] - res[0][1]).abs().max()) <= 1e-5 * float(res[0][1].abs().max())
+    assert float((res[1][2] - res[0][2]).abs().max()) <= 1e-4 * float(res[0][2].abs().max())

@@ -47,16 +47,19 @@ def test_parallel_scan_matches_reference_triton_kernel(T, regime):
         assert rel_err(theirs, ref) <= TOL       # the reference kernel itself meets the bar it sets
 
 
-def _copy_layer_weights(dst, src):
-    dst.load_state_dict(src.state_dict())
-
-
 @pytest.mark.parametrize("T", [5, 50, 64, 200])
 def test_gated_recurrent_layer_matches_reference_on_gpu(T):
     """Our GatedRecurrentLayer (h0 instead of the left pad, fused conv / gate+scan / z-gate kernels) vs the reference's
-    (literal pad + Triton scan) with the same weights on the same input: output and every gradient."""
+    (literal pad + Triton scan) with the same weights on the same input: output and every gradient.
+
+    Ground truth = the reference module itself in float64 with a sequential scan.  Measured on B200 (profiles/r2_parity.md):
+    this repo's fp32 path is within ~1e-6..4e-6 of it everywhere, while the REFERENCE's own fp32 GPU path (cuDNN depthwise
+    conv + ~12 separate elementwise kernels + Triton scan) is 1e-4..3e-3 away in the gradients.  So the bars are: ours vs
+    float64 <= 1e-4 (north star), and ours vs reference <= the reference's own distance from float64 (x2) + 1e-4."""
+    import copy
     from datamining_recblr_b200.recblr import GatedRecurrentLayer
-    mod, _ = build_ref.load_gpu_reference()
+    from oracle.reference_loader import sequential_scan
+    mod, ps = build_ref.load_gpu_reference()
     torch.manual_seed(T)
     ref = mod.GatedRecurrentLayer(d_model=64, expansion_factor=2, kernel_size=4).cuda()
     with torch.no_grad():
@@ -66,27 +69,33 @@ def test_gated_recurrent_layer_matches_reference_on_gpu(T):
         ref.gates.bias.normal_(std=0.5)
         ref.conv1d.bias.normal_(std=0.5)
     ours = GatedRecurrentLayer(d_model=64, expansion_factor=2, kernel_size=4).cuda()
-    _copy_layer_weights(ours, ref)
+    ours.load_state_dict(ref.state_dict())
+    r64 = copy.deepcopy(ref).double()
     x = torch.randn(7, T, 64, device="cuda")
     gy = torch.randn(7, T, 64, device="cuda")
-    res = []
-    # the reference's F.conv1d fallback goes through cuDNN, whose default (torch.backends.cudnn.allow_tf32 = True) rounds
-    # the depthwise conv to TF32 (~1e-3): switch it to true fp32 for the comparison, as the fp32 contract implies
+    res = {}
     tf32 = torch.backends.cudnn.allow_tf32
-    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False     # the fp32 contract: no TF32 in the reference's cuDNN conv fallback
     try:
-        for m in (ours, ref):
-            xi = x.clone().requires_grad_(True)
+        for name, m, dt in (("ours", ours, torch.float32), ("ref", ref, torch.float32), ("f64", r64, torch.float64)):
+            mod.parallel_scan = sequential_scan if name == "f64" else ps.parallel_scan
+            xi = x.to(dt).clone().requires_grad_(True)
             y = m(xi)
-            y.backward(gy)
-            res.append((y.detach(), xi.grad, {n: p.grad.clone() for n, p in m.named_parameters()}))
-            m.zero_grad()
+            y.backward(gy.to(dt))
+            res[name] = {"y": y.detach().double(), "dx": xi.grad.double(),
+                         **{n: p.grad.double().clone() for n, p in m.named_parameters()}}
     finally:
         torch.backends.cudnn.allow_tf32 = tf32
-    assert rel_err(res[0][0], res[1][0].double().cpu().numpy()) <= TOL
-    assert rel_err(res[0][1], res[1][1].double().cpu().numpy()) <= TOL
-    for n, gr in res[1][2].items():
-        assert rel_err(res[0][2][n], gr.double().cpu().numpy()) <= 5e-4, n   # fp32 reductions over B*T in different orders
+        mod.parallel_scan = ps.parallel_scan
+    rel = lambda a, b: float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+    report = {}
+    for key, truth in res["f64"].items():
+        e_ours, e_ref, e_pair = rel(res["ours"][key], truth), rel(res["ref"][key], truth), rel(res["ours"][key], res["ref"][key])
+        report[key] = (e_ours, e_ref, e_pair)
+        assert e_ours <= TOL, (key, report)
+        assert e_pair <= 2 * e_ref + TOL, (key, report)
+    print("layer parity T=%d (ours vs f64, reference vs f64, ours vs reference):" % T,
+          {k: tuple(float(f"{x:.2g}") for x in v) for k, v in report.items()})
 
 
 def test_model_loss_and_scores_match_reference_on_gpu():

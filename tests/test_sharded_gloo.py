@@ -213,13 +213,22 @@ class _CpuTableKernels:
         return dg.float(), db.float()
 
     @staticmethod
-    def ce_stats(q_all, shard, pos_all, lo):
-        return _cpu_ce_stats(q_all, shard, pos_all, id_offset=lo)
+    def ce_rowmax(q_all, shard):
+        # a deliberately SLOPPY reference (true maximum minus 3): the result must not depend on it (shift invariance)
+        return ((q_all.double() @ shard.double().T).max(1).values - 3.0).float()
 
     @staticmethod
-    def ce_grads(q_all, shard, pos_all, lse, scale, lo, grad_loss, out_de):
-        dq, _ = _cpu_ce_grads(q_all, shard, pos_all, lse, scale, id_offset=lo, scale_dev=grad_loss, out_de=out_de)
-        return dq
+    def ce_fwd_dq(q_all, shard, ref):
+        p = torch.exp(q_all.double() @ shard.double().T - ref.double()[:, None])
+        return (p @ shard.double()).float(), p.sum(1).float()
+
+    @staticmethod
+    def assert_finite(s):
+        assert torch.isfinite(s).all()
+
+    @staticmethod
+    def ce_de(q_all, shard, pos_all, lse, scale, lo, grad_loss, out_de):
+        _cpu_ce_grads(q_all, shard, pos_all, lse, scale, id_offset=lo, scale_dev=grad_loss, out_de=out_de)
 
     @staticmethod
     def scatter_rows(ids_all, rows_all, dst, lo, hi, padding_idx):
