@@ -329,14 +329,21 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const BwdParams p) {
           auto chunk_math = [&](auto check_tag) {
             constexpr bool CHECK = decltype(check_tag)::value;
 #pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              float pr[2];
+            for (int i = 0; i < 32; i += 4) {
+              float pr[4];
+              // dE pass: the four columns' statistics in ONE 128-bit broadcast read (the per-element LDS was a quarter
+              // of this loop's issue slots)
+              float cl[4] = {0.f, 0.f, 0.f, 0.f};
+              if (TRANSPOSED) {
+                const float4 l4 = *reinterpret_cast<const float4*>(my_lse + c * 32 + i);
+                cl[0] = l4.x; cl[1] = l4.y; cl[2] = l4.z; cl[3] = l4.w;
+              }
 #pragma unroll
-              for (int u = 0; u < 2; ++u) {
+              for (int u = 0; u < 4; ++u) {
                 const int col = c * 32 + i + u;
                 const float sv = __uint_as_float(raw[i + u]);
                 if (TRANSPOSED) {
-                  pr[u] = ex2_mixed<TRANSPOSED ? kPolyMaskDE : kPolyMaskDQ, 3>(fmaf(sv, kLog2e, -my_lse[col]), i + u);
+                  pr[u] = ex2_mixed<TRANSPOSED ? kPolyMaskDE : kPolyMaskDQ, 3>(fmaf(sv, kLog2e, -cl[u]), i + u);
                   if (CHECK && my_pos[col] == (int)row_pos) pr[u] -= 1.f;
                 } else {
                   pr[u] = ex2_mixed<TRANSPOSED ? kPolyMaskDE : kPolyMaskDQ, 3>(fmaf(sv, kLog2e, -row_lse2), i + u);
@@ -344,11 +351,13 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const BwdParams p) {
                 }
               }
               if (FWD) {
-                rsum[0] += pr[0];
-                rsum[1] += pr[1];
+                rsum[0] += pr[0] + pr[2];
+                rsum[1] += pr[1] + pr[3];
               }
-              const __nv_bfloat162 h = __floats2bfloat162_rn(pr[0], pr[1]);
-              packed[(c * 32 + i) >> 1] = *reinterpret_cast<const uint32_t*>(&h);
+              const __nv_bfloat162 h0 = __floats2bfloat162_rn(pr[0], pr[1]);
+              const __nv_bfloat162 h1 = __floats2bfloat162_rn(pr[2], pr[3]);
+              packed[(c * 32 + i) >> 1] = *reinterpret_cast<const uint32_t*>(&h0);
+              packed[((c * 32 + i) >> 1) + 1] = *reinterpret_cast<const uint32_t*>(&h1);
             }
           };
           if (TRANSPOSED ? onehot_here : tail) chunk_math(std::true_type{});

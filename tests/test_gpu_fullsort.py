@@ -252,9 +252,11 @@ def test_sharded_ce_wrapper_single_rank_matches_fused_ce(with_bias):
         loss = fn(q, e, b)
         loss.backward()
         outs.append((loss.detach(), q.grad, e.grad, None if b is None else b.grad))
-    assert torch.equal(outs[0][0], outs[1][0])
+    # fullsort_cross_entropy takes the fused forward (dQ out of the forward pass), the sharded wrapper the statistics
+    # kernel + both gradient passes: same mathematics, different bf16 rounding points of P
+    assert abs(float(outs[0][0]) - float(outs[1][0])) <= 1e-6 * abs(float(outs[0][0]))
     for a, c in zip(outs[0][1:], outs[1][1:]):
-        assert (a is None and c is None) or torch.equal(a, c)
+        assert (a is None and c is None) or float((a - c).abs().max()) <= 1e-2 * float(a.abs().max())
 
 
 def test_item_bias_unsupported_width_raises():
@@ -413,4 +415,5 @@ def test_fused_ce_paths_agree():
     for r in res[1:]:
         assert abs(r[0] - res[0][0]) <= 1e-6 * abs(res[0][0])
         assert float((r[1] - res[0][1]).abs().max()) <= 1e-5 * float(res[0][1].abs().max())
-    assert float((res[1][2] - res[0][2]).abs().max()) <= 1e-4 * float(res[0][2].abs().max())
+    # dQ: P = exp(l - ref) is rounded to bf16 before the second GEMM, so a different reference moves the rounding points
+    assert float((res[1][2] - res[0][2]).abs().max()) <= 1e-2 * float(res[0][2].abs().max())

@@ -49,10 +49,19 @@ lsef = lse.float().contiguous()
 
 
 def run(dq, de):
-    L.check(lib.bdlru_fullsort_ce_bwd(L.ptr(q), L.ptr(e), L.ptr(pos), L.ptr(lsef), 1.0 / B, B, N, D, 0, L.ptr(dq), L.ptr(de),
-                                      L.ptr(ws), nws, st))
+    L.check(lib.bdlru_fullsort_ce_bwd(L.ptr(q), L.ptr(e), L.ptr(pos), L.ptr(lsef), 1.0 / B, None, B, N, D, 0, L.ptr(dq),
+                                      L.ptr(de), L.ptr(ws), nws, st))
 
 
 t_q = timeit(lambda: run(dQ, None))
 t_e = timeit(lambda: run(None, dE))
 print(f"  dQ pass {t_q:.3f} ms ({2 * fl / t_q / 1e9:.0f} TFLOP/s executed), dE pass {t_e:.3f} ms ({2 * fl / t_e / 1e9:.0f} TFLOP/s executed)")
+
+# fused forward of the training step: reference maximum (sampled / exact) + one exponential pass (denominator + dQ)
+for stride in (16, 1):
+    t_m = timeit(lambda: ops.fullsort_rowmax(q, e, stride))
+    print(f"  rowmax stride {stride}: {t_m:.3f} ms ({fl / stride / t_m / 1e9:.0f} TFLOP/s executed)")
+ref = ops.fullsort_rowmax(q, e, 16)
+t_fd = timeit(lambda: ops.fullsort_ce_fwd_dq(q, e, ref))
+print(f"  fused fwd+dQ pass {t_fd:.3f} ms ({2 * fl / t_fd / 1e9:.0f} TFLOP/s, all credited)")
+print(f"  training CE total: fused {t_fd + t_e:.3f} ms + reference  vs  stats fwd + dQ + dE {t_f + t_q + t_e:.3f} ms")
