@@ -262,7 +262,7 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const BwdParams p) {
         row_pos = xrow;
       }
       float pre_lse[NCH];
-      int pre_pos[NCH];
+      long pre_pos[NCH];
       bool pre_valid = false;
       float rsum[2] = {0.f, 0.f};   // MODE_FWD: this thread's share of sum_j exp(l - m) (two chains for ILP)
       for (long t = t0; t < t1; ++t, ++g) {
@@ -274,13 +274,16 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const BwdParams p) {
         if (TRANSPOSED) {
           // Column statistics of this tile (lse*log2e, local positive row) -> per-warp scratch.  The values were
           // prefetched into registers while the previous own tile was processed (first own tile: loaded here).
+          // (the prefetched values stay RAW in registers — lse unscaled, pos as loaded — and are converted only here, one
+          // tile later: converting at prefetch time made the very next instruction wait for the global load, ncu
+          // long-scoreboard stalls on the scaling FMUL)
           if (!pre_valid) {
 #pragma unroll
             for (int k = 0; k < NCH; ++k) {
               const long u = cbase + lane + 32 * k;
               const bool ok = u < p.n_users;
-              pre_lse[k] = ok ? p.lse[u] * kLog2e : INFINITY;
-              pre_pos[k] = ok ? (int)(p.pos[u] - p.id_offset) : -1;
+              pre_lse[k] = ok ? p.lse[u] : INFINITY;
+              pre_pos[k] = ok ? p.pos[u] : -1;
             }
           }
           __syncwarp();
@@ -288,9 +291,10 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const BwdParams p) {
           bool mine = false;
 #pragma unroll
           for (int k = 0; k < NCH; ++k) {
-            my_lse[lane + 32 * k] = pre_lse[k];
-            my_pos[lane + 32 * k] = pre_pos[k];
-            mine |= (pre_pos[k] >= row_lo && pre_pos[k] < row_lo + 32);
+            const int lp = pre_pos[k] < 0 ? -1 : (int)(pre_pos[k] - p.id_offset);
+            my_lse[lane + 32 * k] = pre_lse[k] * kLog2e;
+            my_pos[lane + 32 * k] = lp;
+            mine |= (lp >= row_lo && lp < row_lo + 32);
           }
           onehot_here = __any_sync(0xffffffffu, mine);  // rare: some column's positive item is one of this warp's rows
           __syncwarp();
@@ -302,8 +306,8 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const BwdParams p) {
             for (int k = 0; k < NCH; ++k) {
               const long u = nt * NT + lane + 32 * k;
               const bool ok = u < p.n_users;
-              pre_lse[k] = ok ? p.lse[u] * kLog2e : INFINITY;
-              pre_pos[k] = ok ? (int)(p.pos[u] - p.id_offset) : -1;
+              pre_lse[k] = ok ? p.lse[u] : INFINITY;
+              pre_pos[k] = ok ? p.pos[u] : -1;
             }
           }
         }

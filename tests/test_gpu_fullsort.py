@@ -414,6 +414,6 @@ def test_fused_ce_paths_agree():
     ops.CE_REFERENCE_STRIDE = 16
     for r in res[1:]:
         assert abs(r[0] - res[0][0]) <= 1e-6 * abs(res[0][0])
-        assert float((r[1] - res[0][1]).abs().max()) <= 1e-5 * float(res[0][1].abs().max())
+        assert float((r[1] - res[0][1]).abs().max()) <= 1e-3 * float(res[0][1].abs().max())   # bf16 rounding points of P
     # dQ: P = exp(l - ref) is rounded to bf16 before the second GEMM, so a different reference moves the rounding points
     assert float((res[1][2] - res[0][2]).abs().max()) <= 1e-2 * float(res[0][2].abs().max())
