@@ -269,7 +269,7 @@ def run_reference(args):
                 higher_is_better=True, scaling="weak", vs_baseline=None, data="synthetic", cpu_baseline=base,
                 e2e=dict(value=base["value"], unit=base["unit"], h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                 gpu_launches=0)
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------- our arm: training step
@@ -553,7 +553,7 @@ def run_train(args):
                 parity_check=({**(fullsort or {}).get("parity_check", {}), **parity, "status": "ok"}
                               if parity is not None else None),
                 sweep=sweep, vs_triton=vs_triton, cpu_baseline=base, **bench_header())
-    print(json.dumps(line), flush=True)
+    emit(line)
     del graphed
     finish_distributed(world)
 
@@ -588,6 +588,22 @@ def model_fullsort_leg(model, w, dev, amp, steps):
                 includes="model forward + fused scoring + top-10")
 
 
+def reserve_stdout():
+    """The contract is ONE JSON line on stdout: everything else that may write to file descriptor 1 during the run (NCCL's
+    version banner, library chatter) is sent to stderr; emit() writes the line to the real stdout.  The saved descriptor
+    lives on `sys` because this file is loaded twice (as __main__ and, from bench_score.py, as module `bench`)."""
+    if getattr(sys, "_bdlru_json_fd", None) is None:
+        sys.stdout.flush()
+        sys._bdlru_json_fd = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    fd = getattr(sys, "_bdlru_json_fd", None)
+    os.write(1 if fd is None else fd, (json.dumps(line) + "\n").encode())
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -600,6 +616,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-graph", action="store_true", help="run the training step eagerly instead of as a CUDA graph")
     args = ap.parse_args()
+    reserve_stdout()
     train_name = "strain10m" if args.workload == "north_star" else args.workload
     if args.steps <= 0:
         big_w = train_name in WORKLOADS and WORKLOADS[train_name].get("big")

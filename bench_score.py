@@ -151,8 +151,8 @@ def score_leg(E, lo, n_total, steps, warmup, k=10, B=4096, full_table=None, grap
 
 def run_score(args):
     import torch.distributed as dist
-    from bench import SCORE_WORKLOADS, ClockSampler, bench_header, cpu_score_baseline, dist_env, finish_distributed, \
-        ncu_traffic, peaks
+    from bench import SCORE_WORKLOADS, ClockSampler, bench_header, cpu_score_baseline, dist_env, emit, \
+        finish_distributed, ncu_traffic, peaks
 
     rank, world, local = dist_env()
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU path)"
@@ -195,5 +195,5 @@ def run_score(args):
                             if world > 1 else "single", launch=leg["launch"]),
                 e2e=leg["e2e"], gpu_launches=leg["gpu_launches"], clocks=clocks, roofline=roofline,
                 parity_check=leg["parity_check"], cpu_baseline=base, **bench_header())
-    print(json.dumps(line), flush=True)
+    emit(line)
     finish_distributed(world)
