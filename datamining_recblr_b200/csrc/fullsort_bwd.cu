@@ -39,6 +39,7 @@ namespace bdlru {
 
 constexpr int kRows = 128;
 constexpr int kBwdMaxStages = 6;
+constexpr int kBwdMaxAcc = 3;     // accumulator / P stages = softmax warp groups
 constexpr int kBwdSmem = 200 * 1024;
 // Which elements of each 32-column chunk take exp2 on the FMA pipe instead of the SFU (bit i = column i; common.cuh
 // ex2_mixed).  Overridable at build time for tuning (tools/ce_variants.py).  Measured at 8192 x 1 M x 128
@@ -51,6 +52,10 @@ constexpr int kBwdSmem = 200 * 1024;
 #define BDLRU_CE_DE_POLY_MASK 0u
 #endif
 constexpr uint32_t kPolyMaskDQ = BDLRU_CE_DQ_POLY_MASK, kPolyMaskDE = BDLRU_CE_DE_POLY_MASK;
+#ifndef BDLRU_CE_DE_THREE_GROUPS
+#define BDLRU_CE_DE_THREE_GROUPS 1
+#endif
+constexpr bool kDeThreeGroups = BDLRU_CE_DE_THREE_GROUPS != 0;
 
 struct BwdParams {
   const void* X;        // [n_x, D] bf16 rows owned by CTAs
@@ -84,16 +89,16 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const BwdParams p) {
   constexpr int NCH = NT / 32;
   constexpr int NG = NSTG;                 // softmax warp groups: group g owns accumulator / P stage g
   uint8_t* sY = smem;
-  float* col_lse = reinterpret_cast<float*>(sY + (size_t)p.stages * n_slab * kSlabB);  // [8 warps][NT]
-  int* col_pos = reinterpret_cast<int*>(col_lse + 8 * NT);                              // [8 warps][NT]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(col_pos + 8 * NT);
+  float* col_lse = reinterpret_cast<float*>(sY + (size_t)p.stages * n_slab * kSlabB);  // [4 * NSTG warps][NT]
+  int* col_pos = reinterpret_cast<int*>(col_lse + 4 * NSTG * NT);                       // [4 * NSTG warps][NT]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(col_pos + 4 * NSTG * NT);
   uint64_t* y_full = bars;
   uint64_t* y_empty = y_full + kBwdMaxStages;
   uint64_t* s_full = y_empty + kBwdMaxStages;
-  uint64_t* s_empty = s_full + 2;
-  uint64_t* p_full = s_empty + 2;
-  uint64_t* p_empty = p_full + 2;
-  uint64_t* x_full = p_empty + 2;
+  uint64_t* s_empty = s_full + kBwdMaxAcc;
+  uint64_t* p_full = s_empty + kBwdMaxAcc;
+  uint64_t* p_empty = p_full + kBwdMaxAcc;
+  uint64_t* x_full = p_empty + kBwdMaxAcc;
   uint64_t* dx_full = x_full + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dx_full + 1);
 
@@ -228,7 +233,7 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const BwdParams p) {
     uint32_t wi = 0;
     long long tq_wait_s = 0, tq_math = 0, tq_wait_p = 0, tq_st = 0, tq_n = 0;
     const long long tq_begin = FS_CLOCK();
-    const int xj_per_grp = (p.D >> 4) / NG;  // 8-column groups of X handled by this warp group
+    const int xj0 = ((p.D >> 4) * grp) / NG, xj1 = ((p.D >> 4) * (grp + 1)) / NG;  // 8-column groups of X of this warp group
     for (long w = blockIdx.x; w < n_work; w += gridDim.x, ++wi) {
       const long rb = w % p.row_blocks;
       const int split = (int)(w / p.row_blocks);
@@ -236,7 +241,7 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const BwdParams p) {
       const long xrow = rb * kRows + row;
       {  // this thread's row of X -> TMEM (packed bf16 pairs, channel 2j in the low half); columns split over groups
         const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.X) + xrow * p.D);
-        for (int j = grp * xj_per_grp; j < (grp + 1) * xj_per_grp; ++j) {
+        for (int j = xj0; j < xj1; ++j) {
           uint4 lo = make_uint4(0, 0, 0, 0), hi = lo;
           if (xrow < p.n_x) {
             lo = src[2 * j];
@@ -445,13 +450,20 @@ struct BwdPlan {
   size_t smem;
 };
 
-static void bwd_plan(long n_x, long n_y, int D, BwdPlan* pl) {
+// three_groups: the dE pass at D <= 128 runs 64-column tiles with THREE accumulator stages / softmax warp groups (TMEM
+// D/2 + D + 3*64 + 3*32 = 480 columns): its softmax warps are latency-bound (ncu: issue slots 35 % busy, tensor and XU
+// pipes ~52 %), so a third group in flight hides more of the per-tile hand-off latency than wider tiles gain.
+static void bwd_plan(long n_x, long n_y, int D, BwdPlan* pl, bool three_groups = false) {
   pl->NT = D <= 128 ? 96 : 64;
   pl->NSTG = D <= 192 ? 2 : 1;
+  if (three_groups && D <= 128) {
+    pl->NT = 64;
+    pl->NSTG = 3;
+  }
   pl->row_blocks = (n_x + kRows - 1) / kRows;
   pl->tiles = (n_y + pl->NT - 1) / pl->NT;
   const size_t stage = (size_t)(D / 64) * pl->NT * 128;
-  int stages = (int)(((size_t)kBwdSmem - 1024 - 16 * pl->NT * 4 - 512) / stage);
+  int stages = (int)(((size_t)kBwdSmem - 1024 - 8 * pl->NSTG * pl->NT * 4 - 512) / stage);
   pl->stages = stages > kBwdMaxStages ? kBwdMaxStages : stages;
   // column splits per row block: the smallest count whose work items fill the persistent grid to >= 95 % in whole waves
   // (e.g. 64 row blocks on 148 SMs: 2 splits leave 20 SMs idle, 9 splits = 576 items = 3.9 waves), at least 4 tiles each
@@ -468,7 +480,7 @@ static void bwd_plan(long n_x, long n_y, int D, BwdPlan* pl) {
   pl->splits = (int)splits;
   const long n_work = pl->row_blocks * splits;
   pl->grid = (int)(n_work < sm_count() ? n_work : sm_count());
-  pl->smem = 1024 + (size_t)pl->stages * stage + 16 * pl->NT * 4 + 512;
+  pl->smem = 1024 + (size_t)pl->stages * stage + 8 * pl->NSTG * pl->NT * 4 + 512;
 }
 
 template <int TR>
@@ -482,6 +494,7 @@ static int bwd_launch(const BwdPlan& pl, const CUtensorMap& my, const BwdParams&
     return BDLRU_OK;                                                                                            \
   }
   BWD_CASE(96, 2) BWD_CASE(64, 2) BWD_CASE(64, 1)
+  if constexpr (TR == MODE_DE) { BWD_CASE(64, 3) }
 #undef BWD_CASE
   set_error("fullsort_ce_bwd: no kernel for NT=%d NSTG=%d", pl.NT, pl.NSTG);
   return BDLRU_ERR_UNSUPPORTED;
@@ -493,7 +506,7 @@ static int bwd_one(const void* X, long n_x, const void* Y, long n_y, int D, cons
                    long n_users, long id_offset, float scale, const float* scale_dev, float* grad, float* scratch,
                    cudaStream_t st) {
   BwdPlan pl;
-  bwd_plan(n_x, n_y, D, &pl);
+  bwd_plan(n_x, n_y, D, &pl, TR == MODE_DE && kDeThreeGroups);
   CUtensorMap my;
   int rc = make_rows_map(&my, Y, n_y, D, pl.NT);
   if (rc) return rc;
@@ -525,7 +538,7 @@ __global__ void rowsum_merge_kernel(const float* __restrict__ parts, long n, int
 size_t ce_bwd_workspace_bytes(long n_users, long n_rows, int D) {
   BwdPlan a, b;
   bwd_plan(n_users, n_rows, D, &a);
-  bwd_plan(n_rows, n_users, D, &b);
+  bwd_plan(n_rows, n_users, D, &b, kDeThreeGroups);
   const size_t wa = a.splits > 1 ? (size_t)a.splits * n_users * D * 4 : 0;
   const size_t wb = b.splits > 1 ? (size_t)b.splits * n_rows * D * 4 : 0;
   return wa > wb ? wa : wb;

@@ -156,7 +156,13 @@ class RecBLR(SequentialRecommender):
             self._dropout_step.add_(1)
         item_emb = self._front(item_seq)
         ctx = (self._seed_base(), self._dropout_step if dropping else None)
+        last = len(self.recurrent_layers) - 1
         for i, layer in enumerate(self.recurrent_layers):
+            if i == last and not self.training and not torch.is_grad_enabled():
+                # only position len-1 of the last layer's output is ever used (RecBLR.py:83): the recurrence still walks the
+                # whole sequence, but the out-projection, both residual LayerNorms and the FFN (RecBLR.py:140-145) run
+                # on [B, D] instead of [B, L, D] and the gather is folded in
+                return layer.forward_last(item_emb, item_seq_len - 1)
             item_emb = layer(item_emb, dropout_ctx=(ctx[0] + 7919 * (i + 1), ctx[1]))
         return self.gather_indexes(item_emb, item_seq_len - 1)
 
@@ -278,6 +284,28 @@ class RecurrentLayer(nn.Module):
         if not self.disable_ffn:
             hidden_states = self.ffn(hidden_states, dropout_ctx)
         return hidden_states
+
+    @torch.no_grad()
+    def forward_last(self, input_tensor, last_index):
+        """Inference form of `forward` followed by `gather_indexes(., last_index)`: [B, L, D], [B] -> [B, D].  Same
+        arithmetic per kept row; nothing downstream of the scan is computed for the L-1 rows that would be discarded."""
+        bm = self.behavior_modeling
+        _, seq_len, _ = input_tensor.shape
+        xz = bm.input(input_tensor)
+        y = ops.bdlru_block(xz, bm.conv1d.weight.squeeze(1), bm.conv1d.bias, bm.gates.weight, bm.gates.bias, bm.Lambda,
+                            h0=bm.phantom_state(seq_len), use_conv=not bm.disable_conv1d)
+        y_last = _gather_rows(y, last_index)                       # [B, C]
+        x_last = _gather_rows(input_tensor, last_index)            # [B, D] residual
+        h = self.layer_norm(bm.output(y_last) + x_last.to(y_last.dtype))
+        if not self.disable_ffn:
+            f = self.ffn
+            h = f.layer_norm(f.w_2(F.silu(f.w_1(h))) + h)
+        return h
+
+
+def _gather_rows(x, index):
+    """x[b, index[b], :] for x [B, T, C] -> [B, C] (SequentialRecommender.gather_indexes)."""
+    return x.gather(1, index.view(-1, 1, 1).expand(-1, 1, x.shape[-1])).squeeze(1)
 
 
 class GatedRecurrentLayer(nn.Module):
