@@ -52,8 +52,10 @@ constexpr int kBwdSmem = 200 * 1024;
 #define BDLRU_CE_DE_POLY_MASK 0u
 #endif
 constexpr uint32_t kPolyMaskDQ = BDLRU_CE_DQ_POLY_MASK, kPolyMaskDE = BDLRU_CE_DE_POLY_MASK;
+// Measured at 8 192 x 10 M x 128 (B200): three groups 46.1 ms vs two groups with 96-column tiles 41.6 ms — the narrower
+// GEMM1 tiles cost more than the extra group hides; kept as a build-time variant, off.
 #ifndef BDLRU_CE_DE_THREE_GROUPS
-#define BDLRU_CE_DE_THREE_GROUPS 1
+#define BDLRU_CE_DE_THREE_GROUPS 0
 #endif
 constexpr bool kDeThreeGroups = BDLRU_CE_DE_THREE_GROUPS != 0;
 

@@ -35,11 +35,12 @@ struct GScanParams {
   const float* lambda;
   const float* h0;
   long h0_bs;
-  float* part_dc;   // [grid, 4*tcn] partial sums of dL/dc (c = softplus(Lambda))
-  float* part_dh0;  // [grid, 4*tcn] partial sums of dh0 when h0 is broadcast
+  float* part_dc;   // [grid, V*tcn] partial sums of dL/dc (c = softplus(Lambda))
+  float* part_dh0;  // [grid, V*tcn] partial sums of dh0 when h0 is broadcast
   float* dh0;       // direct output when h0 is per batch
   int B, T, C;
   int tcn, NS, n_ctile, n_iter, n_units;
+  bool wide_ok;     // every view is 16-byte aligned with strides that are multiples of 8 elements (bf16: 8 channels/thread)
 };
 
 template <typename T>
@@ -55,24 +56,43 @@ template <int NTC>
 __device__ __forceinline__ int cta_threads() { return NTC ? NTC : (int)blockDim.x; }
 
 // ------------------------------------------------------------------------------------------ forward
-template <typename T, int S, bool GATED, bool HAS_Z, int NTC>
+// V = channels per thread (one 16-byte access: 4 x fp32 or 8 x bf16; 4 x bf16 when C is not a multiple of 8).
+// Per-thread vectors of V floats go through shared memory as V/4 float4.
+template <int V>
+__device__ __forceinline__ void st_vec(float* dst, const float (&v)[V]) {
+#pragma unroll
+  for (int k = 0; k < V / 4; ++k)
+    reinterpret_cast<float4*>(dst)[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+}
+template <int V>
+__device__ __forceinline__ void ld_vec(const float* src, float (&v)[V]) {
+#pragma unroll
+  for (int k = 0; k < V / 4; ++k) {
+    const float4 f = reinterpret_cast<const float4*>(src)[k];
+    v[4 * k] = f.x; v[4 * k + 1] = f.y; v[4 * k + 2] = f.z; v[4 * k + 3] = f.w;
+  }
+}
+
+template <typename T, int V, int S, bool GATED, bool HAS_Z, int NTC>
 __global__ void __launch_bounds__(256) gscan_fwd_kernel(const GScanParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
-  constexpr int EB = IO<T>::BYTES;
+  using IOx = IOV<T, V>;
+  constexpr int EB = IOx::BYTES;
+  constexpr bool FAST = sizeof(T) == 2;
   constexpr int NARR = (GATED ? 3 : 2) + (HAS_Z ? 1 : 0);
   const int NT = cta_threads<NTC>(), tid = threadIdx.x;
   const int tc = tid % p.tcn, ts = tid / p.tcn;
   const int ROW = NT * EB;                      // bytes between consecutive staged vectors of a thread
   const int stage_bytes = NARR * S * ROW;
   unsigned char* mine = smem + tid * EB;        // thread-private column of the staging area
-  float4* agg = reinterpret_cast<float4*>(smem + 2 * stage_bytes);  // [2 parity][2 (A,H)][NT]
+  float* agg = reinterpret_cast<float*>(smem + 2 * stage_bytes);  // [2 parity][2 (A,H)][NT][V]
 
   const int my_units = (p.n_units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int my_total = my_units * p.n_iter;
   const int Tb = p.NS * S;
   // channel offset is fixed per CTA (the host sizes the grid as a multiple of n_ctile); the producer
   // side keeps its own (unit, iteration) cursor so that no division happens per iteration.
-  const int c = (((int)blockIdx.x % p.n_ctile) * p.tcn + tc) * 4;
+  const int c = (((int)blockIdx.x % p.n_ctile) * p.tcn + tc) * V;
   const long xrb = row_bytes<T>(p.x), rrb = row_bytes<T>(p.r), irb = row_bytes<T>(p.i), zrb = row_bytes<T>(p.z);
   const long hrb = row_bytes<T>(p.h), yrb = row_bytes<T>(p.y);
 
@@ -103,11 +123,11 @@ __global__ void __launch_bounds__(256) gscan_fwd_kernel(const GScanParams p) {
   issue(0);
   issue(1);
 
-  float state[4] = {0.f, 0.f, 0.f, 0.f};
-  float csp[4] = {0.f, 0.f, 0.f, 0.f};
-  if (GATED) {
+  float state[V], csp[V];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) csp[e] = softplus_acc(p.lambda[c + e]);
+  for (int e = 0; e < V; ++e) {
+    state[e] = 0.f;
+    csp[e] = GATED ? softplus_acc(p.lambda[c + e]) : 0.f;
   }
   int cu = blockIdx.x, it = 0, buf = 0;  // consumer cursor
   long b = cu / p.n_ctile;
@@ -116,25 +136,27 @@ __global__ void __launch_bounds__(256) gscan_fwd_kernel(const GScanParams p) {
     const unsigned char* src = mine + buf * stage_bytes;
     if (it == 0) {
 #pragma unroll
-      for (int e = 0; e < 4; ++e) state[e] = p.h0 ? p.h0[b * p.h0_bs + c + e] : 0.f;
+      for (int e = 0; e < V; ++e) state[e] = p.h0 ? p.h0[b * p.h0_bs + c + e] : 0.f;
     }
     cp_async_wait<1>();
 
     // pass 1: local scan from a zero state
-    float hloc[S][4], cum[S][4];
-    float hl[4] = {0.f, 0.f, 0.f, 0.f}, ca[4] = {1.f, 1.f, 1.f, 1.f};
+    float hloc[S][V], cum[S][V];
+    float hl[V], ca[V];
+#pragma unroll
+    for (int e = 0; e < V; ++e) { hl[e] = 0.f; ca[e] = 1.f; }
 #pragma unroll
     for (int s = 0; s < S; ++s) {
       if (t0 + s < p.T) {
-        float xv[4], rv[4], iv[4];
-        IO<T>::load(src + (0 * S + s) * ROW, xv);
-        IO<T>::load(src + (1 * S + s) * ROW, rv);
-        if (GATED) IO<T>::load(src + (2 * S + s) * ROW, iv);
+        float xv[V], rv[V], iv[V];
+        IOx::load(src + (0 * S + s) * ROW, xv);
+        IOx::load(src + (1 * S + s) * ROW, rv);
+        if (GATED) IOx::load(src + (2 * S + s) * ROW, iv);
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
+        for (int e = 0; e < V; ++e) {
           float a, bb;
           if (GATED) {
-            Gate gt = gate_full<(sizeof(T) == 2)>(csp[e], rv[e], iv[e]);
+            Gate gt = gate_full<FAST>(csp[e], rv[e], iv[e]);
             a = gt.a;
             bb = gt.q * gt.si * xv[e];
           } else {
@@ -146,24 +168,29 @@ __global__ void __launch_bounds__(256) gscan_fwd_kernel(const GScanParams p) {
         }
       }
 #pragma unroll
-      for (int e = 0; e < 4; ++e) { hloc[s][e] = hl[e]; cum[s][e] = ca[e]; }
+      for (int e = 0; e < V; ++e) { hloc[s][e] = hl[e]; cum[s][e] = ca[e]; }
     }
     if (!HAS_Z) issue(buf);  // slots of this buffer are consumed: refill (thread-private)
 
     // combine chunk aggregates across the NS slices
-    float4* aggA = agg + (buf * 2 + 0) * NT;
-    float4* aggH = agg + (buf * 2 + 1) * NT;
-    aggA[tid] = make_float4(ca[0], ca[1], ca[2], ca[3]);
-    aggH[tid] = make_float4(hl[0], hl[1], hl[2], hl[3]);
+    float* aggA = agg + (size_t)(buf * 2 + 0) * NT * V;
+    float* aggH = agg + (size_t)(buf * 2 + 1) * NT * V;
+    st_vec<V>(aggA + tid * V, ca);
+    st_vec<V>(aggH + tid * V, hl);
     __syncthreads();
-    float cin[4] = {0.f, 0.f, 0.f, 0.f};
+    float cin[V];
+#pragma unroll
+    for (int e = 0; e < V; ++e) cin[e] = 0.f;
     for (int j = 0; j < p.NS; ++j) {
-      const float4 A = aggA[j * p.tcn + tc], H = aggH[j * p.tcn + tc];
-      if (j == ts) { cin[0] = state[0]; cin[1] = state[1]; cin[2] = state[2]; cin[3] = state[3]; }
-      state[0] = fmaf(A.x, state[0], H.x);
-      state[1] = fmaf(A.y, state[1], H.y);
-      state[2] = fmaf(A.z, state[2], H.z);
-      state[3] = fmaf(A.w, state[3], H.w);
+      float A[V], H[V];
+      ld_vec<V>(aggA + (j * p.tcn + tc) * V, A);
+      ld_vec<V>(aggH + (j * p.tcn + tc) * V, H);
+      if (j == ts) {
+#pragma unroll
+        for (int e = 0; e < V; ++e) cin[e] = state[e];
+      }
+#pragma unroll
+      for (int e = 0; e < V; ++e) state[e] = fmaf(A[e], state[e], H[e]);
     }
 
     // pass 2: apply the carry-in and write
@@ -172,16 +199,16 @@ __global__ void __launch_bounds__(256) gscan_fwd_kernel(const GScanParams p) {
 #pragma unroll
     for (int s = 0; s < S; ++s) {
       if (t0 + s < p.T) {
-        float hv[4];
+        float hv[V];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) hv[e] = fmaf(cum[s][e], cin[e], hloc[s][e]);
-        IO<T>::store(ph + s * hrb, hv);
+        for (int e = 0; e < V; ++e) hv[e] = fmaf(cum[s][e], cin[e], hloc[s][e]);
+        IOx::store(ph + s * hrb, hv);
         if (HAS_Z) {
-          float zv[4], yv[4];
-          IO<T>::load(src + ((NARR - 1) * S + s) * ROW, zv);
+          float zv[V], yv[V];
+          IOx::load(src + ((NARR - 1) * S + s) * ROW, zv);
 #pragma unroll
-          for (int e = 0; e < 4; ++e) yv[e] = zv[e] * sigmoid_t<(sizeof(T) == 2)>(zv[e]) * hv[e];
-          IO<T>::store(py + s * yrb, yv);
+          for (int e = 0; e < V; ++e) yv[e] = zv[e] * sigmoid_t<FAST>(zv[e]) * hv[e];
+          IOx::store(py + s * yrb, yv);
         }
       }
     }
@@ -194,10 +221,12 @@ __global__ void __launch_bounds__(256) gscan_fwd_kernel(const GScanParams p) {
 // ------------------------------------------------------------------------------------------ backward
 // Staged vectors per thread: GATED: x'[S], r[S], i[S], g[S], h[t0-1 ..][NH] (+ z[S] and one more h entry
 // when HAS_Z);  RAW: a[S] (in p.r), g[S], h[NH].
-template <typename T, int S, bool GATED, bool HAS_Z, int NTC>
+template <typename T, int V, int S, bool GATED, bool HAS_Z, int NTC>
 __global__ void __launch_bounds__(256) gscan_bwd_kernel(const GScanParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
-  constexpr int EB = IO<T>::BYTES;
+  using IOx = IOV<T, V>;
+  constexpr int EB = IOx::BYTES;
+  constexpr bool FAST = sizeof(T) == 2;
   constexpr int NH = S + (HAS_Z ? 1 : 0);                          // staged h entries: h[t0-1 .. t0+NH-2]
   constexpr int NVEC = (GATED ? 4 : 2) * S + NH + (HAS_Z ? S : 0);  // vectors staged per thread
   constexpr int OFF_X = 0, OFF_R = GATED ? S : 0, OFF_I = 2 * S, OFF_G = GATED ? 3 * S : S;
@@ -207,16 +236,16 @@ __global__ void __launch_bounds__(256) gscan_bwd_kernel(const GScanParams p) {
   const int ROW = NT * EB;
   const int stage_bytes = NVEC * ROW;
   unsigned char* mine = smem + tid * EB;
-  float4* agg = reinterpret_cast<float4*>(smem + 2 * stage_bytes);  // [2][2][NT]
+  float* agg = reinterpret_cast<float*>(smem + 2 * stage_bytes);  // [2][2][NT][V]
   // GATED pass 1 leaves sigmoid(r) and alpha for pass 2 in thread-private fp32 scratch: for fp32 I/O it
-  // overwrites the consumed r and g staging slots, for bf16 I/O (8-byte slots) it has its own array.
+  // overwrites the consumed r and g staging slots, for bf16 I/O (smaller slots) it has its own array.
   constexpr bool INPLACE = sizeof(T) == 4;
-  float4* scr = agg + 4 * NT + tid;  // !INPLACE: [2 (sr, a)][S][NT]
+  float* scr = agg + (size_t)4 * NT * V + tid * V;  // !INPLACE: [2 (sr, a)][S][NT][V]
 
   const int my_units = (p.n_units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int my_total = my_units * p.n_iter;
   const int Tb = p.NS * S;
-  const int c = (((int)blockIdx.x % p.n_ctile) * p.tcn + tc) * 4;  // fixed per CTA
+  const int c = (((int)blockIdx.x % p.n_ctile) * p.tcn + tc) * V;  // fixed per CTA
   const long xrb = row_bytes<T>(p.x), rrb = row_bytes<T>(p.r), irb = row_bytes<T>(p.i), zrb = row_bytes<T>(p.z);
   const long hrb = row_bytes<T>(p.h), grb = row_bytes<T>(p.g);
   const long dxrb = row_bytes<T>(p.dx), drrb = row_bytes<T>(p.dr), dirb = row_bytes<T>(p.di), dzrb = row_bytes<T>(p.dz);
@@ -256,12 +285,11 @@ __global__ void __launch_bounds__(256) gscan_bwd_kernel(const GScanParams p) {
   issue(0);
   issue(1);
 
-  float ustate[4] = {0.f, 0.f, 0.f, 0.f};
-  float csp[4] = {0.f, 0.f, 0.f, 0.f}, h0v[4] = {0.f, 0.f, 0.f, 0.f};
-  float dc_acc[4] = {0.f, 0.f, 0.f, 0.f}, dh0_acc[4] = {0.f, 0.f, 0.f, 0.f};
-  if (GATED) {
+  float ustate[V], csp[V], h0v[V], dc_acc[V], dh0_acc[V];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) csp[e] = softplus_acc(p.lambda[c + e]);
+  for (int e = 0; e < V; ++e) {
+    ustate[e] = h0v[e] = dc_acc[e] = dh0_acc[e] = 0.f;
+    csp[e] = GATED ? softplus_acc(p.lambda[c + e]) : 0.f;
   }
 
   int cu = blockIdx.x, it = p.n_iter - 1, buf = 0;  // consumer cursor
@@ -269,15 +297,15 @@ __global__ void __launch_bounds__(256) gscan_bwd_kernel(const GScanParams p) {
   for (int w = 0; w < my_total; ++w, buf ^= 1) {
     const int t0 = it * Tb + ts * S;
     unsigned char* src = mine + buf * stage_bytes;
-    auto scr_sr = [&](int s) -> float4* {
-      return INPLACE ? reinterpret_cast<float4*>(src + (OFF_R + s) * ROW) : scr + (0 * S + s) * NT;
+    auto scr_sr = [&](int s) -> float* {
+      return INPLACE ? reinterpret_cast<float*>(src + (OFF_R + s) * ROW) : scr + (size_t)(0 * S + s) * NT * V;
     };
-    auto scr_a = [&](int s) -> float4* {
-      return INPLACE ? reinterpret_cast<float4*>(src + (OFF_G + s) * ROW) : scr + (1 * S + s) * NT;
+    auto scr_a = [&](int s) -> float* {
+      return INPLACE ? reinterpret_cast<float*>(src + (OFF_G + s) * ROW) : scr + (size_t)(1 * S + s) * NT * V;
     };
     if (it == p.n_iter - 1) {
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
+      for (int e = 0; e < V; ++e) {
         h0v[e] = p.h0 ? p.h0[b * p.h0_bs + c + e] : 0.f;
         ustate[e] = 0.f;
       }
@@ -285,42 +313,46 @@ __global__ void __launch_bounds__(256) gscan_bwd_kernel(const GScanParams p) {
     cp_async_wait<1>();
 
     // pass 1 (reverse time): local dh~ from u_in = 0; pm = product of the gates AFTER step s
-    float dloc[S][4], pm[S][4];
-    float ul[4] = {0.f, 0.f, 0.f, 0.f}, pc[4] = {1.f, 1.f, 1.f, 1.f};
+    float dloc[S][V], pm[S][V];
+    float ul[V], pc[V];
+#pragma unroll
+    for (int e = 0; e < V; ++e) { ul[e] = 0.f; pc[e] = 1.f; }
     unsigned char* pdz = HAS_Z ? const_cast<unsigned char*>(at<T>(p.dz, b, t0, c)) : nullptr;
 #pragma unroll
     for (int s = S - 1; s >= 0; --s) {
-      float av[4] = {1.f, 1.f, 1.f, 1.f}, gv[4] = {0.f, 0.f, 0.f, 0.f};
+      float av[V], gv[V];
+#pragma unroll
+      for (int e = 0; e < V; ++e) { av[e] = 1.f; gv[e] = 0.f; }
       if (t0 + s < p.T) {
-        float rv[4];
-        IO<T>::load(src + (OFF_R + s) * ROW, rv);
-        IO<T>::load(src + (OFF_G + s) * ROW, gv);
+        float rv[V];
+        IOx::load(src + (OFF_R + s) * ROW, rv);
+        IOx::load(src + (OFF_G + s) * ROW, gv);
         if (HAS_Z) {
           // upstream is dL/dy with y = silu(z) * h:  dz = dy * h_t * silu'(z),  g = dy * silu(z)
-          float zv[4], hv[4], dzv[4];
-          IO<T>::load(src + (OFF_Z + s) * ROW, zv);
-          IO<T>::load(src + (OFF_H + s + 1) * ROW, hv);
+          float zv[V], hv[V], dzv[V];
+          IOx::load(src + (OFF_Z + s) * ROW, zv);
+          IOx::load(src + (OFF_H + s + 1) * ROW, hv);
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float sz = sigmoid_t<(sizeof(T) == 2)>(zv[e]);
+          for (int e = 0; e < V; ++e) {
+            const float sz = sigmoid_t<FAST>(zv[e]);
             dzv[e] = gv[e] * hv[e] * silu_grad_f(zv[e], sz);
             gv[e] *= zv[e] * sz;
           }
-          IO<T>::store(pdz + s * dzrb, dzv);
+          IOx::store(pdz + s * dzrb, dzv);
         }
         if (GATED) {
-          float srv[4];
+          float srv[V];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) av[e] = gate_alpha<(sizeof(T) == 2)>(csp[e], rv[e], srv[e]);
-          *scr_sr(s) = make_float4(srv[0], srv[1], srv[2], srv[3]);
-          *scr_a(s) = make_float4(av[0], av[1], av[2], av[3]);
+          for (int e = 0; e < V; ++e) av[e] = gate_alpha<FAST>(csp[e], rv[e], srv[e]);
+          st_vec<V>(scr_sr(s), srv);
+          st_vec<V>(scr_a(s), av);
         } else {
 #pragma unroll
-          for (int e = 0; e < 4; ++e) av[e] = rv[e];
+          for (int e = 0; e < V; ++e) av[e] = rv[e];
         }
       }
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
+      for (int e = 0; e < V; ++e) {
         const float d = gv[e] + ul[e];
         dloc[s][e] = d;
         pm[s][e] = pc[e];
@@ -330,27 +362,32 @@ __global__ void __launch_bounds__(256) gscan_bwd_kernel(const GScanParams p) {
     }
 
     // combine (carry flows from later slices to earlier ones)
-    float4* aggA = agg + (buf * 2 + 0) * NT;
-    float4* aggU = agg + (buf * 2 + 1) * NT;
-    aggA[tid] = make_float4(pc[0], pc[1], pc[2], pc[3]);
-    aggU[tid] = make_float4(ul[0], ul[1], ul[2], ul[3]);
+    float* aggA = agg + (size_t)(buf * 2 + 0) * NT * V;
+    float* aggU = agg + (size_t)(buf * 2 + 1) * NT * V;
+    st_vec<V>(aggA + tid * V, pc);
+    st_vec<V>(aggU + tid * V, ul);
     __syncthreads();
-    float uin[4] = {0.f, 0.f, 0.f, 0.f};
+    float uin[V];
+#pragma unroll
+    for (int e = 0; e < V; ++e) uin[e] = 0.f;
     for (int j = p.NS - 1; j >= 0; --j) {
-      const float4 A = aggA[j * p.tcn + tc], U = aggU[j * p.tcn + tc];
-      if (j == ts) { uin[0] = ustate[0]; uin[1] = ustate[1]; uin[2] = ustate[2]; uin[3] = ustate[3]; }
-      ustate[0] = fmaf(A.x, ustate[0], U.x);
-      ustate[1] = fmaf(A.y, ustate[1], U.y);
-      ustate[2] = fmaf(A.z, ustate[2], U.z);
-      ustate[3] = fmaf(A.w, ustate[3], U.w);
+      float A[V], U[V];
+      ld_vec<V>(aggA + (j * p.tcn + tc) * V, A);
+      ld_vec<V>(aggU + (j * p.tcn + tc) * V, U);
+      if (j == ts) {
+#pragma unroll
+        for (int e = 0; e < V; ++e) uin[e] = ustate[e];
+      }
+#pragma unroll
+      for (int e = 0; e < V; ++e) ustate[e] = fmaf(A[e], ustate[e], U[e]);
     }
     if (it == 0 && ts == 0) {  // u flowing out of t = 0 is dL/dh0 for this (b, channel vector)
       if (p.dh0) {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) p.dh0[b * p.C + c + e] = ustate[e];
+        for (int e = 0; e < V; ++e) p.dh0[b * p.C + c + e] = ustate[e];
       } else {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) dh0_acc[e] += ustate[e];
+        for (int e = 0; e < V; ++e) dh0_acc[e] += ustate[e];
       }
     }
 
@@ -362,27 +399,25 @@ __global__ void __launch_bounds__(256) gscan_bwd_kernel(const GScanParams p) {
     for (int s = 0; s < S; ++s) {
       const int t = t0 + s;
       if (t < p.T) {
-        float d[4], hp[4];
+        float d[V], hp[V];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) d[e] = fmaf(pm[s][e], uin[e], dloc[s][e]);
+        for (int e = 0; e < V; ++e) d[e] = fmaf(pm[s][e], uin[e], dloc[s][e]);
         if (t == 0) {
 #pragma unroll
-          for (int e = 0; e < 4; ++e) hp[e] = h0v[e];
+          for (int e = 0; e < V; ++e) hp[e] = h0v[e];
         } else {
-          IO<T>::load(src + (OFF_H + s) * ROW, hp);
+          IOx::load(src + (OFF_H + s) * ROW, hp);
         }
         if (GATED) {
-          float xv[4], iv[4], dxv[4], drv[4], div[4];
-          IO<T>::load(src + (OFF_X + s) * ROW, xv);
-          IO<T>::load(src + (OFF_I + s) * ROW, iv);
-          const float4 sr4 = *scr_sr(s);
-          const float4 a4 = *scr_a(s);
-          const float srv[4] = {sr4.x, sr4.y, sr4.z, sr4.w};
-          const float av[4] = {a4.x, a4.y, a4.z, a4.w};
+          float xv[V], iv[V], dxv[V], drv[V], div[V], srv[V], av[V];
+          IOx::load(src + (OFF_X + s) * ROW, xv);
+          IOx::load(src + (OFF_I + s) * ROW, iv);
+          ld_vec<V>(scr_sr(s), srv);
+          ld_vec<V>(scr_a(s), av);
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float si = sigmoid_t<(sizeof(T) == 2)>(iv[e]);
-            const float v = one_minus_exp_neg(2.0f * csp[e] * srv[e], av[e] * av[e]) + 1e-8f;
+          for (int e = 0; e < V; ++e) {
+            const float si = sigmoid_t<FAST>(iv[e]);
+            const float v = one_minus_a2<FAST>(csp[e], srv[e], av[e]);
             const float rq = rsqrt_ftz(v), q = v * rq;
             const float dbeta = d[e] * xv[e];
             dxv[e] = d[e] * q * si;
@@ -392,15 +427,15 @@ __global__ void __launch_bounds__(256) gscan_bwd_kernel(const GScanParams p) {
             drv[e] = -csp[e] * daa * srv[e] * (1.0f - srv[e]);
             dc_acc[e] = fmaf(-daa, srv[e], dc_acc[e]);
           }
-          IO<T>::store(pdx + s * dxrb, dxv);
-          IO<T>::store(pdr + s * drrb, drv);
-          IO<T>::store(pdi + s * dirb, div);
+          IOx::store(pdx + s * dxrb, dxv);
+          IOx::store(pdr + s * drrb, drv);
+          IOx::store(pdi + s * dirb, div);
         } else {
-          float dgv[4];
+          float dgv[V];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) dgv[e] = hp[e] * d[e];
-          IO<T>::store(pdx + s * dxrb, d);     // d_tokens
-          IO<T>::store(pdr + s * drrb, dgv);   // d_gates
+          for (int e = 0; e < V; ++e) dgv[e] = hp[e] * d[e];
+          IOx::store(pdx + s * dxrb, d);     // d_tokens
+          IOx::store(pdr + s * drrb, dgv);   // d_gates
         }
       }
     }
@@ -412,23 +447,23 @@ __global__ void __launch_bounds__(256) gscan_bwd_kernel(const GScanParams p) {
   // per-CTA partial sums of dL/dc and (broadcast) dh0: reduce over the NS slices, one row per CTA.
   // The host sizes the grid as a multiple of n_ctile, so a CTA sees a single channel tile.
   __syncthreads();
-  float4* red = agg;  // reuse: [NT]
+  float* red = agg;  // reuse: [NT][V]
   if (GATED) {
-    red[tid] = make_float4(dc_acc[0], dc_acc[1], dc_acc[2], dc_acc[3]);
+    st_vec<V>(red + tid * V, dc_acc);
     __syncthreads();
     if (ts == 0) {
-      float4 s4 = red[tc];
+      float s4[V];
+      ld_vec<V>(red + tc * V, s4);
       for (int j = 1; j < p.NS; ++j) {
-        const float4 v = red[j * p.tcn + tc];
-        s4.x += v.x; s4.y += v.y; s4.z += v.z; s4.w += v.w;
+        float v[V];
+        ld_vec<V>(red + (j * p.tcn + tc) * V, v);
+#pragma unroll
+        for (int e = 0; e < V; ++e) s4[e] += v[e];
       }
-      reinterpret_cast<float4*>(p.part_dc)[(size_t)blockIdx.x * p.tcn + tc] = s4;
+      st_vec<V>(p.part_dc + ((size_t)blockIdx.x * p.tcn + tc) * V, s4);
     }
   }
-  if (p.part_dh0 && ts == 0) {
-    reinterpret_cast<float4*>(p.part_dh0)[(size_t)blockIdx.x * p.tcn + tc] =
-        make_float4(dh0_acc[0], dh0_acc[1], dh0_acc[2], dh0_acc[3]);
-  }
+  if (p.part_dh0 && ts == 0) st_vec<V>(p.part_dh0 + ((size_t)blockIdx.x * p.tcn + tc) * V, dh0_acc);
 }
 
 // ------------------------------------------------------------------------------------------ host side
@@ -436,10 +471,10 @@ struct Tiling {
   int tcn, NS, NT, n_ctile, n_iter, n_units, grid;
 };
 
-template <int S>
+template <int S, int V>
 static Tiling make_tiling(int B, int T, int C) {
   Tiling t;
-  const int cvec = C / 4;
+  const int cvec = C / V;
   t.tcn = 1;
   while (t.tcn < 32 && cvec % (t.tcn * 2) == 0) t.tcn *= 2;
   t.n_ctile = cvec / t.tcn;
@@ -474,16 +509,21 @@ static int check_view(const char* name, const bdlru_view& v, int esize, bool req
   return BDLRU_OK;
 }
 static View mk(const bdlru_view& v) { return View{reinterpret_cast<const unsigned char*>(v.ptr), v.bstride, v.rstride}; }
+static bool view_wide(const View& v) { return !v.p || (aligned(v.p, 16) && v.bs % 8 == 0 && v.rs % 8 == 0); }
+static void set_wide(GScanParams& p) {
+  p.wide_ok = view_wide(p.x) && view_wide(p.r) && view_wide(p.i) && view_wide(p.z) && view_wide(p.h) && view_wide(p.y) &&
+              view_wide(p.g) && view_wide(p.dx) && view_wide(p.dr) && view_wide(p.di) && view_wide(p.dz);
+}
 
-constexpr int kS = 4;  // steps per slice per iteration
-
-template <typename T, bool GATED, bool HAS_Z>
-static int launch_fwd(GScanParams& p, cudaStream_t st) {
-  Tiling t = make_tiling<kS>(p.B, p.T, p.C);
+// (V channels, S steps) per thread and iteration: fp32 4 x 4; bf16 8 x 2 when C is a multiple of 8 (same 16 elements
+// per thread and iteration, same register footprint, half the memory instructions), else 4 x 4.
+template <typename T, int V, int kS, bool GATED, bool HAS_Z>
+static int launch_fwd_v(GScanParams& p, cudaStream_t st) {
+  Tiling t = make_tiling<kS, V>(p.B, p.T, p.C);
   p.tcn = t.tcn; p.NS = t.NS; p.n_ctile = t.n_ctile; p.n_iter = t.n_iter; p.n_units = t.n_units;
   constexpr int NARR = (GATED ? 3 : 2) + (HAS_Z ? 1 : 0);
-  const size_t smem = 2 * (size_t)NARR * kS * t.NT * IO<T>::BYTES + 4 * (size_t)t.NT * sizeof(float4);
-  auto kern = t.NT == 256 ? gscan_fwd_kernel<T, kS, GATED, HAS_Z, 256> : gscan_fwd_kernel<T, kS, GATED, HAS_Z, 0>;
+  const size_t smem = 2 * (size_t)NARR * kS * t.NT * IOV<T, V>::BYTES + 4 * (size_t)t.NT * V * sizeof(float);
+  auto kern = t.NT == 256 ? gscan_fwd_kernel<T, V, kS, GATED, HAS_Z, 256> : gscan_fwd_kernel<T, V, kS, GATED, HAS_Z, 0>;
   BDLRU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 1;
   BDLRU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, t.NT, smem));
@@ -494,21 +534,36 @@ static int launch_fwd(GScanParams& p, cudaStream_t st) {
   return BDLRU_OK;
 }
 
+// Measured on B200 (tools/scan_bench.py, bf16): 8 channels x 2 steps per thread is SLOWER than 4 x 4 at C = 128
+// (2 048 x 200 x 128 fwd+bwd 0.64 ms vs 0.38 ms: only 16 channel vectors, so 16 time slices per CTA and a 16-long
+// aggregate walk per 16 elements) and equal at C = 256 — the wide instantiation is kept for experiments, off by default.
+#ifndef BDLRU_GSCAN_WIDE
+#define BDLRU_GSCAN_WIDE 0
+#endif
+
 template <typename T, bool GATED, bool HAS_Z>
-static int launch_bwd(GScanParams& p, float* dLambda, float* dh0_out, void* ws, size_t ws_bytes, cudaStream_t st) {
-  Tiling t = make_tiling<kS>(p.B, p.T, p.C);
+static int launch_fwd(GScanParams& p, cudaStream_t st) {
+  if constexpr (sizeof(T) == 2 && BDLRU_GSCAN_WIDE) {
+    if (p.C % 8 == 0 && p.wide_ok) return launch_fwd_v<T, 8, 2, GATED, HAS_Z>(p, st);
+  }
+  return launch_fwd_v<T, 4, 4, GATED, HAS_Z>(p, st);
+}
+
+template <typename T, int V, int kS, bool GATED, bool HAS_Z>
+static int launch_bwd_v(GScanParams& p, float* dLambda, float* dh0_out, void* ws, size_t ws_bytes, cudaStream_t st) {
+  Tiling t = make_tiling<kS, V>(p.B, p.T, p.C);
   p.tcn = t.tcn; p.NS = t.NS; p.n_ctile = t.n_ctile; p.n_iter = t.n_iter; p.n_units = t.n_units;
   constexpr int NH = kS + (HAS_Z ? 1 : 0);
   constexpr int NVEC = (GATED ? 4 : 2) * kS + NH + (HAS_Z ? kS : 0);
-  const size_t smem = 2 * (size_t)NVEC * t.NT * IO<T>::BYTES + 4 * (size_t)t.NT * sizeof(float4) +
-                      ((GATED && sizeof(T) != 4) ? 2 * (size_t)kS * t.NT * sizeof(float4) : 0);
-  auto kern = t.NT == 256 ? gscan_bwd_kernel<T, kS, GATED, HAS_Z, 256> : gscan_bwd_kernel<T, kS, GATED, HAS_Z, 0>;
+  const size_t smem = 2 * (size_t)NVEC * t.NT * IOV<T, V>::BYTES + 4 * (size_t)t.NT * V * sizeof(float) +
+                      ((GATED && sizeof(T) != 4) ? 2 * (size_t)kS * t.NT * V * sizeof(float) : 0);
+  auto kern = t.NT == 256 ? gscan_bwd_kernel<T, V, kS, GATED, HAS_Z, 256> : gscan_bwd_kernel<T, V, kS, GATED, HAS_Z, 0>;
   BDLRU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 1;
   BDLRU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, t.NT, smem));
   if (occ < 1) occ = 1;
   const int grid = pick_grid(t, occ);
-  const int ctw = 4 * t.tcn;
+  const int ctw = V * t.tcn;
   const size_t need = 2 * (size_t)grid * ctw * sizeof(float);
   BDLRU_REQUIRE(ws && ws_bytes >= need, "gated_scan_bwd: workspace too small (%zu < %zu)", ws_bytes, need);
   p.part_dc = reinterpret_cast<float*>(ws);
@@ -527,6 +582,14 @@ static int launch_bwd(GScanParams& p, float* dLambda, float* dh0_out, void* ws, 
     if (rc) return rc;
   }
   return BDLRU_OK;
+}
+
+template <typename T, bool GATED, bool HAS_Z>
+static int launch_bwd(GScanParams& p, float* dLambda, float* dh0_out, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if constexpr (sizeof(T) == 2 && BDLRU_GSCAN_WIDE) {
+    if (p.C % 8 == 0 && p.wide_ok) return launch_bwd_v<T, 8, 2, GATED, HAS_Z>(p, dLambda, dh0_out, ws, ws_bytes, st);
+  }
+  return launch_bwd_v<T, 4, 4, GATED, HAS_Z>(p, dLambda, dh0_out, ws, ws_bytes, st);
 }
 
 static int check_common(int B, int T, int C, int dtype) {
@@ -548,8 +611,8 @@ using namespace bdlru;
 
 extern "C" BDLRU_API size_t bdlru_gated_scan_bwd_workspace_bytes(int B, int T, int C) {
   (void)B; (void)T;
-  // 2 partial arrays of [grid, 4*tcn] floats; grid <= 32 CTAs/SM * SMs, 4*tcn <= 128
-  return 2 * (size_t)32 * (size_t)sm_count() * 128 * sizeof(float) + 2 * (size_t)(C / 4 + 1) * 128 * sizeof(float);
+  // 2 partial arrays of [grid, V*tcn] floats; grid <= 32 CTAs/SM * SMs, V*tcn <= 256
+  return 2 * (size_t)32 * (size_t)sm_count() * 256 * sizeof(float) + 2 * (size_t)(C / 4 + 1) * 256 * sizeof(float);
 }
 
 extern "C" BDLRU_API int bdlru_gated_scan_fwd(bdlru_view xp, bdlru_view r, bdlru_view i, const float* Lambda, const float* h0,
@@ -566,6 +629,7 @@ extern "C" BDLRU_API int bdlru_gated_scan_fwd(bdlru_view xp, bdlru_view r, bdlru
   GScanParams p{};
   p.x = mk(xp); p.r = mk(r); p.i = mk(i); p.z = mk(z); p.h = mk(h); p.y = mk(y);
   p.lambda = Lambda; p.h0 = h0; p.h0_bs = h0_bstride; p.B = B; p.T = T; p.C = C;
+  set_wide(p);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (dtype == BDLRU_F32)
     return z.ptr ? launch_fwd<float, true, true>(p, st) : launch_fwd<float, true, false>(p, st);
@@ -590,6 +654,7 @@ extern "C" BDLRU_API int bdlru_gated_scan_bwd(bdlru_view xp, bdlru_view r, bdlru
   p.x = mk(xp); p.r = mk(r); p.i = mk(i); p.z = mk(z); p.h = mk(h); p.g = mk(grad);
   p.dx = mk(dxp); p.dr = mk(dr); p.di = mk(di); p.dz = mk(dz);
   p.lambda = Lambda; p.h0 = h0; p.h0_bs = h0_bstride; p.B = B; p.T = T; p.C = C;
+  set_wide(p);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (dtype == BDLRU_F32)
     return z.ptr ? launch_bwd<float, true, true>(p, dLambda, dh0, workspace, workspace_bytes, st)
@@ -607,6 +672,7 @@ extern "C" BDLRU_API int bdlru_scan_cl_fwd(bdlru_view a, bdlru_view b, const flo
   BDLRU_REQUIRE(h0_bstride == 0 || h0_bstride == C, "h0_bstride must be 0 or C");
   GScanParams p{};
   p.x = mk(b); p.r = mk(a); p.h = mk(h); p.h0 = h0; p.h0_bs = h0_bstride; p.B = B; p.T = T; p.C = C;
+  set_wide(p);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   return dtype == BDLRU_F32 ? launch_fwd<float, false, false>(p, st) : launch_fwd<__nv_bfloat16, false, false>(p, st);
 }
@@ -623,6 +689,7 @@ extern "C" BDLRU_API int bdlru_scan_cl_bwd(bdlru_view a, const float* h0, int64_
   GScanParams p{};
   p.r = mk(a); p.h = mk(h); p.g = mk(grad); p.dx = mk(db); p.dr = mk(da);
   p.h0 = h0; p.h0_bs = h0_bstride; p.B = B; p.T = T; p.C = C;
+  set_wide(p);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   return dtype == BDLRU_F32
              ? launch_bwd<float, false, false>(p, nullptr, dh0, workspace, workspace_bytes, st)
