@@ -353,8 +353,10 @@ fullsort_kernel(const __grid_constant__ CUtensorMap tmE, const FsParams p) {
     // and resolved by id in the merge).  This makes S short streams insert like ONE long stream (K ln(N/K) in total
     // instead of per split).  `sthr` lags by one tile so the L2 read is never waited for.
     float sthr = -INFINITY;
-    unsigned sthr_raw = 0u;  // loaded one tile ago, decoded (= first use) only now
     const bool share = MODE == MODE_TOPK && p.shared_thr != nullptr && user < p.n_users;
+    // loaded one tile ago, decoded (= first use) only now; the first value is the SEED a sampled pre-pass left there
+    // (bdlru_fullsort_topk), fetched here so that its latency hides behind the wait for the first accumulator
+    unsigned sthr_raw = share ? __ldcg(p.shared_thr + user) : 0u;
     float run_m = -INFINITY, run_s = 0.f;   // CE: online max / sum of exp
     long pos_local = -1;
     if (MODE == MODE_CE && user < p.n_users) {
@@ -508,7 +510,7 @@ fullsort_kernel(const __grid_constant__ CUtensorMap tmE, const FsParams p) {
 __global__ void __launch_bounds__(128) topk_merge_kernel(const float* __restrict__ cs, const int* __restrict__ ci,
                                                          long n_users, int n_cand, int k, long list_stride,
                                                          long user_stride, float* __restrict__ os,
-                                                         int* __restrict__ oi) {
+                                                         int* __restrict__ oi, unsigned* __restrict__ seed_out) {
   extern __shared__ uint8_t msm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long user = (long)blockIdx.x * 4 + warp;
@@ -544,6 +546,8 @@ __global__ void __launch_bounds__(128) topk_merge_kernel(const float* __restrict
       os[user * k + r] = bj >= 0 ? bs : -INFINITY;
       oi[user * k + r] = bj >= 0 ? bi : -1;
       if (bj >= 0) id[bj] = -1;  // taken
+      // pre-pass: the K-th best of the SAMPLE is a lower bound of the K-th best of the whole table -> threshold seed
+      if (seed_out && r == k - 1 && bj >= 0) atomicMax(seed_out + user, thr_encode(bs));
     }
     __syncwarp();
   }
@@ -661,17 +665,39 @@ extern "C" BDLRU_API int bdlru_fullsort_topk(const void* Q, const void* E, int64
   p.part_scores = reinterpret_cast<float*>(workspace);
   p.part_ids = reinterpret_cast<int*>(p.part_scores + (size_t)n_users * pl.splits * k);
   p.shared_thr = nullptr;
-  if (pl.splits > 1 && !(fs_debug() & 16)) {  // BDLRU_FS_DEBUG & 16: disable threshold sharing (tuning / A-B runs)
-    p.shared_thr = reinterpret_cast<unsigned*>(p.part_ids + (size_t)n_users * pl.splits * k);
-    BDLRU_CUDA(cudaMemsetAsync(p.shared_thr, 0, (size_t)n_users * 4, st));
-  }
-  if ((rc = fs_launch<MODE_TOPK>(pl, me, p, st))) return rc;
   const int n_cand = pl.splits * k;
   const size_t msmem = (size_t)4 * n_cand * 8;
   BDLRU_REQUIRE(msmem <= 200 * 1024, "fullsort_topk: merge of %d candidates per user does not fit", n_cand);
   BDLRU_CUDA(cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
+  if (pl.splits > 1 && !(fs_debug() & 16)) {  // BDLRU_FS_DEBUG & 16: disable threshold sharing (tuning / A-B runs)
+    p.shared_thr = reinterpret_cast<unsigned*>(p.part_ids + (size_t)n_users * pl.splits * k);
+    BDLRU_CUDA(cudaMemsetAsync(p.shared_thr, 0, (size_t)n_users * 4, st));
+    // Threshold SEED.  A stream's insert work is ~K ln(n/K) and almost all of it falls on its first tiles, which is what
+    // keeps 1 M-item shards at 0.74 of the tensor rate against 0.95+ at 10 M.  A pre-pass runs the SAME kernel over a
+    // strided sample of the tiles (>= 256 tiles, ~1/32 of the table) and its merged K-th best score per user — a lower
+    // bound of the true K-th best, whatever the sample — is left in shared_thr, so the real streams start filtering at
+    // the ~(32 K)-th best score instead of -inf.  The result is unchanged (ties at the threshold are admitted).
+    const long n_samp = pl.tiles_total / 32 > 256 ? pl.tiles_total / 32 : 256;
+    const long stride = pl.tiles_total / n_samp;
+    if (stride >= 4 && !(fs_debug() & 32)) {  // BDLRU_FS_DEBUG & 32: no seed (A-B runs)
+      FsParams ps = p;
+      FsPlan pp = pl;
+      ps.tile_stride = (int)stride;
+      ps.tiles_total = (pl.tiles_total + stride - 1) / stride;
+      const long max_s = ps.tiles_total / 4 > 0 ? ps.tiles_total / 4 : 1;
+      if (pp.splits > max_s) pp.splits = (int)max_s;
+      ps.splits = pp.splits;
+      if ((rc = fs_launch<MODE_TOPK>(pp, me, ps, st))) return rc;
+      const int nc = pp.splits * k;
+      // the sample's merged lists land in the output buffers (overwritten by the real merge below)
+      topk_merge_kernel<<<(unsigned)((n_users + 3) / 4), 128, (size_t)4 * nc * 8, st>>>(
+          ps.part_scores, ps.part_ids, n_users, nc, k, k, (long)nc, out_scores, out_ids, p.shared_thr);
+      BDLRU_LAUNCHED();
+    }
+  }
+  if ((rc = fs_launch<MODE_TOPK>(pl, me, p, st))) return rc;
   topk_merge_kernel<<<(unsigned)((n_users + 3) / 4), 128, msmem, st>>>(p.part_scores, p.part_ids, n_users, n_cand, k, k,
-                                                                      (long)n_cand, out_scores, out_ids);
+                                                                      (long)n_cand, out_scores, out_ids, nullptr);
   BDLRU_LAUNCHED();
   return BDLRU_OK;
 }
@@ -686,7 +712,7 @@ static int merge_impl(const float* cand_scores, const int32_t* cand_ids, int64_t
   BDLRU_REQUIRE(msmem <= 200 * 1024, "topk_merge: %d candidates per user do not fit", n_cand);
   BDLRU_CUDA(cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
   topk_merge_kernel<<<(unsigned)((n_users + 3) / 4), 128, msmem, reinterpret_cast<cudaStream_t>(stream)>>>(
-      cand_scores, cand_ids, n_users, n_cand, k, list_stride, user_stride, out_scores, out_ids);
+      cand_scores, cand_ids, n_users, n_cand, k, list_stride, user_stride, out_scores, out_ids, nullptr);
   BDLRU_LAUNCHED();
   return BDLRU_OK;
 }
