@@ -255,11 +255,12 @@ __device__ __forceinline__ float gate_alpha(float c, float r, float& sr) {
   return exp_f(-c * sr);
 }
 // 1 - a^2 + 1e-8 with a = exp(-c * sr).  Exact path: cancellation-free series for small exponents.  FAST (bf16 I/O, whose
-// sigmoid is already a 5e-4 approximation and whose outputs are rounded to 2^-9): one FMA; its absolute error ~6e-8 is
-// below the bf16 rounding of the result for every a <= 1 - 3e-5.
+// sigmoid is already a 5e-4 approximation and whose outputs are rounded to 2^-9): FMA + add; its absolute error ~6e-8 is
+// below the bf16 rounding of the result for every a <= 1 - 3e-5.  The 1e-8 is added AFTERWARDS (1 + 1e-8 == 1 in fp32):
+// a saturated gate (a == 1) must give sqrt(1e-8), not rsqrt(0) = inf.
 template <bool FAST>
 __device__ __forceinline__ float one_minus_a2(float c, float sr, float a) {
-  if constexpr (FAST) return fmaf(-a, a, 1.0f + 1e-8f);
+  if constexpr (FAST) return fmaf(-a, a, 1.0f) + 1e-8f;
   else return one_minus_exp_neg(2.0f * c * sr, a * a) + 1e-8f;
 }
 template <bool FAST = false>

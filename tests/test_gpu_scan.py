@@ -216,3 +216,24 @@ def test_gated_scan_packed_equals_unpacked(dtype):
         outs.append((y.detach(), txp.grad, tri.grad, tz.grad, tlam.grad, th0.grad))
     for a, b in zip(*outs):
         assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_gated_scan_saturated_gates_stay_finite(dtype):
+    """Saturated recurrence gates (sigmoid(r) == 0 -> alpha == 1 exactly): sqrt(1 - alpha^2 + 1e-8) must stay 1e-4, never
+    rsqrt(0) (regression: the bf16 one-FMA form once folded the 1e-8 into the FMA constant, where it rounds away)."""
+    B, T, C = 3, 21, 64
+    g = torch.Generator(device="cuda").manual_seed(0)
+    xp = torch.randn(B, T, C, device="cuda", generator=g).to(dtype).requires_grad_(True)
+    ri = torch.randn(B, T, 2 * C, device="cuda", generator=g)
+    ri[..., :C] = -60.0                       # sigmoid(r) underflows to 0
+    ri = ri.to(dtype).requires_grad_(True)
+    lam = torch.linspace(-2.2, -6.9, C, device="cuda").requires_grad_(True)
+    z = torch.randn(B, T, C, device="cuda", generator=g).to(dtype).requires_grad_(True)
+    y = _ops().gated_scan_packed(xp, ri, lam, z=z)
+    y.sum().backward()
+    for t in (y, xp.grad, ri.grad, z.grad, lam.grad):
+        assert torch.isfinite(t).all()
+    # alpha == 1, beta' = 1e-4 * sigmoid(i) * x': h is a plain cumulative sum of tiny terms
+    h_ref = (1e-4 * torch.sigmoid(ri[..., C:].double()) * xp.double()).cumsum(1) * torch.nn.functional.silu(z.double())
+    assert float((y.double() - h_ref).abs().max()) <= (1e-6 if dtype == torch.float32 else 2e-2 * float(h_ref.abs().max()) + 1e-6)
