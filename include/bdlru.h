@@ -258,6 +258,16 @@ size_t bdlru_fullsort_ce_fwd_dq_workspace_bytes(int64_t n_users, int64_t n_rows,
 int bdlru_fullsort_ce_fwd_dq(const void* Q, const void* E, const float* ref, int64_t n_users, int64_t n_rows, int D,
                              float* acc, float* row_sumexp, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Optimizer step of a row shard of the item table: torch.optim.Adam's update (amsgrad = False; weight_decay = L2 added
+ * to the gradient) of the fp32 master rows, fused with the refresh of the bf16 compute copy (param_bf16, may be NULL):
+ * one pass, 30 bytes per element instead of 34 in two kernels.  `step` is the 1-based step count (bias correction).
+ * n = number of fp32 elements (multiple of 4); all arrays contiguous.
+ * ------------------------------------------------------------------------------------------- */
+int bdlru_table_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, void* param_bf16,
+                          int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay, int64_t step,
+                          void* stream);
+
 #ifdef __cplusplus
 }
 #endif
