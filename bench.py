@@ -315,9 +315,10 @@ def run_train(args):
     if big:   # tied item table row-sharded over the ranks (world 1: same code, no collectives)
         sit = sharded.shard_item_table(model)
         torch.cuda.empty_cache()
-    opt = torch.optim.Adam(model.parameters(), lr=1e-3, fused=True, capturable=True)
-    if sit is not None:
-        sit.attach(opt)   # refresh of the replicated bf16 copy after every optimizer step
+    if sit is not None:   # dense parameters: torch's fused Adam; table shard: Adam + bf16 refresh in one kernel + all-gather
+        opt = sharded.ShardedTableOptimizer(model, lr=1e-3)
+    else:
+        opt = torch.optim.Adam(model.parameters(), lr=1e-3, fused=True, capturable=True)
     dense = sharded.dense_parameters(model)
     amp = args.dtype == "bf16"
     assert amp or sit is None, "the sharded-table workloads run in bf16"

@@ -409,6 +409,70 @@ def _cuda_kernels():
     return K
 
 
+class ShardedTableOptimizer:
+    """Adam for a model whose item table is row-sharded: torch.optim.Adam (fused) for the dense parameters, and for the
+    table ONE kernel (`bdlru_table_adam_step`) that applies the same Adam update to this rank's fp32 master rows AND writes
+    their bf16 copy, followed by the in-place all-gather of the copy.  Drop-in for the optimizer object RecBole's trainer
+    holds (`zero_grad`, `step`, `state_dict`, `param_groups`): construct it instead of `torch.optim.Adam(model.parameters())`.
+    Same arithmetic as torch.optim.Adam(amsgrad=False) — tests compare the two step by step."""
+
+    def __init__(self, model, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, kernel=None):
+        self.sit = model.table_shard
+        assert self.sit is not None, "call sharded.shard_item_table(model) first"
+        dense = dense_parameters(model)
+        self.dense = torch.optim.Adam(dense, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay,
+                                      fused=dense[0].is_cuda, capturable=dense[0].is_cuda) if dense else None
+        self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
+        m = self.sit.master
+        self.exp_avg = torch.zeros_like(m)
+        self.exp_avg_sq = torch.zeros_like(m)
+        self.steps = 0
+        self._kernel = kernel or _table_adam_cuda
+
+    @property
+    def param_groups(self):
+        return (self.dense.param_groups if self.dense is not None else []) + [
+            {"params": [self.sit.master], "lr": self.lr, "betas": self.betas, "eps": self.eps}]
+
+    def zero_grad(self, set_to_none=True):
+        if self.dense is not None:
+            self.dense.zero_grad(set_to_none=set_to_none)
+        self.sit.master.grad = None if set_to_none else self.sit.master.grad
+
+    @torch.no_grad()
+    def step(self):
+        if self.dense is not None:
+            self.dense.step()
+        sit = self.sit
+        if sit.master.grad is not None:
+            self.steps += 1
+            mine = sit.table_bf16[sit.rank * sit.rows_per:(sit.rank + 1) * sit.rows_per]
+            self._kernel(sit.master.data, sit.master.grad, self.exp_avg, self.exp_avg_sq, mine, self.lr, self.betas[0],
+                         self.betas[1], self.eps, self.weight_decay, self.steps)
+            if sit.world > 1:
+                dist.all_gather_into_tensor(sit.table_bf16, mine, group=sit.group)
+
+    def state_dict(self):
+        return {"dense": self.dense.state_dict() if self.dense is not None else None, "steps": self.steps,
+                "exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq}
+
+    def load_state_dict(self, sd):
+        if self.dense is not None and sd["dense"] is not None:
+            self.dense.load_state_dict(sd["dense"])
+        self.steps = int(sd["steps"])
+        self.exp_avg.copy_(sd["exp_avg"])
+        self.exp_avg_sq.copy_(sd["exp_avg_sq"])
+
+
+def _table_adam_cuda(p, g, m, v, p_bf16, lr, b1, b2, eps, wd, step):
+    from . import _lib as L
+    L.require_cuda(p, g, m, v, p_bf16)
+    assert p.is_contiguous() and g.is_contiguous() and m.is_contiguous() and v.is_contiguous() and p_bf16.is_contiguous()
+    assert g.dtype == torch.float32 and p_bf16.dtype == torch.bfloat16 and p_bf16.numel() == p.numel()
+    L.check(L.load().bdlru_table_adam_step(L.ptr(p), L.ptr(g), L.ptr(m), L.ptr(v), L.ptr(p_bf16), p.numel(), float(lr),
+                                           float(b1), float(b2), float(eps), float(wd), int(step), L.stream_ptr(p)))
+
+
 def shard_item_table(model, group=None):
     """Switches a constructed RecBLR (identical full table on every rank: same seed, or a loaded checkpoint) to the
     row-sharded tied table: `model.item_embedding.weight` becomes this rank's fp32 master shard (what the optimizer

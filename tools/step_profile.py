@@ -28,9 +28,10 @@ with torch.device(dev):   # parameters are created (and initialised) on the GPU:
     model = RecBLR(bench.make_config(w, dev), bench._DS(w["n_items"]))
 big = bool(w.get("big"))
 sit = sharded.shard_item_table(model) if big else None
-opt = torch.optim.Adam(model.parameters(), lr=1e-3, fused=True, capturable=True)
 if sit is not None:
-    sit.attach(opt)
+    opt = sharded.ShardedTableOptimizer(model, lr=1e-3)
+else:
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, fused=True, capturable=True)
 dense = sharded.dense_parameters(model)
 b = tuple(t.to(dev) for t in bench.synthetic_batch(w["B"], w["L"], w["n_items"], 1 + rank))
 ex = {"item_id_list": b[0], "item_length": b[1], "item_id": b[2]}
