@@ -58,6 +58,10 @@ constexpr uint32_t kPolyMaskDQ = BDLRU_CE_DQ_POLY_MASK, kPolyMaskDE = BDLRU_CE_D
 #define BDLRU_CE_DE_THREE_GROUPS 0
 #endif
 constexpr bool kDeThreeGroups = BDLRU_CE_DE_THREE_GROUPS != 0;
+#ifndef BDLRU_CE_DE_AUGMENT
+#define BDLRU_CE_DE_AUGMENT 1
+#endif
+constexpr bool kDeAugment = BDLRU_CE_DE_AUGMENT != 0;
 
 struct BwdParams {
   const void* X;        // [n_x, D] bf16 rows owned by CTAs
@@ -80,18 +84,24 @@ enum { MODE_DQ = 0, MODE_DE = 1, MODE_FWD = 2 };
 
 template <int MODE, int NT, int NSTG>
 __global__ void __launch_bounds__(96 + 128 * NSTG, 1)
-ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const BwdParams p) {
+ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmL, const BwdParams p) {
   constexpr bool TRANSPOSED = MODE == MODE_DE;
   constexpr bool FWD = MODE == MODE_FWD;
+  // dE pass: the per-COLUMN statistic -lse_u rides the recompute GEMM as 16 extra K elements — X gets the constant columns
+  // (1, 1, 1, 0, ...), every user row of Y the exact three-way bf16 split of -lse_u (one more 64-channel slab per stage from
+  // the auxiliary matrix behind tmL, of which one K step is used) — so the accumulator already holds l - lse and the softmax
+  // loop needs neither a shared-memory read nor an FFMA per element (it was latency-bound on exactly those).
+  constexpr bool AUG = kDeAugment && MODE == MODE_DE;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_slab = p.D >> 6;
+  const int n_slab_st = n_slab + (AUG ? 1 : 0);   // slabs per ring stage
   constexpr uint32_t kSlabB = NT * 128;
   constexpr int NCH = NT / 32;
   constexpr int NG = NSTG;                 // softmax warp groups: group g owns accumulator / P stage g
   uint8_t* sY = smem;
-  float* col_lse = reinterpret_cast<float*>(sY + (size_t)p.stages * n_slab * kSlabB);  // [4 * NSTG warps][NT]
+  float* col_lse = reinterpret_cast<float*>(sY + (size_t)p.stages * n_slab_st * kSlabB);  // [4 * NSTG warps][NT]
   int* col_pos = reinterpret_cast<int*>(col_lse + 4 * NSTG * NT);                       // [4 * NSTG warps][NT]
   uint64_t* bars = reinterpret_cast<uint64_t*>(col_pos + 4 * NSTG * NT);
   uint64_t* y_full = bars;
@@ -104,13 +114,14 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const BwdParams p) {
   uint64_t* dx_full = x_full + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dx_full + 1);
 
-  const uint32_t x_cols = (uint32_t)(p.D >> 1);
+  const uint32_t x_cols = (uint32_t)(p.D >> 1) + (AUG ? 8u : 0u);
   const uint32_t dx_col = x_cols;
   const uint32_t s_col = dx_col + (uint32_t)p.D;
   const uint32_t p_col = s_col + NSTG * NT;
 
   if (warp == 2 && lane == 0) {
     tc::prefetch_tensormap(&tmY);
+    if (AUG) tc::prefetch_tensormap(&tmL);
     for (int s = 0; s < p.stages; ++s) {
       tc::mbar_init(&y_full[s], 1);
       tc::mbar_init(&y_empty[s], 1);
@@ -147,9 +158,10 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const BwdParams p) {
         const uint32_t ph = (uint32_t)(g / p.stages) & 1u;
         tc::mbar_wait(&y_empty[s], ph ^ 1u);
         if (tc::elect_one()) {
-          tc::mbar_arrive_expect_tx(&y_full[s], (uint32_t)n_slab * kSlabB);
+          tc::mbar_arrive_expect_tx(&y_full[s], (uint32_t)n_slab_st * kSlabB);
           for (int sl = 0; sl < n_slab; ++sl)
-            tc::tma_load_2d(sY + (size_t)(s * n_slab + sl) * kSlabB, &tmY, &y_full[s], sl * 64, (int)(t * NT));
+            tc::tma_load_2d(sY + (size_t)(s * n_slab_st + sl) * kSlabB, &tmY, &y_full[s], sl * 64, (int)(t * NT));
+          if (AUG) tc::tma_load_2d(sY + (size_t)(s * n_slab_st + n_slab) * kSlabB, &tmL, &y_full[s], 0, (int)(t * NT));
         }
         __syncwarp();
       }
@@ -175,7 +187,7 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const BwdParams p) {
         tc::mbar_wait(&s_empty[b], bph ^ 1u);
         tc::fence_after_sync();
         if (tc::elect_one()) {
-          const uint64_t bd0 = tc::smem_desc_sw128(tc::smem_u32(sY + (size_t)s * n_slab * kSlabB), 16, 1024);
+          const uint64_t bd0 = tc::smem_desc_sw128(tc::smem_u32(sY + (size_t)s * n_slab_st * kSlabB), 16, 1024);
           const uint32_t d_tmem = tmem_base + s_col + (uint32_t)b * NT;
           for (int sl = 0; sl < n_slab; ++sl) {
 #pragma unroll
@@ -184,6 +196,9 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const BwdParams p) {
                                bd0 + (uint64_t)((uint32_t)sl * (kSlabB >> 4) + (uint32_t)k4 * 2), idesc1,
                                (uint32_t)((sl | k4) != 0));
           }
+          if (AUG)   // the 16 augmented K elements: X columns D/2 .. D/2+7, first K step of the extra slab
+            tc::umma_bf16_ts(d_tmem, tmem_base + (uint32_t)(p.D >> 1), bd0 + (uint64_t)((uint32_t)n_slab * (kSlabB >> 4)),
+                             idesc1, 1u);
           tc::umma_commit(&s_full[b]);
         }
         __syncwarp();
@@ -205,7 +220,7 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const BwdParams p) {
         if (tc::elect_one()) {
           // Y tile as the MN-major B operand: leading (MN) stride = one 64-channel slab, K groups of 8 rows are
           // 1024 bytes apart; one MMA consumes 16 rows = 2048 bytes
-          const uint64_t bd0 = tc::smem_desc_sw128(tc::smem_u32(sY + (size_t)s * n_slab * kSlabB), kSlabB, 1024);
+          const uint64_t bd0 = tc::smem_desc_sw128(tc::smem_u32(sY + (size_t)s * n_slab_st * kSlabB), kSlabB, 1024);
           const uint32_t a0 = tmem_base + p_col + (uint32_t)b * (NT / 2);
 #pragma unroll
           for (int kk = 0; kk < NT / 16; ++kk)
@@ -252,6 +267,10 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const BwdParams p) {
           const uint32_t wv[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
           tc::tmem_st_32x32_x8(lane_addr + (uint32_t)j * 8, wv);
         }
+        if (AUG && grp == 0) {  // augmented K elements D .. D+15 of every X row: 1, 1, 1, 0, ... (bf16 1.0 = 0x3F80)
+          const uint32_t ones[8] = {0x3F803F80u, 0x00003F80u, 0u, 0u, 0u, 0u, 0u, 0u};
+          tc::tmem_st_32x32_x8(lane_addr + (uint32_t)(p.D >> 1), ones);
+        }
         tc::tmem_st_wait();
         tc::fence_before_sync();
         __syncwarp();
@@ -289,7 +308,7 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const BwdParams p) {
             for (int k = 0; k < NCH; ++k) {
               const long u = cbase + lane + 32 * k;
               const bool ok = u < p.n_users;
-              pre_lse[k] = ok ? p.lse[u] : INFINITY;
+              if (!AUG) pre_lse[k] = ok ? p.lse[u] : INFINITY;
               pre_pos[k] = ok ? p.pos[u] : -1;
             }
           }
@@ -299,7 +318,7 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const BwdParams p) {
 #pragma unroll
           for (int k = 0; k < NCH; ++k) {
             const int lp = pre_pos[k] < 0 ? -1 : (int)(pre_pos[k] - p.id_offset);
-            my_lse[lane + 32 * k] = pre_lse[k] * kLog2e;
+            if (!AUG) my_lse[lane + 32 * k] = pre_lse[k] * kLog2e;
             my_pos[lane + 32 * k] = lp;
             mine |= (lp >= row_lo && lp < row_lo + 32);
           }
@@ -313,7 +332,7 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const BwdParams p) {
             for (int k = 0; k < NCH; ++k) {
               const long u = nt * NT + lane + 32 * k;
               const bool ok = u < p.n_users;
-              pre_lse[k] = ok ? p.lse[u] : INFINITY;
+              if (!AUG) pre_lse[k] = ok ? p.lse[u] : INFINITY;
               pre_pos[k] = ok ? p.pos[u] : -1;
             }
           }
@@ -345,7 +364,7 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const BwdParams p) {
               // dE pass: the four columns' statistics in ONE 128-bit broadcast read (the per-element LDS was a quarter
               // of this loop's issue slots)
               float cl[4] = {0.f, 0.f, 0.f, 0.f};
-              if (TRANSPOSED) {
+              if (TRANSPOSED && !AUG) {
                 const float4 l4 = *reinterpret_cast<const float4*>(my_lse + c * 32 + i);
                 cl[0] = l4.x; cl[1] = l4.y; cl[2] = l4.z; cl[3] = l4.w;
               }
@@ -354,7 +373,8 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const BwdParams p) {
                 const int col = c * 32 + i + u;
                 const float sv = __uint_as_float(raw[i + u]);
                 if (TRANSPOSED) {
-                  pr[u] = ex2_mixed<TRANSPOSED ? kPolyMaskDE : kPolyMaskDQ, 3>(fmaf(sv, kLog2e, -cl[u]), i + u);
+                  // AUG: the accumulator already holds l - lse (columns past n_users hold 0 and multiply zero rows of Y)
+                  pr[u] = ex2_mixed<TRANSPOSED ? kPolyMaskDE : kPolyMaskDQ, 3>(AUG ? sv * kLog2e : fmaf(sv, kLog2e, -cl[u]), i + u);
                   if (CHECK && my_pos[col] == (int)row_pos) pr[u] -= 1.f;
                 } else {
                   pr[u] = ex2_mixed<TRANSPOSED ? kPolyMaskDE : kPolyMaskDQ, 3>(fmaf(sv, kLog2e, -row_lse2), i + u);
@@ -445,6 +465,24 @@ __global__ void sum_partials_kernel(const float4* __restrict__ part, long n4, in
   out[i] = a;
 }
 
+// L_aug[u, 0..2] = exact three-way bf16 split of -lse[u]; columns 3..63 zero (one 128-byte swizzle row per user)
+__global__ void lse_aug_kernel(const float* __restrict__ lse, long n_users, __nv_bfloat16* __restrict__ out) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;   // one thread per (user, 8-channel group)
+  if (i >= n_users * 8) return;
+  const long u = i >> 3;
+  uint4 w = make_uint4(0, 0, 0, 0);
+  if ((i & 7) == 0) {
+    const float v = -lse[u];
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    const float r1 = v - __bfloat162float(hi);
+    const __nv_bfloat16 mid = __float2bfloat16_rn(r1);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(r1 - __bfloat162float(mid));
+    w.x = (uint32_t)__bfloat16_as_ushort(hi) | ((uint32_t)__bfloat16_as_ushort(mid) << 16);
+    w.y = (uint32_t)__bfloat16_as_ushort(lo);
+  }
+  reinterpret_cast<uint4*>(out)[i] = w;
+}
+
 // ----------------------------------------------------------------------------- host side
 struct BwdPlan {
   int NT, NSTG, stages, splits, grid;
@@ -455,7 +493,7 @@ struct BwdPlan {
 // three_groups: the dE pass at D <= 128 runs 64-column tiles with THREE accumulator stages / softmax warp groups (TMEM
 // D/2 + D + 3*64 + 3*32 = 480 columns): its softmax warps are latency-bound (ncu: issue slots 35 % busy, tensor and XU
 // pipes ~52 %), so a third group in flight hides more of the per-tile hand-off latency than wider tiles gain.
-static void bwd_plan(long n_x, long n_y, int D, BwdPlan* pl, bool three_groups = false) {
+static void bwd_plan(long n_x, long n_y, int D, BwdPlan* pl, bool three_groups = false, bool aug = false) {
   pl->NT = D <= 128 ? 96 : 64;
   pl->NSTG = D <= 192 ? 2 : 1;
   if (three_groups && D <= 128) {
@@ -464,7 +502,7 @@ static void bwd_plan(long n_x, long n_y, int D, BwdPlan* pl, bool three_groups =
   }
   pl->row_blocks = (n_x + kRows - 1) / kRows;
   pl->tiles = (n_y + pl->NT - 1) / pl->NT;
-  const size_t stage = (size_t)(D / 64) * pl->NT * 128;
+  const size_t stage = (size_t)(D / 64 + (aug ? 1 : 0)) * pl->NT * 128;   // aug: one more slab (the -lse columns)
   int stages = (int)(((size_t)kBwdSmem - 1024 - 8 * pl->NSTG * pl->NT * 4 - 512) / stage);
   pl->stages = stages > kBwdMaxStages ? kBwdMaxStages : stages;
   // column splits per row block: the smallest count whose work items fill the persistent grid to >= 95 % in whole waves
@@ -486,12 +524,12 @@ static void bwd_plan(long n_x, long n_y, int D, BwdPlan* pl, bool three_groups =
 }
 
 template <int TR>
-static int bwd_launch(const BwdPlan& pl, const CUtensorMap& my, const BwdParams& p, cudaStream_t st) {
+static int bwd_launch(const BwdPlan& pl, const CUtensorMap& my, const CUtensorMap& ml, const BwdParams& p, cudaStream_t st) {
 #define BWD_CASE(NTv, NSv)                                                                                      \
   if (pl.NT == NTv && pl.NSTG == NSv) {                                                                         \
     BDLRU_CUDA(cudaFuncSetAttribute(ce_bwd_kernel<TR, NTv, NSv>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
                                     (int)pl.smem));                                                             \
-    ce_bwd_kernel<TR, NTv, NSv><<<pl.grid, 96 + 128 * NSv, pl.smem, st>>>(my, p);                                          \
+    ce_bwd_kernel<TR, NTv, NSv><<<pl.grid, 96 + 128 * NSv, pl.smem, st>>>(my, ml, p);                                       \
     BDLRU_LAUNCHED();                                                                                           \
     return BDLRU_OK;                                                                                            \
   }
@@ -506,19 +544,26 @@ static int bwd_launch(const BwdPlan& pl, const CUtensorMap& my, const BwdParams&
 template <int TR>
 static int bwd_one(const void* X, long n_x, const void* Y, long n_y, int D, const float* lse, const int64_t* pos,
                    long n_users, long id_offset, float scale, const float* scale_dev, float* grad, float* scratch,
-                   cudaStream_t st) {
+                   __nv_bfloat16* laug, cudaStream_t st) {
   BwdPlan pl;
-  bwd_plan(n_x, n_y, D, &pl, TR == MODE_DE && kDeThreeGroups);
-  CUtensorMap my;
+  constexpr bool AUG = TR == MODE_DE && kDeAugment;
+  bwd_plan(n_x, n_y, D, &pl, TR == MODE_DE && kDeThreeGroups, AUG);
+  CUtensorMap my, ml;
   int rc = make_rows_map(&my, Y, n_y, D, pl.NT);
   if (rc) return rc;
+  ml = my;
+  if (AUG) {   // Y = Q here: one row of -lse splits per user, streamed as a third slab of every stage
+    lse_aug_kernel<<<(unsigned)((n_users * 8 + 255) / 256), 256, 0, st>>>(lse, n_users, laug);
+    BDLRU_LAUNCHED();
+    if ((rc = make_rows_map(&ml, laug, n_users, 64, pl.NT))) return rc;
+  }
   BwdParams p = {};
   p.X = X; p.Y = Y; p.n_x = n_x; p.n_y = n_y; p.D = D; p.stages = pl.stages; p.splits = pl.splits;
   p.row_blocks = pl.row_blocks; p.tiles_total = pl.tiles;
   p.lse = lse; p.pos = pos; p.n_users = n_users; p.id_offset = id_offset; p.scale = scale; p.scale_dev = scale_dev;
   p.dbg = tuning_env("BDLRU_FS_DEBUG");
   p.out = pl.splits > 1 ? scratch : grad;
-  if ((rc = bwd_launch<TR>(pl, my, p, st))) return rc;
+  if ((rc = bwd_launch<TR>(pl, my, ml, p, st))) return rc;
   if (pl.splits > 1) {
     const long n4 = n_x * D / 4;
     sum_partials_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float4*>(scratch), n4,
@@ -537,13 +582,16 @@ __global__ void rowsum_merge_kernel(const float* __restrict__ parts, long n, int
   out[u] = a;
 }
 
+static size_t round128(size_t x) { return (x + 127) & ~(size_t)127; }
+
 size_t ce_bwd_workspace_bytes(long n_users, long n_rows, int D) {
   BwdPlan a, b;
   bwd_plan(n_users, n_rows, D, &a);
-  bwd_plan(n_rows, n_users, D, &b, kDeThreeGroups);
+  bwd_plan(n_rows, n_users, D, &b, kDeThreeGroups, kDeAugment);
   const size_t wa = a.splits > 1 ? (size_t)a.splits * n_users * D * 4 : 0;
   const size_t wb = b.splits > 1 ? (size_t)b.splits * n_rows * D * 4 : 0;
-  return wa > wb ? wa : wb;
+  // + the [n_users, 64] bf16 matrix of -lse splits the dE pass streams next to Q
+  return round128(wa > wb ? wa : wb) + (kDeAugment ? (size_t)n_users * 128 : 0);
 }
 
 }  // namespace bdlru
@@ -566,11 +614,14 @@ extern "C" BDLRU_API int bdlru_fullsort_ce_bwd(const void* Q, const void* E, con
                 workspace_bytes, need);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   int rc;
+  __nv_bfloat16* laug = kDeAugment ? reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<char*>(workspace) + need -
+                                                                   (size_t)n_users * 128)
+                                   : nullptr;
   if (dQ && (rc = bwd_one<MODE_DQ>(Q, n_users, E, n_rows, D, lse, pos, n_users, id_offset, scale, scale_dev, dQ,
-                                 reinterpret_cast<float*>(workspace), st)))
+                                   reinterpret_cast<float*>(workspace), nullptr, st)))
     return rc;
   if (dE && (rc = bwd_one<MODE_DE>(E, n_rows, Q, n_users, D, lse, pos, n_users, id_offset, scale, scale_dev, dE,
-                                reinterpret_cast<float*>(workspace), st)))
+                                   reinterpret_cast<float*>(workspace), laug, st)))
     return rc;
   return BDLRU_OK;
 }
@@ -607,7 +658,7 @@ extern "C" BDLRU_API int bdlru_fullsort_ce_fwd_dq(const void* Q, const void* E, 
   p.dbg = tuning_env("BDLRU_FS_DEBUG");
   p.sum_parts = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + acc_bytes);
   p.out = pl.splits > 1 ? scratch : acc;
-  if ((rc = bwd_launch<MODE_FWD>(pl, my, p, st))) return rc;
+  if ((rc = bwd_launch<MODE_FWD>(pl, my, my, p, st))) return rc;
   if (pl.splits > 1) {
     const long n4 = n_users * D / 4;
     sum_partials_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float4*>(scratch), n4,
