@@ -297,7 +297,10 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ C
         const uint32_t bph = (uint32_t)(g / NSTG) & 1u;
         const long cbase = t * NT;
         bool onehot_here = false;
-        if (TRANSPOSED) {
+        // With the augmented GEMM (AUG) the dE pass needs NO per-column data in its softmax loop: -lse comes out of the
+        // accumulator and the "- onehot" term is applied afterwards by onehot_sub_kernel (dE[pos_b] -= scale * q_b, exact
+        // in fp32) — no staging through shared memory, no vote, no second code path per tile.
+        if (TRANSPOSED && !AUG) {
           // Column statistics of this tile (lse*log2e, local positive row) -> per-warp scratch.  The values were
           // prefetched into registers while the previous own tile was processed (first own tile: loaded here).
           // (the prefetched values stay RAW in registers — lse unscaled, pos as loaded — and are converted only here, one
@@ -465,6 +468,25 @@ __global__ void sum_partials_kernel(const float4* __restrict__ part, long n4, in
   out[i] = a;
 }
 
+// dE[pos_b - id_offset, :] -= scale * q_b for every user whose positive item lives in this shard: the "- onehot" term of
+// dE = scale * (P - onehot)^T Q, applied after the augmented dE pass has written scale * P^T Q.  One warp per user,
+// vector red.global.add (several users may share a positive item).
+__global__ void __launch_bounds__(256) onehot_sub_kernel(const __nv_bfloat16* __restrict__ Q, const int64_t* __restrict__ pos,
+                                                         long n_users, int D, long id_offset, long n_rows, float scale,
+                                                         const float* __restrict__ scale_dev, float* __restrict__ dE) {
+  const long u = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (u >= n_users) return;
+  const long r = pos[u] - id_offset;
+  if (r < 0 || r >= n_rows) return;
+  const float sc = -scale * (scale_dev ? __ldg(scale_dev) : 1.f);
+  for (int v = lane; v < D / 4; v += 32) {
+    float q[4];
+    IO<__nv_bfloat16>::load(Q + u * D + v * 4, q);
+    atomicAdd(reinterpret_cast<float4*>(dE + r * D + v * 4), make_float4(sc * q[0], sc * q[1], sc * q[2], sc * q[3]));
+  }
+}
+
 // L_aug[u, 0..2] = exact three-way bf16 split of -lse[u]; columns 3..63 zero (one 128-byte swizzle row per user)
 __global__ void lse_aug_kernel(const float* __restrict__ lse, long n_users, __nv_bfloat16* __restrict__ out) {
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;   // one thread per (user, 8-channel group)
@@ -568,6 +590,11 @@ static int bwd_one(const void* X, long n_x, const void* Y, long n_y, int D, cons
     const long n4 = n_x * D / 4;
     sum_partials_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float4*>(scratch), n4,
                                                                       pl.splits, reinterpret_cast<float4*>(grad));
+    BDLRU_LAUNCHED();
+  }
+  if (AUG) {   // here X = E (n_x item rows), Y = Q (n_users rows)
+    onehot_sub_kernel<<<(unsigned)((n_users * 32 + 255) / 256), 256, 0, st>>>(
+        reinterpret_cast<const __nv_bfloat16*>(Y), pos, n_users, D, id_offset, n_x, scale, scale_dev, grad);
     BDLRU_LAUNCHED();
   }
   return BDLRU_OK;
