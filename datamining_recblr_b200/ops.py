@@ -384,6 +384,34 @@ class _BDLRUBlock(torch.autograd.Function):
                 dh0.to(h0_dt) if dh0 is not None else None, None)
 
 
+def bdlru_core_supported(xz, C):
+    """True when the fused inference kernel (csrc/fused_core.cu) takes this input: bf16, contiguous [B, T, 2C], C = 128."""
+    return (xz.dtype == torch.bfloat16 and xz.is_cuda and xz.is_contiguous() and xz.data_ptr() % 16 == 0
+            and bool(L.load().bdlru_core_fwd_supported(int(C), L.BF16)))
+
+
+@torch.no_grad()
+def bdlru_core_fused(xz, conv_w, conv_b, gates_w, gates_b, Lambda, h0=None, use_conv=True):
+    """INFERENCE form of bdlru_block as ONE tcgen05 kernel: conv + SiLU, the gates GEMM on the tensor
+    cores, gate math, the recurrence and the z-gate, with x' and the gate pre-activations never written to HBM.
+    xz bf16 contiguous [B, T, 2C] with C = 128; returns y bf16 [B, T, C].  Not differentiable (no saved activations)."""
+    L.require_cuda(xz, gates_w, gates_b, Lambda)
+    B, T, C2 = xz.shape
+    C = C2 // 2
+    assert bdlru_core_supported(xz, C), "bdlru_core_fused: bf16 contiguous [B, T, 256] input required"
+    gw = gates_w.detach().to(torch.bfloat16).contiguous()
+    gb = gates_b.detach().float().contiguous()
+    lam = Lambda.detach().float().contiguous()
+    h0f = h0.detach().float().contiguous() if h0 is not None else None
+    cw = conv_w.detach().float().contiguous() if use_conv else None
+    cb = conv_b.detach().float().contiguous() if use_conv else None
+    assert cw is None or cw.shape == (C, 4), "bdlru_core_fused: conv kernel size 4 is built"
+    y = torch.empty((B, T, C), dtype=torch.bfloat16, device=xz.device)
+    L.check(L.load().bdlru_core_fwd(L.ptr(xz), L.ptr(cw), L.ptr(cb), L.ptr(gw), L.ptr(gb), L.ptr(lam), L.ptr(h0f), L.ptr(y),
+                                    B, T, C, L.stream_ptr(xz)))
+    return y
+
+
 def bdlru_block(xz, conv_w, conv_b, gates_w, gates_b, Lambda, h0=None, use_conv=True):
     """y = silu(z) * BD-LRU(silu(conv(x))) for xz = (x | z) [B, T, 2C] — conv, gates GEMM, gate math, scan and z-gate of
     RecBLR.py:174-206 as one autograd node (see _BDLRUBlock).  conv_w [C, W], gates_w [2C, C]; autocast aware."""

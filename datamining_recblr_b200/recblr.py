@@ -292,8 +292,7 @@ class RecurrentLayer(nn.Module):
         bm = self.behavior_modeling
         _, seq_len, _ = input_tensor.shape
         xz = bm.input(input_tensor)
-        y = ops.bdlru_block(xz, bm.conv1d.weight.squeeze(1), bm.conv1d.bias, bm.gates.weight, bm.gates.bias, bm.Lambda,
-                            h0=bm.phantom_state(seq_len), use_conv=not bm.disable_conv1d)
+        y = bm.core(xz, seq_len)
         y_last = _gather_rows(y, last_index)                       # [B, C]
         x_last = _gather_rows(input_tensor, last_index)            # [B, D] residual
         h = self.layer_norm(bm.output(y_last) + x_last.to(y_last.dtype))
@@ -325,6 +324,7 @@ class GatedRecurrentLayer(nn.Module):
         self.gates = nn.Linear(hidden, 2 * hidden, bias=True)
         self.Lambda = nn.Parameter(torch.linspace(lo, hi, hidden))
         self.output = nn.Linear(hidden, d_model, bias=False)
+        self.fused_core = True   # inference: one tcgen05 kernel for conv + gates GEMM + recurrence (ops.bdlru_core_fused)
 
     def phantom_state(self, seq_len):
         """State the reference's left zero-pad leaves in front of the first real step (RecBLR.py:177-199):
@@ -338,6 +338,18 @@ class GatedRecurrentLayer(nn.Module):
         # one fused kernel each way (as torch ops this is ~45 tiny kernels per layer and step); CUDA only
         return ops.phantom_h0(self.conv1d.bias, self.gates.weight, self.gates.bias, self.Lambda, pad_len)
 
+    def core(self, xz, seq_len):
+        """conv -> gates -> recurrence -> z-gate on xz = (x | z): the fused tcgen05 inference kernel when nothing needs a
+        gradient and the shape is the one it is built for (bf16, C = 128, conv width 4), else the separate kernels."""
+        h0 = self.phantom_state(seq_len)
+        conv_w = self.conv1d.weight.squeeze(1)
+        if (not torch.is_grad_enabled() and self.fused_core and conv_w.shape[1] == 4
+                and ops.bdlru_core_supported(xz, xz.shape[-1] // 2)):
+            return ops.bdlru_core_fused(xz, conv_w, self.conv1d.bias, self.gates.weight, self.gates.bias, self.Lambda,
+                                        h0=h0, use_conv=not self.disable_conv1d)
+        return ops.bdlru_block(xz, conv_w, self.conv1d.bias, self.gates.weight, self.gates.bias, self.Lambda, h0=h0,
+                               use_conv=not self.disable_conv1d)
+
     def forward(self, x, return_tap=False):
         """return_tap=True also returns x as a second output of the in-projection's autograd node (for the caller's
         residual connection)."""
@@ -347,8 +359,7 @@ class GatedRecurrentLayer(nn.Module):
             xz, x = ops.linear_tap(x, self.input.weight)
         else:
             xz = self.input(x)
-        y = ops.bdlru_block(xz, self.conv1d.weight.squeeze(1), self.conv1d.bias, self.gates.weight, self.gates.bias,
-                            self.Lambda, h0=self.phantom_state(seq_len), use_conv=not self.disable_conv1d)
+        y = self.core(xz, seq_len)
         return (self.output(y), x) if return_tap else self.output(y)
 
 

@@ -268,6 +268,18 @@ int bdlru_table_adam_step(float* param, const float* grad, float* exp_avg, float
                           int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay, int64_t step,
                           void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Fused core of GatedRecurrentLayer.forward for INFERENCE (RecBLR.py:182-206 without the two projections):
+ *     y = silu(z) * BD-LRU(x' = silu(conv(x) + conv_b), (r | i) = gates_w x' + gates_b),   xz = (x | z)
+ * as one tcgen05 kernel: reads xz [B, T, 2C] bf16 contiguous once, writes y [B, T, C] bf16; x' and the gate
+ * pre-activations stay in shared memory / TMEM.  conv_w [C, 4] fp32 (NULL with conv_b NULL: no conv, x' = x), gates_w
+ * [2C, C] bf16 row-major, gates_b [2C] / Lambda [C] / h0 [C] (may be NULL) fp32.  Built for C = 128 (hidden 64 x expand 2);
+ * bdlru_core_fwd_supported tells.  The training path keeps the separate kernels (their backward needs x' and r|i).
+ * ------------------------------------------------------------------------------------------- */
+int bdlru_core_fwd_supported(int C, int dtype);
+int bdlru_core_fwd(const void* xz, const float* conv_w, const float* conv_b, const void* gates_w, const float* gates_b,
+                   const float* Lambda, const float* h0, void* y, int B, int T, int C, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
