@@ -10,8 +10,9 @@
 // carried across tiles), later receives the 32 consecutive time steps of its channel's r and i from its TMEM lane with one
 // tcgen05.ld each, and runs gate math + the recurrence h = a h + b' sequentially in registers — no shuffles, no chunk
 // aggregates, no block barriers.  A CTA processes one batch row at a time (persistent over rows), 64 time steps per tile,
-// a 3-deep TMA ring of xz tiles and two accumulator stages, so that the conv of tile k+1 overlaps the MMAs of tile k.
-// TMEM: 128 columns of weights + 2 x 128 accumulator columns = 256 of 512 => two CTAs per SM.
+// a 3-deep TMA ring of xz tiles; the conv of tile k+1 runs while the tensor core works on tile k.
+// TMEM: 128 columns of weights + ONE accumulator stage of (r | i) x 64 = 128 columns = 256 of 512 => two CTAs per SM (a
+// second accumulator stage would need 384 -> 512 columns and halve the resident compute warps, which are the bottleneck).
 //
 // Scope: C = 128 (the reference's hidden_size 64 x expand 2), bf16 activations, inference only (the training path keeps
 // the separate kernels, whose backward needs x' and r|i saved).  DESIGN.md §7.1 discusses D = 128 and the backward.
@@ -60,8 +61,8 @@ __global__ void __launch_bounds__(192, 2) fused_core_fwd_kernel(const __grid_con
   uint64_t* conv_done = full + kFStages;       // x' written in place              (4 warps)
   uint64_t* slot_empty = conv_done + kFStages; // tile fully consumed              (4 warps)
   uint64_t* acc_full = slot_empty + kFStages;  // MMAs of the tile complete        (commit)
-  uint64_t* acc_empty = acc_full + 2;          // accumulator stage read out       (4 warps)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint64_t* acc_empty = acc_full + 1;          // accumulator read out             (4 warps)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 4 && lane == 0) {
@@ -71,10 +72,8 @@ __global__ void __launch_bounds__(192, 2) fused_core_fwd_kernel(const __grid_con
       tc::mbar_init(&conv_done[s], 4);
       tc::mbar_init(&slot_empty[s], 4);
     }
-    for (int a = 0; a < 2; ++a) {
-      tc::mbar_init(&acc_full[a], 1);
-      tc::mbar_init(&acc_empty[a], 4);
-    }
+    tc::mbar_init(acc_full, 1);
+    tc::mbar_init(acc_empty, 4);
     tc::fence_barrier_init();
   }
   if (warp == 5) {
@@ -85,8 +84,10 @@ __global__ void __launch_bounds__(192, 2) fused_core_fwd_kernel(const __grid_con
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
-  // TMEM columns: [0, 64) W_g rows of the r gates, [64, 128) of the i gates (packed pairs), then 2 stages x (r | i) x Tc
+  // TMEM columns: [0, 64) W_g rows of the r gates, [64, 128) of the i gates (packed pairs), [128, 256) the (r | i) x Tc
+  // accumulator
   constexpr uint32_t kAccCol = 128;
+  static_assert(kAccCol + 2 * kFTc <= 256, "TMEM budget: the allocation is 256 columns");
 
   // tiles owned by this CTA: batch rows blockIdx.x, + gridDim.x, ...; n_tiles per row
   const long my_rows = (p.B - (long)blockIdx.x + gridDim.x - 1) / gridDim.x;
@@ -158,8 +159,7 @@ __global__ void __launch_bounds__(192, 2) fused_core_fwd_kernel(const __grid_con
 
     auto scan_tile = [&](long k) {
       const int s = (int)(k % kFStages);
-      const int a = (int)(k & 1);
-      const uint32_t aph = (uint32_t)(k >> 1) & 1u;
+      const uint32_t aph = (uint32_t)k & 1u;
       const int tile = (int)(k % p.n_tiles);
       const long b = (long)blockIdx.x + (k / p.n_tiles) * gridDim.x;
       const int t0 = tile * kFTc;
@@ -167,19 +167,19 @@ __global__ void __launch_bounds__(192, 2) fused_core_fwd_kernel(const __grid_con
       const int tmax = min(kFTc, p.T - t0);
       const uint8_t* sx = smem + (size_t)s * kFStageB;
       const uint8_t* sz = sx + 2 * kFSlab;
-      tc::mbar_wait(&acc_full[a], aph);
+      tc::mbar_wait(acc_full, aph);
       tc::fence_after_sync();
       __nv_bfloat16* yrow = yout + ((size_t)b * p.T + t0) * kFC + c;
 #pragma unroll 1
       for (int half = 0; half < kFTc / 32; ++half) {
         uint32_t rr[32], ii[32];
-        tc::tmem_ld_32x32(lane_addr + kAccCol + (uint32_t)(a * 2 * kFTc + half * 32), rr);
-        tc::tmem_ld_32x32(lane_addr + kAccCol + (uint32_t)(a * 2 * kFTc + kFTc + half * 32), ii);
+        tc::tmem_ld_32x32(lane_addr + kAccCol + (uint32_t)(half * 32), rr);
+        tc::tmem_ld_32x32(lane_addr + kAccCol + (uint32_t)(kFTc + half * 32), ii);
         tc::tmem_ld_wait();
-        if (half == kFTc / 32 - 1) {   // accumulator stage is in registers: the MMAs of tile k + 2 may overwrite it
+        if (half == kFTc / 32 - 1) {   // the accumulator is in registers: the MMAs of the next tile may overwrite it
           tc::fence_before_sync();
           __syncwarp();
-          if (lane == 0) tc::mbar_arrive(&acc_empty[a]);
+          if (lane == 0) tc::mbar_arrive(acc_empty);
         }
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
@@ -226,16 +226,15 @@ __global__ void __launch_bounds__(192, 2) fused_core_fwd_kernel(const __grid_con
     for (long k = 0; k < my_tiles; ++k) {
       const int s = (int)(k % kFStages);
       const uint32_t ph = (uint32_t)(k / kFStages) & 1u;
-      const int a = (int)(k & 1);
-      const uint32_t aph = (uint32_t)(k >> 1) & 1u;
+      const uint32_t aph = (uint32_t)k & 1u;
       tc::mbar_wait(&conv_done[s], ph);
-      tc::mbar_wait(&acc_empty[a], aph ^ 1u);
+      tc::mbar_wait(acc_empty, aph ^ 1u);
       tc::fence_after_sync();
       if (tc::elect_one()) {
         const uint64_t bd0 = tc::smem_desc_sw128(tc::smem_u32(smem + (size_t)s * kFStageB), 16, 1024);
 #pragma unroll
         for (int blk = 0; blk < 2; ++blk) {
-          const uint32_t d_tmem = tmem_base + kAccCol + (uint32_t)(a * 2 * kFTc + blk * kFTc);
+          const uint32_t d_tmem = tmem_base + kAccCol + (uint32_t)(blk * kFTc);
 #pragma unroll
           for (int sl = 0; sl < 2; ++sl)
 #pragma unroll
@@ -244,7 +243,7 @@ __global__ void __launch_bounds__(192, 2) fused_core_fwd_kernel(const __grid_con
                                bd0 + (uint64_t)((uint32_t)sl * (kFSlab >> 4) + (uint32_t)k4 * 2), idesc,
                                (uint32_t)((sl | k4) != 0));
         }
-        tc::umma_commit(&acc_full[a]);
+        tc::umma_commit(acc_full);
       }
       __syncwarp();
     }
