@@ -99,6 +99,19 @@ def triton_leg(B=2048, L=200, d_model=64, iters=5):
     t_bf16, _ = _events(layer_step(ours, x, gy, True), 3, iters, flush_l2)
     res.update(reference_layer_ms=t_ref, ours_layer_f32_ms=t_f32, ours_layer_bf16_ms=t_bf16,
                layer_ratio=t_ref / t_f32, layer_ratio_bf16=t_ref / t_bf16)
+
+    # inference (no_grad): the reference layer's forward vs this repo's, whose conv + gates GEMM + recurrence + z-gate is ONE
+    # tcgen05 kernel at this shape (ops.bdlru_core_fused, bf16 autocast)
+    def layer_infer(m, amp):
+        def run():
+            with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
+                m(x)
+        return run
+    ours.eval(), ref.eval()
+    i_ref, _ = _events(layer_infer(ref, False), 2, iters, flush_l2)
+    i_ours, _ = _events(layer_infer(ours, True), 3, iters, flush_l2)
+    ours.train(), ref.train()
+    res.update(reference_layer_infer_ms=i_ref, ours_layer_infer_bf16_ms=i_ours, layer_infer_ratio=i_ref / i_ours)
     # bare scan op at the reference's own contract: contiguous fp32 [B, C, Tp], power-of-two Tp
     C, Tp = 2 * d_model, 2 ** ((L - 1).bit_length())
     a = (torch.rand(B, C, Tp, device=dev) * 0.5 + 0.5)

@@ -137,8 +137,9 @@ __global__ void __launch_bounds__(192, 2) fused_core_fwd_kernel(const __grid_con
       tc::mbar_wait(&full[s], ph);
       if (USE_CONV) {
         uint8_t* sx = smem + (size_t)s * kFStageB;
+        const int rows = min(kFTc, p.T - tile * kFTc);   // rows past the end of the sequence are never read back
 #pragma unroll 1
-        for (int tb = 0; tb < kFTc; tb += 16) {   // 16 rows at a time: all loads first, so they overlap
+        for (int tb = 0; tb < rows; tb += 16) {   // 16 rows at a time: all loads first, so they overlap
           float xin[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) xin[j] = ld_bf16(sx + sw_off(tb + j, c));
@@ -170,28 +171,41 @@ __global__ void __launch_bounds__(192, 2) fused_core_fwd_kernel(const __grid_con
       tc::mbar_wait(acc_full, aph);
       tc::fence_after_sync();
       __nv_bfloat16* yrow = yout + ((size_t)b * p.T + t0) * kFC + c;
+      const int n_half = (tmax + 31) >> 5;   // a tail tile (T = 200: 8 of 64 steps) skips the halves it does not need
 #pragma unroll 1
-      for (int half = 0; half < kFTc / 32; ++half) {
+      for (int half = 0; half < n_half; ++half) {
         uint32_t rr[32], ii[32];
         tc::tmem_ld_32x32(lane_addr + kAccCol + (uint32_t)(half * 32), rr);
         tc::tmem_ld_32x32(lane_addr + kAccCol + (uint32_t)(kFTc + half * 32), ii);
         tc::tmem_ld_wait();
-        if (half == kFTc / 32 - 1) {   // the accumulator is in registers: the MMAs of the next tile may overwrite it
+        if (half == n_half - 1) {   // the accumulator is in registers: the MMAs of the next tile may overwrite it
           tc::fence_before_sync();
           __syncwarp();
           if (lane == 0) tc::mbar_arrive(acc_empty);
         }
+        // Three phases over the 32 time steps so that only the recurrence itself is a dependent chain: (1) gate math for
+        // every step (independent: the MUFU / FMA latencies overlap), leaving a_t in rr and b'_t in ii; (2) the serial
+        // h_t = a_t h_{t-1} + b'_t (one FMA per step), leaving h_t in rr; (3) z-gate and store (independent again).
+        float zg[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const int t = half * 32 + j;
-          if (t < tmax) {
-            const float xc = ld_bf16(sx + sw_off(t, c));
-            const float zv = ld_bf16(sz + sw_off(t, c));
-            const Gate g = gate_full<true>(csp, __uint_as_float(rr[j]) + br, __uint_as_float(ii[j]) + bi);
-            h = fmaf(g.a, h, g.q * g.si * xc);
-            const float yv = zv * sigmoid_t<true>(zv) * h;
-            yrow[(size_t)t * kFC] = __float2bfloat16_rn(yv);
-          }
+          const float xc = ld_bf16(sx + sw_off(t, c));
+          const float zv = ld_bf16(sz + sw_off(t, c));
+          const Gate g = gate_full<true>(csp, __uint_as_float(rr[j]) + br, __uint_as_float(ii[j]) + bi);
+          rr[j] = __float_as_uint(g.a);
+          ii[j] = __float_as_uint(g.q * g.si * xc);
+          zg[j] = zv * sigmoid_t<true>(zv);
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          if (half * 32 + j < tmax) h = fmaf(__uint_as_float(rr[j]), h, __uint_as_float(ii[j]));
+          rr[j] = __float_as_uint(h);
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int t = half * 32 + j;
+          if (t < tmax) yrow[(size_t)t * kFC] = __float2bfloat16_rn(zg[j] * __uint_as_float(rr[j]));
         }
       }
       __syncwarp();
