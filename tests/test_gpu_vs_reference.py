@@ -138,3 +138,38 @@ def test_model_loss_and_scores_match_reference_on_gpu():
         dense = q_ref.bfloat16().double() @ table.bfloat16().double().T
         dense[:, 0] = float("-inf")
         assert torch.equal(ids.long(), top(dense))
+
+
+def test_level1_adoption_unmodified_reference_module_over_the_two_shims():
+    """INTEGRATION.md level 1: the UNMODIFIED RecBLR.py with only its two imported kernels swapped for this repo's drop-ins
+    (`parallel_scan` -> csrc/scan_bct.cu, `causal_conv1d_fn` -> csrc/conv1d.cu) — loss and every parameter gradient equal
+    the same module running its own Triton scan + F.conv1d fallback."""
+    from datamining_recblr_b200.causal_conv1d import causal_conv1d_fn
+    from datamining_recblr_b200.parallel_scan import parallel_scan
+    from oracle import torch_port as TP
+    from oracle.reference_loader import FakeDataset, make_config
+    mod, ps = build_ref.load_gpu_reference()
+    n_items, L, B = 400, 50, 24
+    cfg = make_config(hidden_size=64, num_layers=2, dropout_prob=0.0, max_len=L)
+    cfg["device"] = "cuda"
+    torch.manual_seed(2)
+    model = mod.RecBLR(cfg, FakeDataset(n_items)).cuda().train()
+    seq, lens, pos = TP.synthetic_batch(B, L, n_items, seed=6)
+    inter = {"item_id_list": seq.cuda(), "item_length": lens.cuda(), "item_id": pos.cuda()}
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    res = []
+    try:
+        for scan, conv in ((ps.parallel_scan, None), (parallel_scan, causal_conv1d_fn)):
+            mod.parallel_scan, mod.causal_conv1d_fn = scan, conv
+            model.zero_grad(set_to_none=True)
+            loss = model.calculate_loss(inter)
+            loss.backward()
+            res.append((float(loss), {n: p.grad.clone() for n, p in model.named_parameters()}))
+    finally:
+        torch.backends.cudnn.allow_tf32 = tf32
+        mod.parallel_scan, mod.causal_conv1d_fn = ps.parallel_scan, None
+    assert abs(res[0][0] - res[1][0]) <= 1e-5 * abs(res[0][0])
+    for n, g in res[0][1].items():
+        den = float(g.abs().max()) + 1e-12
+        assert float((g - res[1][1][n]).abs().max()) <= 2e-3 * den, n     # the reference's own fp32 GPU path is ~1e-3 noisy
