@@ -57,6 +57,8 @@ SIGNATURES = {
     "bdlru_colsum": (_i, [_p, _i64, _i, _i64, _i, _p, _p, _sz, _p]),
     "bdlru_core_fwd_supported": (_i, [_i, _i]),
     "bdlru_core_fwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p]),
+    "bdlru_layer_fwd_supported": (_i, [_i, _i, _i, _i]),
+    "bdlru_layer_fwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _f, _p, _i, _i, _i, _i, _p]),
     "bdlru_table_adam_step": (_i, [_p, _p, _p, _p, _p, _i64, _f, _f, _f, _f, _f, _i64, _p]),
     "bdlru_fullsort_available": (_i, []),
     "bdlru_fullsort_topk_workspace_bytes": (_sz, [_i64, _i64, _i, _i]),

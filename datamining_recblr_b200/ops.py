@@ -412,6 +412,34 @@ def bdlru_core_fused(xz, conv_w, conv_b, gates_w, gates_b, Lambda, h0=None, use_
     return y
 
 
+def bdlru_layer_supported(x, C, conv_width):
+    """True when the full-chain inference kernel (csrc/fused_layer.cu) takes this layer input: bf16 contiguous [B, T, 64]."""
+    return (x.dtype == torch.bfloat16 and x.is_cuda and x.is_contiguous() and x.data_ptr() % 16 == 0 and x.dim() == 3
+            and bool(L.load().bdlru_layer_fwd_supported(int(x.shape[-1]), int(C), int(conv_width), L.BF16)))
+
+
+@torch.no_grad()
+def bdlru_layer_fused(x, in_w, conv_w, conv_b, gates_w, gates_b, Lambda, h0, out_w, ln_gamma, ln_beta, eps, use_conv=True):
+    """INFERENCE form of the first half of RecurrentLayer.forward — in-projection, conv + SiLU, gates GEMM, gate math,
+    recurrence, z-gate, out-projection, + residual, LayerNorm (RecBLR.py:140-142, 170-206) — as ONE tcgen05 kernel: reads
+    x [B, T, 64] bf16 once, writes the post-LayerNorm [B, T, 64] bf16; nothing in between touches HBM."""
+    L.require_cuda(x, in_w, gates_w, out_w)
+    B, T, D = x.shape
+    C = gates_w.shape[1]
+    bf = lambda w: w.detach().to(torch.bfloat16).contiguous()
+    fl = lambda w: w.detach().float().contiguous()
+    iw, gw, ow = bf(in_w), bf(gates_w), bf(out_w)
+    assert iw.shape == (2 * C, D) and gw.shape == (2 * C, C) and ow.shape == (D, C)
+    cw = fl(conv_w) if use_conv else None
+    cb = fl(conv_b) if use_conv else None
+    h0f = fl(h0) if h0 is not None else None
+    out = torch.empty((B, T, D), dtype=torch.bfloat16, device=x.device)
+    L.check(L.load().bdlru_layer_fwd(L.ptr(x), L.ptr(iw), L.ptr(cw), L.ptr(cb), L.ptr(gw), L.ptr(fl(gates_b)), L.ptr(fl(Lambda)),
+                                     L.ptr(h0f), L.ptr(ow), L.ptr(fl(ln_gamma)), L.ptr(fl(ln_beta)), float(eps), L.ptr(out),
+                                     B, T, D, C, L.stream_ptr(x)))
+    return out
+
+
 def bdlru_block(xz, conv_w, conv_b, gates_w, gates_b, Lambda, h0=None, use_conv=True):
     """y = silu(z) * BD-LRU(silu(conv(x))) for xz = (x | z) [B, T, 2C] — conv, gates GEMM, gate math, scan and z-gate of
     RecBLR.py:174-206 as one autograd node (see _BDLRUBlock).  conv_w [C, W], gates_w [2C, C]; autocast aware."""

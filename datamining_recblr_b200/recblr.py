@@ -275,9 +275,22 @@ class RecurrentLayer(nn.Module):
         self.layer_norm = nn.LayerNorm(d_model, eps=1e-12)
         self.ffn = FeedForward(d_model=d_model, inner_size=d_model * 4, dropout=dropout)
 
+    fused_layer = True   # inference: the whole first half as one tcgen05 kernel when the shape is the one it is built for
+
     def forward(self, input_tensor, dropout_ctx=None):
         """dropout_ctx = (seed, device step counter or None): the counter stream shared by the model's fused dropouts
         (RecBLR.forward supplies it; standalone use falls back to a host-side step count)."""
+        bm = self.behavior_modeling
+        if (self.fused_layer and not self.training and not torch.is_grad_enabled()
+                and ops.bdlru_layer_supported(input_tensor, bm.gates.weight.shape[1], bm.conv1d.weight.shape[-1])):
+            # in-projection, conv, gates GEMM, recurrence, z-gate, out-projection, residual and LayerNorm: ONE kernel
+            hidden_states = ops.bdlru_layer_fused(
+                input_tensor, bm.input.weight, bm.conv1d.weight.squeeze(1), bm.conv1d.bias, bm.gates.weight, bm.gates.bias,
+                bm.Lambda, bm.phantom_state(input_tensor.shape[1]), bm.output.weight, self.layer_norm.weight,
+                self.layer_norm.bias, self.layer_norm.eps, use_conv=not bm.disable_conv1d)
+            if not self.disable_ffn:
+                hidden_states = self.ffn(hidden_states, dropout_ctx)
+            return hidden_states
         # the layer input feeds the in-projection AND the residual: taken from one autograd node (ops.linear_tap)
         hidden_states, residual = self.behavior_modeling(input_tensor, return_tap=True)
         hidden_states = _residual_ln(self, self.layer_norm, self.dropout, hidden_states, residual, dropout_ctx, 1)

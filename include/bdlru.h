@@ -280,6 +280,18 @@ int bdlru_core_fwd_supported(int C, int dtype);
 int bdlru_core_fwd(const void* xz, const float* conv_w, const float* conv_b, const void* gates_w, const float* gates_b,
                    const float* Lambda, const float* h0, void* y, int B, int T, int C, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * The whole first half of RecurrentLayer.forward for INFERENCE (RecBLR.py:140-142 + 170-206) as one tcgen05 kernel:
+ *     out = LayerNorm(out_w (silu(z) * BD-LRU(silu(conv(x)), gates_w . + gates_b)) + X) * ln_gamma + ln_beta,  (x | z) = in_w X
+ * X [B, T, d_model] bf16 contiguous -> out [B, T, d_model] bf16; in_w [2C, d_model], gates_w [2C, C], out_w [d_model, C] bf16
+ * row-major (nn.Linear layout), the rest fp32; conv_w / conv_b NULL: no conv; h0 may be NULL.  Built for d_model 64, C 128,
+ * conv width 4 (bdlru_layer_fwd_supported).  Nothing between X and out touches HBM.
+ * ------------------------------------------------------------------------------------------- */
+int bdlru_layer_fwd_supported(int d_model, int C, int conv_width, int dtype);
+int bdlru_layer_fwd(const void* x, const void* in_w, const float* conv_w, const float* conv_b, const void* gates_w,
+                    const float* gates_b, const float* Lambda, const float* h0, const void* out_w, const float* ln_gamma,
+                    const float* ln_beta, float eps, void* out, int B, int T, int d_model, int C, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
