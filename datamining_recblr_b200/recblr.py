@@ -275,13 +275,19 @@ class RecurrentLayer(nn.Module):
         self.layer_norm = nn.LayerNorm(d_model, eps=1e-12)
         self.ffn = FeedForward(d_model=d_model, inner_size=d_model * 4, dropout=dropout)
 
-    fused_layer = True   # inference: the whole first half as one tcgen05 kernel when the shape is the one it is built for
+    # Inference: the whole first half as ONE tcgen05 kernel (csrc/fused_layer.cu) when the shape is the one it is built for
+    # and the problem is small enough to be launch-bound (measured on B200: at 4 096 x 50 tokens the eager eval forward
+    # drops from 0.95 to 0.80 ms; in steady-state throughput its three serialised MMA phases per 32-step tile make it 0.86-0.90x
+    # of "cuBLAS projections + fused core kernel + add_ln", so larger problems keep that path).
+    fused_layer = True
+    fused_layer_max_tokens = 1 << 18
 
     def forward(self, input_tensor, dropout_ctx=None):
         """dropout_ctx = (seed, device step counter or None): the counter stream shared by the model's fused dropouts
         (RecBLR.forward supplies it; standalone use falls back to a host-side step count)."""
         bm = self.behavior_modeling
         if (self.fused_layer and not self.training and not torch.is_grad_enabled()
+                and input_tensor.shape[0] * input_tensor.shape[1] <= self.fused_layer_max_tokens
                 and ops.bdlru_layer_supported(input_tensor, bm.gates.weight.shape[1], bm.conv1d.weight.shape[-1])):
             # in-projection, conv, gates GEMM, recurrence, z-gate, out-projection, residual and LayerNorm: ONE kernel
             hidden_states = ops.bdlru_layer_fused(

@@ -35,3 +35,30 @@ for (B, T) in [(4096, 50), (2048, 200), (4096, 200), (16384, 200), (512, 1024)]:
     ts, _, _ = time_graph(mk, separate, 8 * E, iters=5)
     print(f"B={B} T={T} C={C}: fused {tf:.4f} ms ({3 * E / tf / 1e6:.0f} GB/s of its 3-unit traffic, "
           f"{B * T * C / tf / 1e6:.1f} G elem/s)   separate kernels {ts:.4f} ms   speed-up {ts / tf:.2f}x   (R={R})")
+
+# ---- the whole first half of RecurrentLayer (in-proj .. residual LayerNorm): ONE kernel vs the module's separate path
+from datamining_recblr_b200.recblr import RecurrentLayer  # noqa: E402
+
+D = 64
+layer = RecurrentLayer(d_model=D, d_conv=4, expand=2, dropout=0.0, num_layers=1, bd_lru_only=False, disable_conv1d=False,
+                       disable_ffn=True).cuda().eval()
+for (B, T) in [(4096, 50), (2048, 200), (4096, 200), (16384, 200)]:
+    E = B * T * D * 2
+
+    def mkx():
+        return torch.randn(B, T, D, device=dev).to(torch.bfloat16)
+
+    def run_layer(fused_layer, fused_core):
+        def run(x):
+            layer.fused_layer = fused_layer
+            layer.behavior_modeling.fused_core = fused_core
+            with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+                layer(x)
+        return run
+
+    t_full, _, R = time_graph(mkx, run_layer(True, True), 4 * E, iters=5)
+    t_core, _, _ = time_graph(mkx, run_layer(False, True), 16 * E, iters=5)
+    t_sep, _, _ = time_graph(mkx, run_layer(False, False), 30 * E, iters=5)
+    print(f"layer first half B={B} T={T} D={D}: one kernel {t_full:.4f} ms ({2 * E / t_full / 1e6:.0f} GB/s of its 2 D-wide units, "
+          f"{B * T * 128 / t_full / 1e6:.1f} G elem/s) | cuBLAS proj + fused core + add_ln {t_core:.4f} ms | all separate "
+          f"{t_sep:.4f} ms | speed-up {t_sep / t_full:.2f}x / {t_core / t_full:.2f}x")
