@@ -116,6 +116,18 @@ struct IOV<float, 4> : IO<float> {};
 template <>
 struct IOV<__nv_bfloat16, 4> : IO<__nv_bfloat16> {};
 template <>
+struct IOV<__nv_bfloat16, 2> {
+  static constexpr int BYTES = 4;
+  __device__ __forceinline__ static void load(const void* p, float (&v)[2]) {
+    const uint32_t u = *reinterpret_cast<const uint32_t*>(p);
+    v[0] = __uint_as_float(u << 16); v[1] = __uint_as_float(u & 0xffff0000u);
+  }
+  __device__ __forceinline__ static void store(void* p, const float (&v)[2]) {
+    const __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]);
+    *reinterpret_cast<uint32_t*>(p) = *reinterpret_cast<const uint32_t*>(&a);
+  }
+};
+template <>
 struct IOV<__nv_bfloat16, 8> {
   static constexpr int BYTES = 16;
   __device__ __forceinline__ static void load(const void* p, float (&v)[8]) {

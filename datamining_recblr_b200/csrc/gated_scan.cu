@@ -466,6 +466,237 @@ __global__ void __launch_bounds__(256) gscan_bwd_kernel(const GScanParams p) {
   if (p.part_dh0 && ts == 0) st_vec<V>(p.part_dh0 + ((size_t)blockIdx.x * p.tcn + tc) * V, dh0_acc);
 }
 
+// ------------------------------------------------------------------------------------------ sequential variant
+// Large B*C (the training shapes: 8 192 x 256, 2 048 x 128): there are enough (batch row, channel vector) pairs to fill the
+// machine with ONE thread per pair walking the whole sequence — no time slices, no chunk aggregates, no second pass, no
+// shared-memory staging, no block barrier.  ncu on the chunked bf16 kernels showed them issue-bound (62.6 thread
+// instructions per element forward against a budget of 66 at full HBM rate, a quarter of the stall samples on the
+// aggregate walk and its barrier); this form needs ~35.  Lanes of a warp hold consecutive channel vectors of one row, so
+// every step is one coalesced row segment per array; U steps are loaded before they are consumed (U x 3..6 independent
+// loads in flight per thread) and occupancy hides the rest.  GATED, bf16 only; everything else stays on the chunked kernels.
+template <typename T, int V, int U, bool HAS_Z>
+__global__ void __launch_bounds__(256) gscan_seq_fwd_kernel(const GScanParams p) {
+  using IOx = IOV<T, V>;
+  constexpr bool FAST = sizeof(T) == 2;
+  const int lanes = p.C / V, rpb = (int)blockDim.x / lanes;
+  const int li = (int)threadIdx.x % lanes, rw = (int)threadIdx.x / lanes;
+  const int c = li * V;
+  const long xrb = row_bytes<T>(p.x), rrb = row_bytes<T>(p.r), irb = row_bytes<T>(p.i), zrb = row_bytes<T>(p.z);
+  const long hrb = row_bytes<T>(p.h), yrb = row_bytes<T>(p.y);
+  float csp[V];
+#pragma unroll
+  for (int e = 0; e < V; ++e) csp[e] = softplus_acc(p.lambda[c + e]);
+  for (long b = (long)blockIdx.x * rpb + rw; b < p.B; b += (long)gridDim.x * rpb) {
+    float h[V];
+#pragma unroll
+    for (int e = 0; e < V; ++e) h[e] = p.h0 ? p.h0[b * p.h0_bs + c + e] : 0.f;
+    const unsigned char* px = at<T>(p.x, b, 0, c);
+    const unsigned char* pr = at<T>(p.r, b, 0, c);
+    const unsigned char* pi = at<T>(p.i, b, 0, c);
+    const unsigned char* pz = HAS_Z ? at<T>(p.z, b, 0, c) : nullptr;
+    unsigned char* ph = const_cast<unsigned char*>(at<T>(p.h, b, 0, c));
+    unsigned char* py = HAS_Z ? const_cast<unsigned char*>(at<T>(p.y, b, 0, c)) : nullptr;
+    for (int t0 = 0; t0 < p.T; t0 += U) {
+      float xv[U][V], rv[U][V], iv[U][V], zv[U][V];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (t0 + u < p.T) {
+          IOx::load(px + (long)(t0 + u) * xrb, xv[u]);
+          IOx::load(pr + (long)(t0 + u) * rrb, rv[u]);
+          IOx::load(pi + (long)(t0 + u) * irb, iv[u]);
+          if (HAS_Z) IOx::load(pz + (long)(t0 + u) * zrb, zv[u]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (t0 + u < p.T) {
+          float hv[V], yv[V];
+#pragma unroll
+          for (int e = 0; e < V; ++e) {
+            const Gate g = gate_full<FAST>(csp[e], rv[u][e], iv[u][e]);
+            h[e] = fmaf(g.a, h[e], g.q * g.si * xv[u][e]);
+            hv[e] = h[e];
+            if (HAS_Z) yv[e] = zv[u][e] * sigmoid_t<FAST>(zv[u][e]) * h[e];
+          }
+          IOx::store(ph + (long)(t0 + u) * hrb, hv);
+          if (HAS_Z) IOx::store(py + (long)(t0 + u) * yrb, yv);
+        }
+      }
+    }
+  }
+}
+
+template <typename T, int V, int U, bool HAS_Z>
+__global__ void __launch_bounds__(256) gscan_seq_bwd_kernel(const GScanParams p) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  using IOx = IOV<T, V>;
+  constexpr bool FAST = sizeof(T) == 2;
+  const int lanes = p.C / V, rpb = (int)blockDim.x / lanes;
+  const int li = (int)threadIdx.x % lanes, rw = (int)threadIdx.x / lanes;
+  const int c = li * V;
+  const long xrb = row_bytes<T>(p.x), rrb = row_bytes<T>(p.r), irb = row_bytes<T>(p.i), zrb = row_bytes<T>(p.z);
+  const long hrb = row_bytes<T>(p.h), grb = row_bytes<T>(p.g);
+  const long dxrb = row_bytes<T>(p.dx), drrb = row_bytes<T>(p.dr), dirb = row_bytes<T>(p.di), dzrb = row_bytes<T>(p.dz);
+  float csp[V], dc_acc[V], dh0_acc[V];
+#pragma unroll
+  for (int e = 0; e < V; ++e) {
+    csp[e] = softplus_acc(p.lambda[c + e]);
+    dc_acc[e] = dh0_acc[e] = 0.f;
+  }
+  for (long b = (long)blockIdx.x * rpb + rw; b < p.B; b += (long)gridDim.x * rpb) {
+    float u_[V], h0v[V];
+#pragma unroll
+    for (int e = 0; e < V; ++e) {
+      u_[e] = 0.f;
+      h0v[e] = p.h0 ? p.h0[b * p.h0_bs + c + e] : 0.f;
+    }
+    const unsigned char* px = at<T>(p.x, b, 0, c);
+    const unsigned char* pr = at<T>(p.r, b, 0, c);
+    const unsigned char* pi = at<T>(p.i, b, 0, c);
+    const unsigned char* pg = at<T>(p.g, b, 0, c);
+    const unsigned char* pz = HAS_Z ? at<T>(p.z, b, 0, c) : nullptr;
+    const unsigned char* ph = at<T>(p.h, b, 0, c);
+    unsigned char* pdx = const_cast<unsigned char*>(at<T>(p.dx, b, 0, c));
+    unsigned char* pdr = const_cast<unsigned char*>(at<T>(p.dr, b, 0, c));
+    unsigned char* pdi = const_cast<unsigned char*>(at<T>(p.di, b, 0, c));
+    unsigned char* pdz = HAS_Z ? const_cast<unsigned char*>(at<T>(p.dz, b, 0, c)) : nullptr;
+    // time chunks in reverse: chunk k covers steps [k*U, k*U + U)
+    for (int t0 = ((p.T - 1) / U) * U; t0 >= 0; t0 -= U) {
+      float xv[U][V], rv[U][V], iv[U][V], gv[U][V], zv[U][V], hv[U + 1][V];   // hv[j] = h_{t0 + j - 1}
+#pragma unroll
+      for (int j = 0; j <= U; ++j) {
+        const int t = t0 + j - 1;
+        if (t < 0) {
+#pragma unroll
+          for (int e = 0; e < V; ++e) hv[j][e] = h0v[e];
+        } else if (t < p.T) {
+          IOx::load(ph + (long)t * hrb, hv[j]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (t0 + u < p.T) {
+          IOx::load(px + (long)(t0 + u) * xrb, xv[u]);
+          IOx::load(pr + (long)(t0 + u) * rrb, rv[u]);
+          IOx::load(pi + (long)(t0 + u) * irb, iv[u]);
+          IOx::load(pg + (long)(t0 + u) * grb, gv[u]);
+          if (HAS_Z) IOx::load(pz + (long)(t0 + u) * zrb, zv[u]);
+        }
+      }
+#pragma unroll
+      for (int u = U - 1; u >= 0; --u) {
+        if (t0 + u < p.T) {
+          float dxv[V], drv[V], div[V], dzv[V];
+#pragma unroll
+          for (int e = 0; e < V; ++e) {
+            float g = gv[u][e];
+            if (HAS_Z) {
+              const float sz = sigmoid_t<FAST>(zv[u][e]);
+              dzv[e] = g * hv[u + 1][e] * silu_grad_f(zv[u][e], sz);
+              g *= zv[u][e] * sz;
+            }
+            float sr;
+            const float a = gate_alpha<FAST>(csp[e], rv[u][e], sr);
+            const float si = sigmoid_t<FAST>(iv[u][e]);
+            const float v = one_minus_a2<FAST>(csp[e], sr, a);
+            const float rq = rsqrt_ftz(v), q = v * rq;
+            const float d = g + u_[e];
+            const float dbeta = d * xv[u][e];
+            dxv[e] = d * q * si;
+            div[e] = dbeta * q * si * (1.0f - si);
+            const float da = fmaf(hv[u][e], d, -dbeta * si * a * rq);
+            const float daa = da * a;
+            drv[e] = -csp[e] * daa * sr * (1.0f - sr);
+            dc_acc[e] = fmaf(-daa, sr, dc_acc[e]);
+            u_[e] = a * d;
+          }
+          IOx::store(pdx + (long)(t0 + u) * dxrb, dxv);
+          IOx::store(pdr + (long)(t0 + u) * drrb, drv);
+          IOx::store(pdi + (long)(t0 + u) * dirb, div);
+          if (HAS_Z) IOx::store(pdz + (long)(t0 + u) * dzrb, dzv);
+        }
+      }
+    }
+    if (p.dh0) {
+#pragma unroll
+      for (int e = 0; e < V; ++e) p.dh0[b * p.C + c + e] = u_[e];
+    } else {
+#pragma unroll
+      for (int e = 0; e < V; ++e) dh0_acc[e] += u_[e];
+    }
+  }
+  // per-CTA partial rows [C] of dL/dc and (broadcast) dh0: reduce over the rpb batch rows of the block
+  float* red = reinterpret_cast<float*>(smem);   // [2][blockDim.x][V]
+#pragma unroll
+  for (int e = 0; e < V; ++e) {
+    red[(size_t)threadIdx.x * V + e] = dc_acc[e];
+    red[(size_t)(blockDim.x + threadIdx.x) * V + e] = dh0_acc[e];
+  }
+  __syncthreads();
+  if (rw == 0) {
+#pragma unroll
+    for (int e = 0; e < V; ++e) {
+      float s0 = 0.f, s1 = 0.f;
+      for (int j = 0; j < rpb; ++j) {
+        s0 += red[(size_t)(j * lanes + li) * V + e];
+        s1 += red[(size_t)(blockDim.x + j * lanes + li) * V + e];
+      }
+      p.part_dc[(size_t)blockIdx.x * p.C + c + e] = s0;
+      if (p.part_dh0) p.part_dh0[(size_t)blockIdx.x * p.C + c + e] = s1;
+    }
+  }
+}
+
+// sequential variant: which vector width (0 = use the chunked kernels)
+static int seq_vector_width(const GScanParams& p) {
+#ifdef BDLRU_GSCAN_NO_SEQ
+  return 0;
+#endif
+  const long min_warps = 4096;   // ~28 warps per SM
+  for (int V : {4, 2}) {
+    if (p.C % V) continue;
+    const int lanes = p.C / V;
+    if (lanes > 256 || 256 % lanes) continue;
+    if ((long)p.B * lanes / 32 >= min_warps) return V;
+  }
+  return 0;
+}
+
+template <typename T, int V, bool HAS_Z>
+static int launch_seq_fwd(GScanParams& p, cudaStream_t st) {
+  const int lanes = p.C / V, rpb = 256 / lanes;
+  long grid = ((long)p.B + rpb - 1) / rpb;
+  const long cap = (long)sm_count() * 8;
+  if (grid > cap) grid = cap;
+  gscan_seq_fwd_kernel<T, V, 4, HAS_Z><<<(unsigned)grid, 256, 0, st>>>(p);
+  BDLRU_LAUNCHED();
+  return BDLRU_OK;
+}
+
+template <typename T, int V, bool HAS_Z>
+static int launch_seq_bwd(GScanParams& p, float* dLambda, float* dh0_out, void* ws, size_t ws_bytes, cudaStream_t st) {
+  const int lanes = p.C / V, rpb = 256 / lanes;
+  long grid = ((long)p.B + rpb - 1) / rpb;
+  const long cap = (long)sm_count() * 6;
+  if (grid > cap) grid = cap;
+  const size_t need = 2 * (size_t)grid * p.C * sizeof(float);
+  BDLRU_REQUIRE(ws && ws_bytes >= need, "gated_scan_bwd: workspace too small (%zu < %zu)", ws_bytes, need);
+  p.part_dc = reinterpret_cast<float*>(ws);
+  const bool bcast_h0 = dh0_out && p.h0_bs == 0;
+  p.part_dh0 = bcast_h0 ? p.part_dc + (size_t)grid * p.C : nullptr;
+  p.dh0 = (dh0_out && !bcast_h0) ? dh0_out : nullptr;
+  const size_t smem = 2 * 256 * (size_t)V * sizeof(float);
+  gscan_seq_bwd_kernel<T, V, 2, HAS_Z><<<(unsigned)grid, 256, smem, st>>>(p);
+  BDLRU_LAUNCHED();
+  int rc = launch_colsum(p.part_dc, (int)grid, p.C, p.C, COLSUM_SIGMOID, dLambda, nullptr, 0, p.lambda, st);
+  if (rc) return rc;
+  if (bcast_h0) {
+    rc = launch_colsum(p.part_dh0, (int)grid, p.C, p.C, COLSUM_SPLIT, dh0_out, nullptr, p.C, nullptr, st);
+    if (rc) return rc;
+  }
+  return BDLRU_OK;
+}
+
 // ------------------------------------------------------------------------------------------ host side
 struct Tiling {
   int tcn, NS, NT, n_ctile, n_iter, n_units, grid;
@@ -543,6 +774,11 @@ static int launch_fwd_v(GScanParams& p, cudaStream_t st) {
 
 template <typename T, bool GATED, bool HAS_Z>
 static int launch_fwd(GScanParams& p, cudaStream_t st) {
+  if constexpr (sizeof(T) == 2 && GATED) {
+    const int V = seq_vector_width(p);
+    if (V == 4) return launch_seq_fwd<T, 4, HAS_Z>(p, st);
+    if (V == 2) return launch_seq_fwd<T, 2, HAS_Z>(p, st);
+  }
   if constexpr (sizeof(T) == 2 && BDLRU_GSCAN_WIDE) {
     if (p.C % 8 == 0 && p.wide_ok) return launch_fwd_v<T, 8, 2, GATED, HAS_Z>(p, st);
   }
@@ -586,6 +822,11 @@ static int launch_bwd_v(GScanParams& p, float* dLambda, float* dh0_out, void* ws
 
 template <typename T, bool GATED, bool HAS_Z>
 static int launch_bwd(GScanParams& p, float* dLambda, float* dh0_out, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if constexpr (sizeof(T) == 2 && GATED) {
+    const int V = seq_vector_width(p);
+    if (V == 4) return launch_seq_bwd<T, 4, HAS_Z>(p, dLambda, dh0_out, ws, ws_bytes, st);
+    if (V == 2) return launch_seq_bwd<T, 2, HAS_Z>(p, dLambda, dh0_out, ws, ws_bytes, st);
+  }
   if constexpr (sizeof(T) == 2 && BDLRU_GSCAN_WIDE) {
     if (p.C % 8 == 0 && p.wide_ok) return launch_bwd_v<T, 8, 2, GATED, HAS_Z>(p, dLambda, dh0_out, ws, ws_bytes, st);
   }
@@ -612,7 +853,9 @@ using namespace bdlru;
 extern "C" BDLRU_API size_t bdlru_gated_scan_bwd_workspace_bytes(int B, int T, int C) {
   (void)B; (void)T;
   // 2 partial arrays of [grid, V*tcn] floats; grid <= 32 CTAs/SM * SMs, V*tcn <= 256
-  return 2 * (size_t)32 * (size_t)sm_count() * 256 * sizeof(float) + 2 * (size_t)(C / 4 + 1) * 256 * sizeof(float);
+  const size_t chunked = 2 * (size_t)32 * (size_t)sm_count() * 256 * sizeof(float) + 2 * (size_t)(C / 4 + 1) * 256 * sizeof(float);
+  const size_t seq = 2 * (size_t)6 * (size_t)sm_count() * (size_t)C * sizeof(float);   // sequential variant: [grid, C] x 2
+  return chunked > seq ? chunked : seq;
 }
 
 extern "C" BDLRU_API int bdlru_gated_scan_fwd(bdlru_view xp, bdlru_view r, bdlru_view i, const float* Lambda, const float* h0,

@@ -63,7 +63,9 @@ def _gated_inputs(rng, B, T, C, dtype):
 
 
 @pytest.mark.parametrize("B,T,C", [(2, 1, 4), (3, 5, 8), (2, 50, 128), (2, 200, 128), (1, 37, 64), (2, 130, 256),
-                                   (3, 64, 12), (5, 33, 192), (160, 50, 128), (2, 1000, 64)])
+                                   (3, 64, 12), (5, 33, 192), (160, 50, 128), (2, 1000, 64),
+                                   # large B*C: the sequential bf16 variant (one thread per (row, channel vector)), V = 4 / 2
+                                   (4096, 9, 128), (2048, 6, 128), (4100, 1, 128), (1024, 11, 256)])
 @pytest.mark.parametrize("h0_mode", ["none", "bcast", "batch"])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_gated_scan(B, T, C, h0_mode, dtype):
@@ -99,7 +101,8 @@ def test_gated_scan(B, T, C, h0_mode, dtype):
         assert rel_err(th0.grad, a[:, 0, :] * dtok[:, :, 0]) <= tol
 
 
-@pytest.mark.parametrize("B,T,C", [(2, 5, 8), (2, 50, 128), (3, 200, 128), (2, 67, 64)])
+@pytest.mark.parametrize("B,T,C", [(2, 5, 8), (2, 50, 128), (3, 200, 128), (2, 67, 64), (4096, 9, 128), (2048, 6, 128),
+                                   (8192, 3, 64), (1024, 5, 256)])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_gated_scan_fused_zgate(B, T, C, dtype):
     rng = np.random.default_rng(7 + T)
