@@ -648,8 +648,12 @@ __global__ void __launch_bounds__(256) gscan_seq_bwd_kernel(const GScanParams p)
 }
 
 // sequential variant: which vector width (0 = use the chunked kernels)
+// Measured on B200 (tools/scan_bench.py, bf16): SLOWER than the chunked kernels — 2 048 x 200 x 128 fwd+bwd 0.68 vs 0.35 ms,
+// 8 192 x 200 x 256 (z-gated) fwd 1.30 vs 1.10 ms, bwd 2.81 vs 2.24 ms: with 94-128 registers per thread only 16-20 warps
+// per SM are resident and each walks its row with dependent strided loads; the chunked kernels' cp.async staging hides
+// that latency better than occupancy does.  Kept as a build-time variant (-DBDLRU_GSCAN_SEQ), parity-tested, off.
 static int seq_vector_width(const GScanParams& p) {
-#ifdef BDLRU_GSCAN_NO_SEQ
+#ifndef BDLRU_GSCAN_SEQ
   return 0;
 #endif
   const long min_warps = 4096;   // ~28 warps per SM
