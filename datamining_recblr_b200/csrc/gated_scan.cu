@@ -707,7 +707,7 @@ struct Tiling {
 };
 
 template <int S, int V>
-static Tiling make_tiling(int B, int T, int C) {
+static Tiling make_tiling(int B, int T, int C, int esize) {
   Tiling t;
   const int cvec = C / V;
   t.tcn = 1;
@@ -716,6 +716,11 @@ static Tiling make_tiling(int B, int T, int C) {
   // time slices per CTA: enough to cover T when it is short, at most 256 threads / 32 slices
   int ns = 256 / t.tcn;
   if (ns > 32) ns = 32;  // tcn < 8 (C/4 not a multiple of 8): fewer threads rather than a long combine loop
+  // bf16 I/O is issue-bound (half the bytes, the same instructions): smaller CTAs = a shorter aggregate walk and cheaper
+  // barrier per element, more CTAs per SM.  Measured on B200 (tools/scan_bench.py, S1 fwd+bwd, fraction of HBM peak):
+  // 2 048 x 200 x 128: NS 8 / 4 / 2 = 0.54 / 0.63 / 0.58;  256 x 4096 x 256: 0.53 / 0.58 / 0.50;  8 192 x 200 x 256 (z-gated)
+  // fwd 0.69 / 0.76 / 0.82, bwd 0.57 / 0.60 / 0.63.  fp32 I/O (0.82-0.95) is bandwidth-bound and keeps 8.
+  if (esize == 2 && t.tcn == 32) ns = ((long)B * t.n_ctile >= 8192) ? 2 : 4;
   static const int force_ns = tuning_env("BDLRU_GSCAN_NS");
   if (force_ns > 0 && force_ns < ns) ns = force_ns;
   t.NS = ns;
@@ -754,7 +759,7 @@ static void set_wide(GScanParams& p) {
 // per thread and iteration, same register footprint, half the memory instructions), else 4 x 4.
 template <typename T, int V, int kS, bool GATED, bool HAS_Z>
 static int launch_fwd_v(GScanParams& p, cudaStream_t st) {
-  Tiling t = make_tiling<kS, V>(p.B, p.T, p.C);
+  Tiling t = make_tiling<kS, V>(p.B, p.T, p.C, (int)sizeof(T));
   p.tcn = t.tcn; p.NS = t.NS; p.n_ctile = t.n_ctile; p.n_iter = t.n_iter; p.n_units = t.n_units;
   constexpr int NARR = (GATED ? 3 : 2) + (HAS_Z ? 1 : 0);
   const size_t smem = 2 * (size_t)NARR * kS * t.NT * IOV<T, V>::BYTES + 4 * (size_t)t.NT * V * sizeof(float);
@@ -791,7 +796,7 @@ static int launch_fwd(GScanParams& p, cudaStream_t st) {
 
 template <typename T, int V, int kS, bool GATED, bool HAS_Z>
 static int launch_bwd_v(GScanParams& p, float* dLambda, float* dh0_out, void* ws, size_t ws_bytes, cudaStream_t st) {
-  Tiling t = make_tiling<kS, V>(p.B, p.T, p.C);
+  Tiling t = make_tiling<kS, V>(p.B, p.T, p.C, (int)sizeof(T));
   p.tcn = t.tcn; p.NS = t.NS; p.n_ctile = t.n_ctile; p.n_iter = t.n_iter; p.n_units = t.n_units;
   constexpr int NH = kS + (HAS_Z ? 1 : 0);
   constexpr int NVEC = (GATED ? 4 : 2) * kS + NH + (HAS_Z ? kS : 0);
