@@ -62,6 +62,10 @@ constexpr bool kDeThreeGroups = BDLRU_CE_DE_THREE_GROUPS != 0;
 #define BDLRU_CE_DE_AUGMENT 1
 #endif
 constexpr bool kDeAugment = BDLRU_CE_DE_AUGMENT != 0;
+#ifndef BDLRU_CE_DE_EARLY_X
+#define BDLRU_CE_DE_EARLY_X 1
+#endif
+constexpr bool kDeEarlyX = BDLRU_CE_DE_EARLY_X != 0;
 
 struct BwdParams {
   const void* X;        // [n_x, D] bf16 rows owned by CTAs
@@ -92,6 +96,14 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ C
   // the auxiliary matrix behind tmL, of which one K step is used) — so the accumulator already holds l - lse and the softmax
   // loop needs neither a shared-memory read nor an FFMA per element (it was latency-bound on exactly those).
   constexpr bool AUG = kDeAugment && MODE == MODE_DE;
+  // dE pass: a row block is only ~86 tiles long, so the hand-over between row blocks (drain dX, fetch the next X rows,
+  // refill the GEMM1 -> softmax -> GEMM2 pipeline: ~6 us of a 74 us block, measured by sweeping the user count) matters.
+  // With EARLY_X the softmax warps prefetch their share of the NEXT block's X rows into registers during the current block
+  // (cp.async into a thread-private shared-memory slot: holding them in registers cost 4 % of the steady state)
+  // and store them into TMEM as soon as the last GEMM1 of the current block has completed — before they drain dX — so the
+  // global-load latency and the first GEMM1s of the next block overlap the drain.
+  constexpr bool EARLY_X = kDeEarlyX && MODE == MODE_DE;
+  constexpr int XPF = 4;   // the prefetch slot holds XPF 8-column groups of packed X per thread (D <= 64 * NSTG)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -112,7 +124,9 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ C
   uint64_t* p_empty = p_full + kBwdMaxAcc;
   uint64_t* x_full = p_empty + kBwdMaxAcc;
   uint64_t* dx_full = x_full + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dx_full + 1);
+  uint64_t* dx_empty = dx_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dx_empty + 1);
+  uint4* x_stage = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(bars) + 512);   // EARLY_X: [2 * XPF][128 * NG] x 16 B
 
   const uint32_t x_cols = (uint32_t)(p.D >> 1) + (AUG ? 8u : 0u);
   const uint32_t dx_col = x_cols;
@@ -134,6 +148,7 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ C
     }
     tc::mbar_init(x_full, 4 * NG);
     tc::mbar_init(dx_full, 1);
+    tc::mbar_init(dx_empty, 4 * NG);
     tc::fence_barrier_init();
   }
   if (warp == 0) {
@@ -208,9 +223,13 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ C
     // ===================================================================== GEMM2 issuer:  dX += P(t) Y(t)
     const uint32_t idesc2 = tc::idesc_bf16_f32(kRows, p.D, 0, 1);  // B is MN-major in GEMM2
     long g = 0;
-    for (long w = blockIdx.x; w < n_work; w += gridDim.x) {
+    uint32_t wi = 0;
+    for (long w = blockIdx.x; w < n_work; w += gridDim.x, ++wi) {
       const int split = (int)(w / p.row_blocks);
       const long t0 = p.tiles_total * split / p.splits, t1 = p.tiles_total * (split + 1) / p.splits;
+      // the softmax warps of an early-X pass (below) hand the next row block to GEMM1 BEFORE they drain dX: the first
+      // GEMM2 of that block (accumulate = 0) must not start until the drain has read the accumulator
+      if (EARLY_X && wi > 0) tc::mbar_wait(dx_empty, (wi - 1) & 1u);
       for (long t = t0; t < t1; ++t, ++g) {
         const int s = (int)(g % p.stages);
         const int b = (int)(g % NSTG);
@@ -249,33 +268,81 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ C
     long g = 0;
     uint32_t wi = 0;
     long long tq_wait_s = 0, tq_math = 0, tq_wait_p = 0, tq_st = 0, tq_n = 0;
+    long long tb_x = 0, tb_wait_dx = 0, tb_drain = 0, tb_head = 0, tb_n = 0;
     const long long tq_begin = FS_CLOCK();
     const int xj0 = ((p.D >> 4) * grp) / NG, xj1 = ((p.D >> 4) * (grp + 1)) / NG;  // 8-column groups of X of this warp group
+    // this thread's row of X -> TMEM (packed bf16 pairs, channel 2j in the low half); columns split over the groups
+    auto x_publish = [&]() {
+      if (AUG && grp == 0) {  // augmented K elements D .. D+15 of every X row: 1, 1, 1, 0, ... (bf16 1.0 = 0x3F80)
+        const uint32_t ones[8] = {0x3F803F80u, 0x00003F80u, 0u, 0u, 0u, 0u, 0u, 0u};
+        tc::tmem_st_32x32_x8(lane_addr + (uint32_t)(p.D >> 1), ones);
+      }
+      tc::tmem_st_wait();
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(x_full);
+    };
+    auto x_direct = [&](long xr_row) {
+      const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.X) + xr_row * p.D);
+      for (int j = xj0; j < xj1; ++j) {
+        uint4 lo = make_uint4(0, 0, 0, 0), hi = lo;
+        if (xr_row < p.n_x) {
+          lo = src[2 * j];
+          hi = src[2 * j + 1];
+        }
+        const uint32_t wv[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+        tc::tmem_st_32x32_x8(lane_addr + (uint32_t)j * 8, wv);
+      }
+      x_publish();
+    };
+    const bool use_pf = EARLY_X && NSTG <= 2 && (xj1 - xj0) <= XPF;
+    uint4* my_stage = x_stage + (threadIdx.x - 96);   // slot k of this thread: my_stage[k * 128 * NG] (conflict-free)
+    auto x_fetch = [&](long xr_row) {
+      const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.X) + xr_row * p.D);
+#pragma unroll
+      for (int jj = 0; jj < XPF; ++jj) {
+        const int j = xj0 + jj;
+        if (j < xj1) {
+          if (xr_row < p.n_x) {
+            cp_async<16>(my_stage + (2 * jj) * (128 * NG), src + 2 * j);
+            cp_async<16>(my_stage + (2 * jj + 1) * (128 * NG), src + 2 * j + 1);
+          } else {
+            my_stage[(2 * jj) * (128 * NG)] = my_stage[(2 * jj + 1) * (128 * NG)] = make_uint4(0, 0, 0, 0);
+          }
+        }
+      }
+      cp_async_commit();
+    };
+    auto x_store = [&]() {
+      cp_async_wait<0>();
+#pragma unroll
+      for (int jj = 0; jj < XPF; ++jj) {
+        const int j = xj0 + jj;
+        if (j < xj1) {
+          const uint4 lo = my_stage[(2 * jj) * (128 * NG)], hi = my_stage[(2 * jj + 1) * (128 * NG)];
+          const uint32_t wv[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+          tc::tmem_st_32x32_x8(lane_addr + (uint32_t)j * 8, wv);
+        }
+      }
+      x_publish();
+    };
     for (long w = blockIdx.x; w < n_work; w += gridDim.x, ++wi) {
       const long rb = w % p.row_blocks;
       const int split = (int)(w / p.row_blocks);
       const long t0 = p.tiles_total * split / p.splits, t1 = p.tiles_total * (split + 1) / p.splits;
       const long xrow = rb * kRows + row;
-      {  // this thread's row of X -> TMEM (packed bf16 pairs, channel 2j in the low half); columns split over groups
-        const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.X) + xrow * p.D);
-        for (int j = xj0; j < xj1; ++j) {
-          uint4 lo = make_uint4(0, 0, 0, 0), hi = lo;
-          if (xrow < p.n_x) {
-            lo = src[2 * j];
-            hi = src[2 * j + 1];
-          }
-          const uint32_t wv[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
-          tc::tmem_st_32x32_x8(lane_addr + (uint32_t)j * 8, wv);
+      const long w_next = w + gridDim.x;
+      const long long b_head0 = FS_CLOCK();
+      if (!use_pf) {
+        x_direct(xrow);
+      } else {
+        if (wi == 0) {
+          x_fetch(xrow);
+          x_store();
         }
-        if (AUG && grp == 0) {  // augmented K elements D .. D+15 of every X row: 1, 1, 1, 0, ... (bf16 1.0 = 0x3F80)
-          const uint32_t ones[8] = {0x3F803F80u, 0x00003F80u, 0u, 0u, 0u, 0u, 0u, 0u};
-          tc::tmem_st_32x32_x8(lane_addr + (uint32_t)(p.D >> 1), ones);
-        }
-        tc::tmem_st_wait();
-        tc::fence_before_sync();
-        __syncwarp();
-        if (lane == 0) tc::mbar_arrive(x_full);
+        if (w_next < n_work) x_fetch((w_next % p.row_blocks) * kRows + row);   // consumed at the end of this row block
       }
+      const long long b_head1 = FS_CLOCK();
       // row statistics (dQ) / row identity (dE)
       float row_lse2 = 0.f;
       long row_pos = -1;   // dQ: local column of the positive item;  dE: this row's local item index
@@ -414,9 +481,19 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ C
         const long long k4 = FS_CLOCK();
         tq_wait_s += k1 - k0; tq_math += k2 - k1; tq_wait_p += k3 - k2; tq_st += k4 - k3; ++tq_n;
       }
+      const long long b0 = FS_CLOCK();
+      if (use_pf && w_next < n_work) {
+        // every GEMM1 of this row block has completed (the last tile's accumulator is full): X may be replaced
+        const long gl = g - 1;
+        tc::mbar_wait(&s_full[(int)(gl % NSTG)], (uint32_t)(gl / NSTG) & 1u);
+        tc::fence_after_sync();
+        x_store();
+      }
       // row block finished: dX accumulator -> global (scaled); 32-column chunks split over the groups
+      const long long b1 = FS_CLOCK();
       tc::mbar_wait(dx_full, wi & 1u);
       tc::fence_after_sync();
+      const long long b2 = FS_CLOCK();
       float* orow = p.out + ((size_t)split * p.n_x + xrow) * p.D;
       const float out_scale = FWD ? 1.f : p.scale * (p.scale_dev ? __ldg(p.scale_dev) : 1.f);
       // dQ pass: "- onehot" = minus the positive item's row of Y, applied once, by the split that owns that column
@@ -442,11 +519,21 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ C
         }
       }
       tc::fence_before_sync();
+      if (EARLY_X) {   // dX has been read: the next row block's first GEMM2 may overwrite it
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(dx_empty);
+      }
+      const long long b3 = FS_CLOCK();
+      tb_x += b1 - b0; tb_wait_dx += b2 - b1; tb_drain += b3 - b2; tb_head += b_head1 - b_head0; ++tb_n;
     }
     if ((FS_DBG(p) & 8) && blockIdx.x == 0 && warp == 3 && lane == 0 && tq_n > 0)
       printf("[ce_bwd softmax warp, transposed=%d] own tiles %lld: total/own-tile %lld = wait s_full %lld + ld+math %lld + "
              "wait p_empty %lld + st+arrive %lld cycles\n", (int)TRANSPOSED, tq_n, (FS_CLOCK() - tq_begin) / tq_n,
              tq_wait_s / tq_n, tq_math / tq_n, tq_wait_p / tq_n, tq_st / tq_n);
+    if ((FS_DBG(p) & 8) && blockIdx.x == 0 && (warp == 3 || warp == 7) && lane == 0 && tb_n > 0)
+      printf("[ce_bwd row-block hand-over, transposed=%d, warp %d] blocks %lld: X fetch/store at head %lld, wait last GEMM1 + X "
+             "store %lld, wait dx_full %lld, drain %lld cycles per block\n", (int)TRANSPOSED, warp, tb_n, tb_head / tb_n,
+             tb_x / tb_n, tb_wait_dx / tb_n, tb_drain / tb_n);
   }
   tc::fence_before_sync();
   __syncthreads();
@@ -515,7 +602,8 @@ struct BwdPlan {
 // three_groups: the dE pass at D <= 128 runs 64-column tiles with THREE accumulator stages / softmax warp groups (TMEM
 // D/2 + D + 3*64 + 3*32 = 480 columns): its softmax warps are latency-bound (ncu: issue slots 35 % busy, tensor and XU
 // pipes ~52 %), so a third group in flight hides more of the per-tile hand-off latency than wider tiles gain.
-static void bwd_plan(long n_x, long n_y, int D, BwdPlan* pl, bool three_groups = false, bool aug = false) {
+static void bwd_plan(long n_x, long n_y, int D, BwdPlan* pl, bool three_groups = false, bool aug = false,
+                     bool early_x = false) {
   pl->NT = D <= 128 ? 96 : 64;
   pl->NSTG = D <= 192 ? 2 : 1;
   if (three_groups && D <= 128) {
@@ -525,7 +613,10 @@ static void bwd_plan(long n_x, long n_y, int D, BwdPlan* pl, bool three_groups =
   pl->row_blocks = (n_x + kRows - 1) / kRows;
   pl->tiles = (n_y + pl->NT - 1) / pl->NT;
   const size_t stage = (size_t)(D / 64 + (aug ? 1 : 0)) * pl->NT * 128;   // aug: one more slab (the -lse columns)
-  int stages = (int)(((size_t)kBwdSmem - 1024 - 8 * pl->NSTG * pl->NT * 4 - 512) / stage);
+  // early_x (dE pass): 16 KB per softmax group of X staging, out of the full 227 KB instead of the 200 KB budget
+  const size_t x_stage = early_x && pl->NSTG <= 2 ? (size_t)8 * 128 * pl->NSTG * 16 : 0;
+  const size_t budget = x_stage ? (size_t)226 * 1024 : (size_t)kBwdSmem;
+  int stages = (int)((budget - 1024 - 8 * pl->NSTG * pl->NT * 4 - 512 - x_stage) / stage);
   pl->stages = stages > kBwdMaxStages ? kBwdMaxStages : stages;
   // column splits per row block: the smallest count whose work items fill the persistent grid to >= 95 % in whole waves
   // (e.g. 64 row blocks on 148 SMs: 2 splits leave 20 SMs idle, 9 splits = 576 items = 3.9 waves), at least 4 tiles each
@@ -542,7 +633,7 @@ static void bwd_plan(long n_x, long n_y, int D, BwdPlan* pl, bool three_groups =
   pl->splits = (int)splits;
   const long n_work = pl->row_blocks * splits;
   pl->grid = (int)(n_work < sm_count() ? n_work : sm_count());
-  pl->smem = 1024 + (size_t)pl->stages * stage + 8 * pl->NSTG * pl->NT * 4 + 512;
+  pl->smem = 1024 + (size_t)pl->stages * stage + 8 * pl->NSTG * pl->NT * 4 + 512 + x_stage;
 }
 
 template <int TR>
@@ -569,7 +660,7 @@ static int bwd_one(const void* X, long n_x, const void* Y, long n_y, int D, cons
                    __nv_bfloat16* laug, cudaStream_t st) {
   BwdPlan pl;
   constexpr bool AUG = TR == MODE_DE && kDeAugment;
-  bwd_plan(n_x, n_y, D, &pl, TR == MODE_DE && kDeThreeGroups, AUG);
+  bwd_plan(n_x, n_y, D, &pl, TR == MODE_DE && kDeThreeGroups, AUG, TR == MODE_DE && kDeEarlyX);
   CUtensorMap my, ml;
   int rc = make_rows_map(&my, Y, n_y, D, pl.NT);
   if (rc) return rc;
@@ -614,7 +705,7 @@ static size_t round128(size_t x) { return (x + 127) & ~(size_t)127; }
 size_t ce_bwd_workspace_bytes(long n_users, long n_rows, int D) {
   BwdPlan a, b;
   bwd_plan(n_users, n_rows, D, &a);
-  bwd_plan(n_rows, n_users, D, &b, kDeThreeGroups, kDeAugment);
+  bwd_plan(n_rows, n_users, D, &b, kDeThreeGroups, kDeAugment, kDeEarlyX);
   const size_t wa = a.splits > 1 ? (size_t)a.splits * n_users * D * 4 : 0;
   const size_t wb = b.splits > 1 ? (size_t)b.splits * n_rows * D * 4 : 0;
   // + the [n_users, 64] bf16 matrix of -lse splits the dE pass streams next to Q
