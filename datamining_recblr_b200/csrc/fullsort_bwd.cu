@@ -80,6 +80,7 @@ struct BwdParams {
   long id_offset;       // global id of item row 0 of this shard
   float scale;
   const float* scale_dev;  // optional device scalar multiplied into `scale` (the upstream dL/dloss: no host sync, no extra pass)
+  int early_x;          // dE pass: X rows by TMA + early hand-over + transposed drain (host: D <= 128, two softmax groups)
   int dbg;              // BDLRU_FS_DEBUG & 8: print per-tile phase timings of one softmax warp
   float* out;           // [splits][n_x][D] fp32 (splits == 1: the final gradient)
 };
@@ -88,7 +89,8 @@ enum { MODE_DQ = 0, MODE_DE = 1, MODE_FWD = 2 };
 
 template <int MODE, int NT, int NSTG>
 __global__ void __launch_bounds__(96 + 128 * NSTG, 1)
-ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmL, const BwdParams p) {
+ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmL,
+              const __grid_constant__ CUtensorMap tmX, const BwdParams p) {
   constexpr bool TRANSPOSED = MODE == MODE_DE;
   constexpr bool FWD = MODE == MODE_FWD;
   // dE pass: the per-COLUMN statistic -lse_u rides the recompute GEMM as 16 extra K elements — X gets the constant columns
@@ -96,14 +98,16 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ C
   // the auxiliary matrix behind tmL, of which one K step is used) — so the accumulator already holds l - lse and the softmax
   // loop needs neither a shared-memory read nor an FFMA per element (it was latency-bound on exactly those).
   constexpr bool AUG = kDeAugment && MODE == MODE_DE;
-  // dE pass: a row block is only ~86 tiles long, so the hand-over between row blocks (drain dX, fetch the next X rows,
-  // refill the GEMM1 -> softmax -> GEMM2 pipeline: ~6 us of a 74 us block, measured by sweeping the user count) matters.
-  // With EARLY_X the softmax warps prefetch their share of the NEXT block's X rows into registers during the current block
-  // (cp.async into a thread-private shared-memory slot: holding them in registers cost 4 % of the steady state)
-  // and store them into TMEM as soon as the last GEMM1 of the current block has completed — before they drain dX — so the
-  // global-load latency and the first GEMM1s of the next block overlap the drain.
+  // dE pass: a row block is only ~86 tiles long, so the hand-over between row blocks matters.  Measured per block (cycles of a
+  // softmax warp, 8192 users): thread == row loads of X 2400 and the thread == row float4 drain of dX 4100 — both touch 32
+  // different lines per warp instruction, ~1 cycle per line in the L1 — out of ~112 000 for the whole block.
+  // With EARLY_X (D <= 128, two softmax groups):
+  //   * the TMA producer fetches the NEXT block's X rows into a swizzled shared-memory stage during the current block;
+  //   * the softmax warps copy them into TMEM as soon as the last GEMM1 of the current block has completed — BEFORE they
+  //     drain dX — so the first GEMM1s of the next block overlap the drain (dx_empty orders its first GEMM2 after it);
+  //   * the drain goes through a per-warp 4 KB transpose in that same stage, so every global store instruction writes
+  //     four full 128-byte lines instead of 32 partial ones.
   constexpr bool EARLY_X = kDeEarlyX && MODE == MODE_DE;
-  constexpr int XPF = 4;   // the prefetch slot holds XPF 8-column groups of packed X per thread (D <= 64 * NSTG)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -113,7 +117,9 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ C
   constexpr int NCH = NT / 32;
   constexpr int NG = NSTG;                 // softmax warp groups: group g owns accumulator / P stage g
   uint8_t* sY = smem;
-  float* col_lse = reinterpret_cast<float*>(sY + (size_t)p.stages * n_slab_st * kSlabB);  // [4 * NSTG warps][NT]
+  constexpr uint32_t kXSlabB = kRows * 128;   // one 64-channel slab of an X row block
+  uint8_t* x_stage = sY + (size_t)p.stages * n_slab_st * kSlabB;   // early_x: 2 slabs (1024-byte aligned: stages are)
+  float* col_lse = reinterpret_cast<float*>(x_stage + (p.early_x ? 2 * kXSlabB : 0));  // [4 * NSTG warps][NT]
   int* col_pos = reinterpret_cast<int*>(col_lse + 4 * NSTG * NT);                       // [4 * NSTG warps][NT]
   uint64_t* bars = reinterpret_cast<uint64_t*>(col_pos + 4 * NSTG * NT);
   uint64_t* y_full = bars;
@@ -125,8 +131,9 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ C
   uint64_t* x_full = p_empty + kBwdMaxAcc;
   uint64_t* dx_full = x_full + 1;
   uint64_t* dx_empty = dx_full + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dx_empty + 1);
-  uint4* x_stage = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(bars) + 512);   // EARLY_X: [2 * XPF][128 * NG] x 16 B
+  uint64_t* x_ready = dx_empty + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(x_ready + 1);
+  const bool use_pf = EARLY_X && p.early_x;
 
   const uint32_t x_cols = (uint32_t)(p.D >> 1) + (AUG ? 8u : 0u);
   const uint32_t dx_col = x_cols;
@@ -136,6 +143,7 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ C
   if (warp == 2 && lane == 0) {
     tc::prefetch_tensormap(&tmY);
     if (AUG) tc::prefetch_tensormap(&tmL);
+    if (EARLY_X) tc::prefetch_tensormap(&tmX);
     for (int s = 0; s < p.stages; ++s) {
       tc::mbar_init(&y_full[s], 1);
       tc::mbar_init(&y_empty[s], 1);
@@ -149,6 +157,7 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ C
     tc::mbar_init(x_full, 4 * NG);
     tc::mbar_init(dx_full, 1);
     tc::mbar_init(dx_empty, 4 * NG);
+    tc::mbar_init(x_ready, 1);
     tc::fence_barrier_init();
   }
   if (warp == 0) {
@@ -165,9 +174,23 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ C
   if (warp == 2) {
     // ===================================================================== TMA producer
     long g = 0;
-    for (long w = blockIdx.x; w < n_work; w += gridDim.x) {
+    uint32_t wi = 0;
+    auto load_x = [&](long wq) {   // X rows of work item wq -> x_stage (rows past n_x arrive as zeros)
+      if (tc::elect_one()) {
+        tc::mbar_arrive_expect_tx(x_ready, (uint32_t)n_slab * kXSlabB);
+        for (int sl = 0; sl < n_slab; ++sl)
+          tc::tma_load_2d(x_stage + (size_t)sl * kXSlabB, &tmX, x_ready, sl * 64, (int)((wq % p.row_blocks) * kRows));
+      }
+      __syncwarp();
+    };
+    if (use_pf && blockIdx.x < n_work) load_x(blockIdx.x);
+    for (long w = blockIdx.x; w < n_work; w += gridDim.x, ++wi) {
       const int split = (int)(w / p.row_blocks);
       const long t0 = p.tiles_total * split / p.splits, t1 = p.tiles_total * (split + 1) / p.splits;
+      // the next block's X is requested once the ring has been filled for this block (so the Y prefetch never waits for
+      // it) and the stage is free: X of THIS block copied to TMEM (x_full) and the previous block's drain, which
+      // transposes through the same stage, finished (dx_empty; it follows that copy)
+      const long x_at = t0 + ((t1 - t0) < p.stages ? (t1 - t0) : p.stages) - 1;
       for (long t = t0; t < t1; ++t, ++g) {
         const int s = (int)(g % p.stages);
         const uint32_t ph = (uint32_t)(g / p.stages) & 1u;
@@ -179,6 +202,11 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ C
           if (AUG) tc::tma_load_2d(sY + (size_t)(s * n_slab_st + n_slab) * kSlabB, &tmL, &y_full[s], 0, (int)(t * NT));
         }
         __syncwarp();
+        if (use_pf && t == x_at && w + gridDim.x < n_work) {
+          if (wi == 0) tc::mbar_wait(x_full, 0u);
+          else tc::mbar_wait(dx_empty, (wi - 1) & 1u);
+          load_x(w + gridDim.x);
+        }
       }
     }
   } else if (warp == 0) {
@@ -295,34 +323,18 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ C
       }
       x_publish();
     };
-    const bool use_pf = EARLY_X && NSTG <= 2 && (xj1 - xj0) <= XPF;
-    uint4* my_stage = x_stage + (threadIdx.x - 96);   // slot k of this thread: my_stage[k * 128 * NG] (conflict-free)
-    auto x_fetch = [&](long xr_row) {
-      const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.X) + xr_row * p.D);
-#pragma unroll
-      for (int jj = 0; jj < XPF; ++jj) {
-        const int j = xj0 + jj;
-        if (j < xj1) {
-          if (xr_row < p.n_x) {
-            cp_async<16>(my_stage + (2 * jj) * (128 * NG), src + 2 * j);
-            cp_async<16>(my_stage + (2 * jj + 1) * (128 * NG), src + 2 * j + 1);
-          } else {
-            my_stage[(2 * jj) * (128 * NG)] = my_stage[(2 * jj + 1) * (128 * NG)] = make_uint4(0, 0, 0, 0);
-          }
-        }
-      }
-      cp_async_commit();
-    };
+    // early_x: this thread's row of the staged X block (TMA 128-byte swizzle: 16-byte chunk c of row r sits at c ^ (r & 7))
+    uint32_t xk = 0;   // X loads consumed so far (phase of x_ready)
     auto x_store = [&]() {
-      cp_async_wait<0>();
-#pragma unroll
-      for (int jj = 0; jj < XPF; ++jj) {
-        const int j = xj0 + jj;
-        if (j < xj1) {
-          const uint4 lo = my_stage[(2 * jj) * (128 * NG)], hi = my_stage[(2 * jj + 1) * (128 * NG)];
-          const uint32_t wv[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
-          tc::tmem_st_32x32_x8(lane_addr + (uint32_t)j * 8, wv);
-        }
+      tc::mbar_wait(x_ready, xk & 1u);
+      ++xk;
+      for (int j = xj0; j < xj1; ++j) {
+        const uint8_t* rowp = x_stage + (size_t)(j >> 2) * kXSlabB + (size_t)row * 128;
+        const int c0 = (2 * j) & 7;
+        const uint4 lo = *reinterpret_cast<const uint4*>(rowp + ((c0 ^ (row & 7)) << 4));
+        const uint4 hi = *reinterpret_cast<const uint4*>(rowp + (((c0 + 1) ^ (row & 7)) << 4));
+        const uint32_t wv[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+        tc::tmem_st_32x32_x8(lane_addr + (uint32_t)j * 8, wv);
       }
       x_publish();
     };
@@ -333,15 +345,8 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ C
       const long xrow = rb * kRows + row;
       const long w_next = w + gridDim.x;
       const long long b_head0 = FS_CLOCK();
-      if (!use_pf) {
-        x_direct(xrow);
-      } else {
-        if (wi == 0) {
-          x_fetch(xrow);
-          x_store();
-        }
-        if (w_next < n_work) x_fetch((w_next % p.row_blocks) * kRows + row);   // consumed at the end of this row block
-      }
+      if (!use_pf) x_direct(xrow);
+      else if (wi == 0) x_store();
       const long long b_head1 = FS_CLOCK();
       // row statistics (dQ) / row identity (dE)
       float row_lse2 = 0.f;
@@ -490,6 +495,8 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ C
         x_store();
       }
       // row block finished: dX accumulator -> global (scaled); 32-column chunks split over the groups
+      // the X stage doubles as the drain's transpose buffer: every softmax warp has finished copying X out of it
+      if (use_pf) asm volatile("bar.sync 1, %0;" ::"n"(128 * NG) : "memory");
       const long long b1 = FS_CLOCK();
       tc::mbar_wait(dx_full, wi & 1u);
       tc::fence_after_sync();
@@ -500,6 +507,33 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ C
       if (FWD && xrow < p.n_x) p.sum_parts[((size_t)split * NG + grp) * p.n_x + xrow] = rsum[0] + rsum[1];
       const bool sub_pos = MODE == MODE_DQ && xrow < p.n_x && row_pos >= t0 * NT && row_pos < t1 * NT && row_pos < p.n_y;
       const __nv_bfloat16* yrow = reinterpret_cast<const __nv_bfloat16*>(p.Y) + (sub_pos ? row_pos : 0) * p.D;
+      if (use_pf) {
+        // transposed drain: thread == row writes its 32 columns into this warp's 4 KB of the X stage (swizzled like the
+        // TMA layout, conflict-free), then 8 lanes x 16 bytes cover one full line of a row: 4 rows per store instruction
+        uint8_t* tr = x_stage + (size_t)ew * 4096;
+        const int rsub = lane >> 3, csub = lane & 7;
+        for (int c = grp; c < (p.D >> 5); c += NG) {
+          uint32_t acc[32];
+          tc::tmem_ld_32x32(lane_addr + dx_col + (uint32_t)c * 32, acc);
+          tc::tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            *reinterpret_cast<float4*>(tr + lane * 128 + ((i ^ (lane & 7)) << 4)) =
+                make_float4(__uint_as_float(acc[4 * i]) * out_scale, __uint_as_float(acc[4 * i + 1]) * out_scale,
+                            __uint_as_float(acc[4 * i + 2]) * out_scale, __uint_as_float(acc[4 * i + 3]) * out_scale);
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rr = i * 4 + rsub;
+            const float4 v = *reinterpret_cast<const float4*>(tr + rr * 128 + ((csub ^ (rr & 7)) << 4));
+            const long grow = rb * kRows + q * 32 + rr;
+            if (grow < p.n_x)
+              *reinterpret_cast<float4*>(p.out + ((size_t)split * p.n_x + grow) * p.D + c * 32 + csub * 4) = v;
+          }
+          __syncwarp();
+        }
+        tc::fence_proxy_async();   // the stage is next written by the TMA (async proxy)
+      } else
       for (int c = grp; c < (p.D >> 5); c += NG) {
         uint32_t acc[32];
         tc::tmem_ld_32x32(lane_addr + dx_col + (uint32_t)c * 32, acc);
@@ -595,6 +629,7 @@ __global__ void lse_aug_kernel(const float* __restrict__ lse, long n_users, __nv
 // ----------------------------------------------------------------------------- host side
 struct BwdPlan {
   int NT, NSTG, stages, splits, grid;
+  bool early_x;
   long row_blocks, tiles;
   size_t smem;
 };
@@ -614,10 +649,14 @@ static void bwd_plan(long n_x, long n_y, int D, BwdPlan* pl, bool three_groups =
   pl->tiles = (n_y + pl->NT - 1) / pl->NT;
   const size_t stage = (size_t)(D / 64 + (aug ? 1 : 0)) * pl->NT * 128;   // aug: one more slab (the -lse columns)
   // early_x (dE pass): 16 KB per softmax group of X staging, out of the full 227 KB instead of the 200 KB budget
-  const size_t x_stage = early_x && pl->NSTG <= 2 ? (size_t)8 * 128 * pl->NSTG * 16 : 0;
+  pl->early_x = early_x && pl->NSTG == 2 && D <= 128;
+  const size_t x_stage = pl->early_x ? (size_t)2 * kRows * 128 : 0;   // two 64-channel slabs of a 128-row block
   const size_t budget = x_stage ? (size_t)226 * 1024 : (size_t)kBwdSmem;
   int stages = (int)((budget - 1024 - 8 * pl->NSTG * pl->NT * 4 - 512 - x_stage) / stage);
   pl->stages = stages > kBwdMaxStages ? kBwdMaxStages : stages;
+#ifdef BDLRU_CE_DE_MAX_STAGES
+  if (early_x && pl->stages > BDLRU_CE_DE_MAX_STAGES) pl->stages = BDLRU_CE_DE_MAX_STAGES;
+#endif
   // column splits per row block: the smallest count whose work items fill the persistent grid to >= 95 % in whole waves
   // (e.g. 64 row blocks on 148 SMs: 2 splits leave 20 SMs idle, 9 splits = 576 items = 3.9 waves), at least 4 tiles each
   const long sm = sm_count();
@@ -637,12 +676,13 @@ static void bwd_plan(long n_x, long n_y, int D, BwdPlan* pl, bool three_groups =
 }
 
 template <int TR>
-static int bwd_launch(const BwdPlan& pl, const CUtensorMap& my, const CUtensorMap& ml, const BwdParams& p, cudaStream_t st) {
+static int bwd_launch(const BwdPlan& pl, const CUtensorMap& my, const CUtensorMap& ml, const CUtensorMap& mx,
+                      const BwdParams& p, cudaStream_t st) {
 #define BWD_CASE(NTv, NSv)                                                                                      \
   if (pl.NT == NTv && pl.NSTG == NSv) {                                                                         \
     BDLRU_CUDA(cudaFuncSetAttribute(ce_bwd_kernel<TR, NTv, NSv>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
                                     (int)pl.smem));                                                             \
-    ce_bwd_kernel<TR, NTv, NSv><<<pl.grid, 96 + 128 * NSv, pl.smem, st>>>(my, ml, p);                                       \
+    ce_bwd_kernel<TR, NTv, NSv><<<pl.grid, 96 + 128 * NSv, pl.smem, st>>>(my, ml, mx, p);                                       \
     BDLRU_LAUNCHED();                                                                                           \
     return BDLRU_OK;                                                                                            \
   }
@@ -676,7 +716,10 @@ static int bwd_one(const void* X, long n_x, const void* Y, long n_y, int D, cons
   p.lse = lse; p.pos = pos; p.n_users = n_users; p.id_offset = id_offset; p.scale = scale; p.scale_dev = scale_dev;
   p.dbg = tuning_env("BDLRU_FS_DEBUG");
   p.out = pl.splits > 1 ? scratch : grad;
-  if ((rc = bwd_launch<TR>(pl, my, ml, p, st))) return rc;
+  p.early_x = pl.early_x ? 1 : 0;
+  CUtensorMap mx = my;
+  if (pl.early_x && (rc = make_rows_map(&mx, X, n_x, D, kRows))) return rc;
+  if ((rc = bwd_launch<TR>(pl, my, ml, mx, p, st))) return rc;
   if (pl.splits > 1) {
     const long n4 = n_x * D / 4;
     sum_partials_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float4*>(scratch), n4,
@@ -776,7 +819,7 @@ extern "C" BDLRU_API int bdlru_fullsort_ce_fwd_dq(const void* Q, const void* E, 
   p.dbg = tuning_env("BDLRU_FS_DEBUG");
   p.sum_parts = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + acc_bytes);
   p.out = pl.splits > 1 ? scratch : acc;
-  if ((rc = bwd_launch<MODE_FWD>(pl, my, my, p, st))) return rc;
+  if ((rc = bwd_launch<MODE_FWD>(pl, my, my, my, p, st))) return rc;
   if (pl.splits > 1) {
     const long n4 = n_users * D / 4;
     sum_partials_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float4*>(scratch), n4,
