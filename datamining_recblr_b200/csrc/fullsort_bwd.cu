@@ -80,7 +80,7 @@ struct BwdParams {
   long id_offset;       // global id of item row 0 of this shard
   float scale;
   const float* scale_dev;  // optional device scalar multiplied into `scale` (the upstream dL/dloss: no host sync, no extra pass)
-  int early_x;          // dE pass: X rows by TMA + early hand-over + transposed drain (host: D <= 128, two softmax groups)
+  int early_x;          // dE pass: X rows by TMA, early hand-over, dX out by bulk stores (host: D <= 128, two softmax groups, one split)
   int dbg;              // BDLRU_FS_DEBUG & 8: print per-tile phase timings of one softmax warp
   float* out;           // [splits][n_x][D] fp32 (splits == 1: the final gradient)
 };
@@ -90,7 +90,7 @@ enum { MODE_DQ = 0, MODE_DE = 1, MODE_FWD = 2 };
 template <int MODE, int NT, int NSTG>
 __global__ void __launch_bounds__(96 + 128 * NSTG, 1)
 ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmL,
-              const __grid_constant__ CUtensorMap tmX, const BwdParams p) {
+              const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmO, const BwdParams p) {
   constexpr bool TRANSPOSED = MODE == MODE_DE;
   constexpr bool FWD = MODE == MODE_FWD;
   // dE pass: the per-COLUMN statistic -lse_u rides the recompute GEMM as 16 extra K elements — X gets the constant columns
@@ -105,8 +105,9 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ C
   //   * the TMA producer fetches the NEXT block's X rows into a swizzled shared-memory stage during the current block;
   //   * the softmax warps copy them into TMEM as soon as the last GEMM1 of the current block has completed — BEFORE they
   //     drain dX — so the first GEMM1s of the next block overlap the drain (dx_empty orders its first GEMM2 after it);
-  //   * the drain goes through a per-warp 4 KB transpose in that same stage, so every global store instruction writes
-  //     four full 128-byte lines instead of 32 partial ones.
+  //   * the drain only moves dX from TMEM into a 64 KB swizzled stage (which contains the X stage) and frees the
+  //     accumulator; the TMA producer writes it to global memory with bulk tensor stores while the next block runs (even
+  //     as full lines, 64 KB of st.global per block kept the softmax warps ~2900 cycles: the SM's store path).
   constexpr bool EARLY_X = kDeEarlyX && MODE == MODE_DE;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -118,8 +119,9 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ C
   constexpr int NG = NSTG;                 // softmax warp groups: group g owns accumulator / P stage g
   uint8_t* sY = smem;
   constexpr uint32_t kXSlabB = kRows * 128;   // one 64-channel slab of an X row block
-  uint8_t* x_stage = sY + (size_t)p.stages * n_slab_st * kSlabB;   // early_x: 2 slabs (1024-byte aligned: stages are)
-  float* col_lse = reinterpret_cast<float*>(x_stage + (p.early_x ? 2 * kXSlabB : 0));  // [4 * NSTG warps][NT]
+  uint8_t* x_stage = sY + (size_t)p.stages * n_slab_st * kSlabB;   // early_x: X slabs (1024-byte aligned: stages are)
+  // early_x: the drain stage = 4 boxes of 128 rows x 32 fp32 columns; its first half is the X stage
+  float* col_lse = reinterpret_cast<float*>(x_stage + (p.early_x ? 4 * kXSlabB : 0));  // [4 * NSTG warps][NT]
   int* col_pos = reinterpret_cast<int*>(col_lse + 4 * NSTG * NT);                       // [4 * NSTG warps][NT]
   uint64_t* bars = reinterpret_cast<uint64_t*>(col_pos + 4 * NSTG * NT);
   uint64_t* y_full = bars;
@@ -132,7 +134,8 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ C
   uint64_t* dx_full = x_full + 1;
   uint64_t* dx_empty = dx_full + 1;
   uint64_t* x_ready = dx_empty + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(x_ready + 1);
+  uint64_t* stage_free = x_ready + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stage_free + 1);
   const bool use_pf = EARLY_X && p.early_x;
 
   const uint32_t x_cols = (uint32_t)(p.D >> 1) + (AUG ? 8u : 0u);
@@ -144,6 +147,7 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ C
     tc::prefetch_tensormap(&tmY);
     if (AUG) tc::prefetch_tensormap(&tmL);
     if (EARLY_X) tc::prefetch_tensormap(&tmX);
+    if (EARLY_X) tc::prefetch_tensormap(&tmO);
     for (int s = 0; s < p.stages; ++s) {
       tc::mbar_init(&y_full[s], 1);
       tc::mbar_init(&y_empty[s], 1);
@@ -158,6 +162,7 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ C
     tc::mbar_init(dx_full, 1);
     tc::mbar_init(dx_empty, 4 * NG);
     tc::mbar_init(x_ready, 1);
+    tc::mbar_init(stage_free, 1);
     tc::fence_barrier_init();
   }
   if (warp == 0) {
@@ -183,13 +188,23 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ C
       }
       __syncwarp();
     };
+    auto store_dx = [&](long wq) {   // the staged dX of work item wq -> global (rows past n_x are clipped by the TMA)
+      if (tc::elect_one()) {
+        for (int c = 0; c < (p.D >> 5); ++c)
+          tc::tma_store_2d(&tmO, x_stage + (size_t)c * kXSlabB, c * 32, (int)((wq % p.row_blocks) * kRows));
+        tc::bulk_commit();
+        tc::bulk_wait_read();
+      }
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(stage_free);
+    };
     if (use_pf && blockIdx.x < n_work) load_x(blockIdx.x);
     for (long w = blockIdx.x; w < n_work; w += gridDim.x, ++wi) {
       const int split = (int)(w / p.row_blocks);
       const long t0 = p.tiles_total * split / p.splits, t1 = p.tiles_total * (split + 1) / p.splits;
       // the next block's X is requested once the ring has been filled for this block (so the Y prefetch never waits for
       // it) and the stage is free: X of THIS block copied to TMEM (x_full) and the previous block's drain, which
-      // transposes through the same stage, finished (dx_empty; it follows that copy)
+      // is staged there and has been read by the bulk stores issued right here (dx_empty; it follows that copy)
       const long x_at = t0 + ((t1 - t0) < p.stages ? (t1 - t0) : p.stages) - 1;
       for (long t = t0; t < t1; ++t, ++g) {
         const int s = (int)(g % p.stages);
@@ -202,12 +217,20 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ C
           if (AUG) tc::tma_load_2d(sY + (size_t)(s * n_slab_st + n_slab) * kSlabB, &tmL, &y_full[s], 0, (int)(t * NT));
         }
         __syncwarp();
-        if (use_pf && t == x_at && w + gridDim.x < n_work) {
-          if (wi == 0) tc::mbar_wait(x_full, 0u);
-          else tc::mbar_wait(dx_empty, (wi - 1) & 1u);
-          load_x(w + gridDim.x);
+        if (use_pf && t == x_at) {
+          if (wi == 0) {
+            tc::mbar_wait(x_full, 0u);
+          } else {   // the previous block's dX has been staged (and its X copied out before that)
+            tc::mbar_wait(dx_empty, (wi - 1) & 1u);
+            store_dx(w - gridDim.x);
+          }
+          if (w + gridDim.x < n_work) load_x(w + gridDim.x);
         }
       }
+    }
+    if (use_pf && wi > 0) {   // the last block of this CTA
+      tc::mbar_wait(dx_empty, (wi - 1) & 1u);
+      store_dx((long)blockIdx.x + (long)(wi - 1) * gridDim.x);
     }
   } else if (warp == 0) {
     // ===================================================================== GEMM1 issuer:  S(t) = X Y(t)^T
@@ -508,31 +531,21 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ C
       const bool sub_pos = MODE == MODE_DQ && xrow < p.n_x && row_pos >= t0 * NT && row_pos < t1 * NT && row_pos < p.n_y;
       const __nv_bfloat16* yrow = reinterpret_cast<const __nv_bfloat16*>(p.Y) + (sub_pos ? row_pos : 0) * p.D;
       if (use_pf) {
-        // transposed drain: thread == row writes its 32 columns into this warp's 4 KB of the X stage (swizzled like the
-        // TMA layout, conflict-free), then 8 lanes x 16 bytes cover one full line of a row: 4 rows per store instruction
-        uint8_t* tr = x_stage + (size_t)ew * 4096;
-        const int rsub = lane >> 3, csub = lane & 7;
+        // thread == row moves its 32-column chunks into the stage (box c = 128 rows x 128 bytes, swizzled like a TMA
+        // box: conflict-free); the producer warp stores the boxes once every softmax warp has arrived on dx_empty
+        if (wi > 0) tc::mbar_wait(stage_free, (wi - 1) & 1u);   // the previous block's bulk stores have read the stage
         for (int c = grp; c < (p.D >> 5); c += NG) {
           uint32_t acc[32];
           tc::tmem_ld_32x32(lane_addr + dx_col + (uint32_t)c * 32, acc);
           tc::tmem_ld_wait();
+          uint8_t* box = x_stage + (size_t)c * kXSlabB + (size_t)row * 128;
 #pragma unroll
           for (int i = 0; i < 8; ++i)
-            *reinterpret_cast<float4*>(tr + lane * 128 + ((i ^ (lane & 7)) << 4)) =
+            *reinterpret_cast<float4*>(box + ((i ^ (row & 7)) << 4)) =
                 make_float4(__uint_as_float(acc[4 * i]) * out_scale, __uint_as_float(acc[4 * i + 1]) * out_scale,
                             __uint_as_float(acc[4 * i + 2]) * out_scale, __uint_as_float(acc[4 * i + 3]) * out_scale);
-          __syncwarp();
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int rr = i * 4 + rsub;
-            const float4 v = *reinterpret_cast<const float4*>(tr + rr * 128 + ((csub ^ (rr & 7)) << 4));
-            const long grow = rb * kRows + q * 32 + rr;
-            if (grow < p.n_x)
-              *reinterpret_cast<float4*>(p.out + ((size_t)split * p.n_x + grow) * p.D + c * 32 + csub * 4) = v;
-          }
-          __syncwarp();
         }
-        tc::fence_proxy_async();   // the stage is next written by the TMA (async proxy)
+        tc::fence_proxy_async();   // generic writes -> visible to the bulk stores (async proxy)
       } else
       for (int c = grp; c < (p.D >> 5); c += NG) {
         uint32_t acc[32];
@@ -647,16 +660,6 @@ static void bwd_plan(long n_x, long n_y, int D, BwdPlan* pl, bool three_groups =
   }
   pl->row_blocks = (n_x + kRows - 1) / kRows;
   pl->tiles = (n_y + pl->NT - 1) / pl->NT;
-  const size_t stage = (size_t)(D / 64 + (aug ? 1 : 0)) * pl->NT * 128;   // aug: one more slab (the -lse columns)
-  // early_x (dE pass): 16 KB per softmax group of X staging, out of the full 227 KB instead of the 200 KB budget
-  pl->early_x = early_x && pl->NSTG == 2 && D <= 128;
-  const size_t x_stage = pl->early_x ? (size_t)2 * kRows * 128 : 0;   // two 64-channel slabs of a 128-row block
-  const size_t budget = x_stage ? (size_t)226 * 1024 : (size_t)kBwdSmem;
-  int stages = (int)((budget - 1024 - 8 * pl->NSTG * pl->NT * 4 - 512 - x_stage) / stage);
-  pl->stages = stages > kBwdMaxStages ? kBwdMaxStages : stages;
-#ifdef BDLRU_CE_DE_MAX_STAGES
-  if (early_x && pl->stages > BDLRU_CE_DE_MAX_STAGES) pl->stages = BDLRU_CE_DE_MAX_STAGES;
-#endif
   // column splits per row block: the smallest count whose work items fill the persistent grid to >= 95 % in whole waves
   // (e.g. 64 row blocks on 148 SMs: 2 splits leave 20 SMs idle, 9 splits = 576 items = 3.9 waves), at least 4 tiles each
   const long sm = sm_count();
@@ -669,6 +672,18 @@ static void bwd_plan(long n_x, long n_y, int D, BwdPlan* pl, bool three_groups =
     if (util > best + 1e-9) { best = util; splits = s; }
     if (util >= 0.95) break;
   }
+  const size_t stage = (size_t)(D / 64 + (aug ? 1 : 0)) * pl->NT * 128;   // aug: one more slab (the -lse columns)
+  // early_x (dE pass): 64 KB stage for the next X block / the drained dX, out of the full 227 KB instead of the 200 KB
+  // budget (4 ring stages instead of 5: no measurable difference, 3 cost 2.5 %).  The bulk stores clip at n_x, which is
+  // only the right bound of the output when there is a single column split.
+  pl->early_x = early_x && pl->NSTG == 2 && D <= 128 && splits == 1;
+  const size_t x_stage = pl->early_x ? (size_t)4 * kRows * 128 : 0;   // 4 boxes of 128 rows x 128 bytes
+  const size_t budget = x_stage ? (size_t)226 * 1024 : (size_t)kBwdSmem;
+  int stages = (int)((budget - 1024 - 8 * pl->NSTG * pl->NT * 4 - 512 - x_stage) / stage);
+  pl->stages = stages > kBwdMaxStages ? kBwdMaxStages : stages;
+#ifdef BDLRU_CE_DE_MAX_STAGES
+  if (early_x && pl->stages > BDLRU_CE_DE_MAX_STAGES) pl->stages = BDLRU_CE_DE_MAX_STAGES;
+#endif
   pl->splits = (int)splits;
   const long n_work = pl->row_blocks * splits;
   pl->grid = (int)(n_work < sm_count() ? n_work : sm_count());
@@ -677,12 +692,12 @@ static void bwd_plan(long n_x, long n_y, int D, BwdPlan* pl, bool three_groups =
 
 template <int TR>
 static int bwd_launch(const BwdPlan& pl, const CUtensorMap& my, const CUtensorMap& ml, const CUtensorMap& mx,
-                      const BwdParams& p, cudaStream_t st) {
+                      const CUtensorMap& mo, const BwdParams& p, cudaStream_t st) {
 #define BWD_CASE(NTv, NSv)                                                                                      \
   if (pl.NT == NTv && pl.NSTG == NSv) {                                                                         \
     BDLRU_CUDA(cudaFuncSetAttribute(ce_bwd_kernel<TR, NTv, NSv>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
                                     (int)pl.smem));                                                             \
-    ce_bwd_kernel<TR, NTv, NSv><<<pl.grid, 96 + 128 * NSv, pl.smem, st>>>(my, ml, mx, p);                                       \
+    ce_bwd_kernel<TR, NTv, NSv><<<pl.grid, 96 + 128 * NSv, pl.smem, st>>>(my, ml, mx, mo, p);                                       \
     BDLRU_LAUNCHED();                                                                                           \
     return BDLRU_OK;                                                                                            \
   }
@@ -717,9 +732,10 @@ static int bwd_one(const void* X, long n_x, const void* Y, long n_y, int D, cons
   p.dbg = tuning_env("BDLRU_FS_DEBUG");
   p.out = pl.splits > 1 ? scratch : grad;
   p.early_x = pl.early_x ? 1 : 0;
-  CUtensorMap mx = my;
+  CUtensorMap mx = my, mo = my;
   if (pl.early_x && (rc = make_rows_map(&mx, X, n_x, D, kRows))) return rc;
-  if ((rc = bwd_launch<TR>(pl, my, ml, mx, p, st))) return rc;
+  if (pl.early_x && (rc = make_rows_map_f32(&mo, p.out, n_x, D, kRows))) return rc;
+  if ((rc = bwd_launch<TR>(pl, my, ml, mx, mo, p, st))) return rc;
   if (pl.splits > 1) {
     const long n4 = n_x * D / 4;
     sum_partials_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float4*>(scratch), n4,
@@ -819,7 +835,7 @@ extern "C" BDLRU_API int bdlru_fullsort_ce_fwd_dq(const void* Q, const void* E, 
   p.dbg = tuning_env("BDLRU_FS_DEBUG");
   p.sum_parts = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + acc_bytes);
   p.out = pl.splits > 1 ? scratch : acc;
-  if ((rc = bwd_launch<MODE_FWD>(pl, my, my, my, p, st))) return rc;
+  if ((rc = bwd_launch<MODE_FWD>(pl, my, my, my, my, p, st))) return rc;
   if (pl.splits > 1) {
     const long n4 = n_users * D / 4;
     sum_partials_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float4*>(scratch), n4,
