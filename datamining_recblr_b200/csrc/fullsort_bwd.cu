@@ -62,6 +62,12 @@ constexpr bool kDeThreeGroups = BDLRU_CE_DE_THREE_GROUPS != 0;
 #define BDLRU_CE_DE_AUGMENT 1
 #endif
 constexpr bool kDeAugment = BDLRU_CE_DE_AUGMENT != 0;
+// Softmax warps: all of S(t) is pulled into registers first and the accumulator stage released BEFORE the exponentials
+// (instead of after the last 32-column chunk was loaded, two thirds into them), and P(t) goes back chunk by chunk.
+#ifndef BDLRU_CE_EARLY_S_RELEASE
+#define BDLRU_CE_EARLY_S_RELEASE 6   // dE and fused-forward passes; the plain dQ pass measured 5 % slower with it
+#endif
+constexpr bool kEarlySRelease = BDLRU_CE_EARLY_S_RELEASE != 0;
 #ifndef BDLRU_CE_DE_EARLY_X
 #define BDLRU_CE_DE_EARLY_X 1
 #endif
@@ -109,6 +115,7 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ C
   //     accumulator; the TMA producer writes it to global memory with bulk tensor stores while the next block runs (even
   //     as full lines, 64 KB of st.global per block kept the softmax warps ~2900 cycles: the SM's store path).
   constexpr bool EARLY_X = kDeEarlyX && MODE == MODE_DE;
+  constexpr bool ESR = kEarlySRelease && ((BDLRU_CE_EARLY_S_RELEASE >> MODE) & 1);   // bit per MODE
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -138,10 +145,13 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ C
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stage_free + 1);
   const bool use_pf = EARLY_X && p.early_x;
 
-  const uint32_t x_cols = (uint32_t)(p.D >> 1) + (AUG ? 8u : 0u);
+  // The 8 augmented X columns sit BEHIND the P stages: in front of dX they shifted every accumulator off its 32-column
+  // alignment, and each MMA then took ~20-35 % longer (measured issue time per MMA: 70 / 79 cycles instead of 58 / 59).
+  const uint32_t x_cols = (uint32_t)(p.D >> 1);
   const uint32_t dx_col = x_cols;
   const uint32_t s_col = dx_col + (uint32_t)p.D;
   const uint32_t p_col = s_col + NSTG * NT;
+  const uint32_t xaug_col = p_col + NSTG * (NT / 2);
 
   if (warp == 2 && lane == 0) {
     tc::prefetch_tensormap(&tmY);
@@ -239,6 +249,7 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ C
     constexpr uint32_t idesc1 = tc::idesc_bf16_f32(kRows, NT, 0, 0);
     long g = 0;
     uint32_t wi = 0;
+    long long ti_y = 0, ti_s = 0, ti_issue = 0, ti_n = 0;
     for (long w = blockIdx.x; w < n_work; w += gridDim.x, ++wi) {
       const int split = (int)(w / p.row_blocks);
       const long t0 = p.tiles_total * split / p.splits, t1 = p.tiles_total * (split + 1) / p.splits;
@@ -249,9 +260,13 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ C
         const uint32_t ph = (uint32_t)(g / p.stages) & 1u;
         const int b = (int)(g % NSTG);
         const uint32_t bph = (uint32_t)(g / NSTG) & 1u;
+        const long long i0 = FS_CLOCK();
         tc::mbar_wait(&y_full[s], ph);
+        const long long i1 = FS_CLOCK();
         tc::mbar_wait(&s_empty[b], bph ^ 1u);
         tc::fence_after_sync();
+        const long long i2 = FS_CLOCK();
+        ti_y += i1 - i0; ti_s += i2 - i1; ++ti_n;
         if (tc::elect_one()) {
           const uint64_t bd0 = tc::smem_desc_sw128(tc::smem_u32(sY + (size_t)s * n_slab_st * kSlabB), 16, 1024);
           const uint32_t d_tmem = tmem_base + s_col + (uint32_t)b * NT;
@@ -263,18 +278,23 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ C
                                (uint32_t)((sl | k4) != 0));
           }
           if (AUG)   // the 16 augmented K elements: X columns D/2 .. D/2+7, first K step of the extra slab
-            tc::umma_bf16_ts(d_tmem, tmem_base + (uint32_t)(p.D >> 1), bd0 + (uint64_t)((uint32_t)n_slab * (kSlabB >> 4)),
+            tc::umma_bf16_ts(d_tmem, tmem_base + xaug_col, bd0 + (uint64_t)((uint32_t)n_slab * (kSlabB >> 4)),
                              idesc1, 1u);
           tc::umma_commit(&s_full[b]);
         }
         __syncwarp();
+        ti_issue += FS_CLOCK() - i2;
       }
     }
+    if ((FS_DBG(p) & 8) && blockIdx.x == 0 && lane == 0 && ti_n > 0)
+      printf("[ce_bwd GEMM1 issuer, mode %d] tiles %lld: wait y_full %lld + wait s_empty %lld + issue %lld cycles per tile\n",
+             MODE, ti_n, ti_y / ti_n, ti_s / ti_n, ti_issue / ti_n);
   } else if (warp == 1) {
     // ===================================================================== GEMM2 issuer:  dX += P(t) Y(t)
     const uint32_t idesc2 = tc::idesc_bf16_f32(kRows, p.D, 0, 1);  // B is MN-major in GEMM2
     long g = 0;
     uint32_t wi = 0;
+    long long tj_p = 0, tj_issue = 0, tj_n = 0;
     for (long w = blockIdx.x; w < n_work; w += gridDim.x, ++wi) {
       const int split = (int)(w / p.row_blocks);
       const long t0 = p.tiles_total * split / p.splits, t1 = p.tiles_total * (split + 1) / p.splits;
@@ -285,8 +305,11 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ C
         const int s = (int)(g % p.stages);
         const int b = (int)(g % NSTG);
         const uint32_t bph = (uint32_t)(g / NSTG) & 1u;
+        const long long j0 = FS_CLOCK();
         tc::mbar_wait(&p_full[b], bph);
         tc::fence_after_sync();
+        const long long j1 = FS_CLOCK();
+        tj_p += j1 - j0; ++tj_n;
         if (tc::elect_one()) {
           // Y tile as the MN-major B operand: leading (MN) stride = one 64-channel slab, K groups of 8 rows are
           // 1024 bytes apart; one MMA consumes 16 rows = 2048 bytes
@@ -302,8 +325,12 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ C
           if (t + 1 == t1) tc::umma_commit(dx_full);
         }
         __syncwarp();
+        tj_issue += FS_CLOCK() - j1;
       }
     }
+    if ((FS_DBG(p) & 8) && blockIdx.x == 0 && lane == 0 && tj_n > 0)
+      printf("[ce_bwd GEMM2 issuer, mode %d] tiles %lld: wait p_full %lld + issue %lld cycles per tile\n", MODE, tj_n,
+             tj_p / tj_n, tj_issue / tj_n);
   } else {
     // ===================================================================== softmax warps: thread == row
     // NG groups of 4 warps; group g handles the tiles whose accumulator stage is g, so the fixed latencies of one
@@ -326,7 +353,7 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ C
     auto x_publish = [&]() {
       if (AUG && grp == 0) {  // augmented K elements D .. D+15 of every X row: 1, 1, 1, 0, ... (bf16 1.0 = 0x3F80)
         const uint32_t ones[8] = {0x3F803F80u, 0x00003F80u, 0u, 0u, 0u, 0u, 0u, 0u};
-        tc::tmem_st_32x32_x8(lane_addr + (uint32_t)(p.D >> 1), ones);
+        tc::tmem_st_32x32_x8(lane_addr + xaug_col, ones);
       }
       tc::tmem_st_wait();
       tc::fence_before_sync();
@@ -441,15 +468,28 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ C
         tc::mbar_wait(&s_full[b], bph);
         tc::fence_after_sync();
         const long long k1 = FS_CLOCK();
+        uint32_t raw_all[ESR ? NCH : 1][32];
+        if (ESR) {
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) tc::tmem_ld_32x32(lane_addr + s_col + (uint32_t)b * NT + c * 32, raw_all[c]);
+          tc::tmem_ld_wait();
+          tc::fence_before_sync();
+          __syncwarp();
+          if (lane == 0) tc::mbar_arrive(&s_empty[b]);   // S(t) is in registers: GEMM1 of tile t + NSTG may overwrite the stage
+          tc::mbar_wait(&p_empty[b], bph ^ 1u);          // GEMM2 of the tile that used this P stage has completed
+          tc::fence_after_sync();
+        }
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
-          uint32_t raw[32];
-          tc::tmem_ld_32x32(lane_addr + s_col + (uint32_t)b * NT + c * 32, raw);
-          tc::tmem_ld_wait();
-          if (c == NCH - 1) {  // S(t) is in registers: GEMM1 of tile t + NSTG may overwrite the stage
-            tc::fence_before_sync();
-            __syncwarp();
-            if (lane == 0) tc::mbar_arrive(&s_empty[b]);
+          uint32_t (&raw)[32] = raw_all[ESR ? c : 0];
+          if (!ESR) {
+            tc::tmem_ld_32x32(lane_addr + s_col + (uint32_t)b * NT + c * 32, raw);
+            tc::tmem_ld_wait();
+            if (c == NCH - 1) {
+              tc::fence_before_sync();
+              __syncwarp();
+              if (lane == 0) tc::mbar_arrive(&s_empty[b]);
+            }
           }
           // P = exp(S - lse) as packed bf16 pairs.  dQ pass: the "- onehot" term is NOT applied here (it would put
           // per-element 64-bit compares into this MUFU-bound loop); it is subtracted as one row of Y when the row block
@@ -491,13 +531,23 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ C
           };
           if (TRANSPOSED ? onehot_here : tail) chunk_math(std::true_type{});
           else chunk_math(std::false_type{});
+          if (ESR) {
+#pragma unroll
+            for (int j = 2 * c; j < 2 * c + 2; ++j) {
+              const uint32_t wv[8] = {packed[8 * j], packed[8 * j + 1], packed[8 * j + 2], packed[8 * j + 3],
+                                      packed[8 * j + 4], packed[8 * j + 5], packed[8 * j + 6], packed[8 * j + 7]};
+              tc::tmem_st_32x32_x8(lane_addr + p_col + (uint32_t)b * (NT / 2) + (uint32_t)j * 8, wv);
+            }
+          }
         }
         const long long k2 = FS_CLOCK();
-        tc::mbar_wait(&p_empty[b], bph ^ 1u);   // GEMM2 of the tile that used this P stage has completed
-        tc::fence_after_sync();
+        if (!ESR) {
+          tc::mbar_wait(&p_empty[b], bph ^ 1u);   // GEMM2 of the tile that used this P stage has completed
+          tc::fence_after_sync();
+        }
         const long long k3 = FS_CLOCK();
 #pragma unroll
-        for (int j = 0; j < NT / 16; ++j) {
+        for (int j = 0; j < (ESR ? 0 : NT / 16); ++j) {
           const uint32_t wv[8] = {packed[8 * j], packed[8 * j + 1], packed[8 * j + 2], packed[8 * j + 3],
                                   packed[8 * j + 4], packed[8 * j + 5], packed[8 * j + 6], packed[8 * j + 7]};
           tc::tmem_st_32x32_x8(lane_addr + p_col + (uint32_t)b * (NT / 2) + (uint32_t)j * 8, wv);
