@@ -65,7 +65,8 @@ constexpr bool kDeAugment = BDLRU_CE_DE_AUGMENT != 0;
 // Softmax warps: all of S(t) is pulled into registers first and the accumulator stage released BEFORE the exponentials
 // (instead of after the last 32-column chunk was loaded, two thirds into them), and P(t) goes back chunk by chunk.
 #ifndef BDLRU_CE_EARLY_S_RELEASE
-#define BDLRU_CE_EARLY_S_RELEASE 6   // dE and fused-forward passes; the plain dQ pass measured 5 % slower with it
+#define BDLRU_CE_EARLY_S_RELEASE 2   // bit per MODE: dE pass only (-3 %); the dQ and fused-forward passes, whose softmax
+                                     // warps carry the row statistics, measured 5-10 % slower with it
 #endif
 constexpr bool kEarlySRelease = BDLRU_CE_EARLY_S_RELEASE != 0;
 #ifndef BDLRU_CE_DE_EARLY_X
