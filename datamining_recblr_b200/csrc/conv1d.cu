@@ -31,13 +31,18 @@ struct ConvParams {
   long n_items;  // B * n_chunk
 };
 
-template <typename T, int W, int S, bool SILU>
-__global__ void __launch_bounds__(256, 2) conv_fwd_kernel(const ConvParams p) {
+#ifndef BDLRU_CONV_FWD_MINB
+#define BDLRU_CONV_FWD_MINB 2
+#endif
+// V channels per thread: 4, or 8 for bf16 rows whose channel count, strides and base addresses allow 16-byte accesses
+// (at 8 bytes per lane the kernel is bound by the number of load / store instructions, not by bytes).
+template <typename T, int W, int S, int V, bool SILU>
+__global__ void __launch_bounds__(256, BDLRU_CONV_FWD_MINB) conv_fwd_kernel(const ConvParams p) {
   const int tc = threadIdx.x, ty = threadIdx.y;
-  const int c = (blockIdx.x * p.tcn + tc) * 4;
-  float wv[4][W], bv[4];
+  const int c = (blockIdx.x * p.tcn + tc) * V;
+  float wv[V][W], bv[V];
 #pragma unroll
-  for (int e = 0; e < 4; ++e) {
+  for (int e = 0; e < V; ++e) {
 #pragma unroll
     for (int j = 0; j < W; ++j) wv[e][j] = p.w[(c + e) * W + j];
     bv[e] = p.bias ? p.bias[c + e] : 0.f;
@@ -45,28 +50,29 @@ __global__ void __launch_bounds__(256, 2) conv_fwd_kernel(const ConvParams p) {
   for (long item = (long)blockIdx.y * blockDim.y + ty; item < p.n_items; item += (long)gridDim.y * blockDim.y) {
     const long b = item / p.n_chunk;
     const int t0 = (int)(item % p.n_chunk) * S;
-    float xs[S + W - 1][4];
+    float xs[S + W - 1][V];
 #pragma unroll
     for (int s = 0; s < S + W - 1; ++s) {
       const int t = t0 + s - (W - 1);
       if (t >= 0 && t < p.T) {
-        IO<T>::load(cat<T>(p.x, b, t, c), xs[s]);
+        IOV<T, V>::load(cat<T>(p.x, b, t, c), xs[s]);
       } else {
-        xs[s][0] = xs[s][1] = xs[s][2] = xs[s][3] = 0.f;
+#pragma unroll
+        for (int e = 0; e < V; ++e) xs[s][e] = 0.f;
       }
     }
 #pragma unroll
     for (int s = 0; s < S; ++s) {
       if (t0 + s < p.T) {
-        float o[4];
+        float o[V];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
+        for (int e = 0; e < V; ++e) {
           float pre = bv[e];
 #pragma unroll
           for (int j = 0; j < W; ++j) pre = fmaf(wv[e][j], xs[s + j][e], pre);
           o[e] = SILU ? silu_f(pre) : pre;
         }
-        IO<T>::store(const_cast<unsigned char*>(cat<T>(p.y, b, t0 + s, c)), o);
+        IOV<T, V>::store(const_cast<unsigned char*>(cat<T>(p.y, b, t0 + s, c)), o);
       }
     }
   }
@@ -211,9 +217,9 @@ constexpr int kConvRun = 32;  // time steps per backward work item (walked chunk
 struct ConvTiling {
   int tcn, ny, n_ctile, n_chunk, gy;
 };
-static ConvTiling conv_tiling(int B, int T, int C, int ctas_per_sm, int S) {
+static ConvTiling conv_tiling(int B, int T, int C, int ctas_per_sm, int S, int V = 4) {
   ConvTiling t;
-  const int cvec = C / 4;
+  const int cvec = C / V;
   t.tcn = 1;
   while (t.tcn < 32 && cvec % (t.tcn * 2) == 0) t.tcn *= 2;
   t.n_ctile = cvec / t.tcn;
@@ -238,17 +244,39 @@ static int conv_check(const char* name, const bdlru_view& v, int es) {
 }
 static CView cmk(const bdlru_view& v) { return CView{reinterpret_cast<const unsigned char*>(v.ptr), v.bstride, v.rstride}; }
 
-template <typename T, int W>
-static int conv_fwd_launch(ConvParams& p, bool silu, cudaStream_t st) {
-  ConvTiling t = conv_tiling(p.B, p.T, p.C, 4, kConvS);
+// Measured at 8192 x 200 x 256 bf16 (tools/conv_bench.py, ms): 8 channels x S steps per thread, grid = resident CTAs
+//   S=1 0.91   S=2 0.50   S=3 0.79   S=4 0.72-0.76   S=8 0.74      (4 channels x 8 steps, the previous kernel: 0.71-0.73)
+#ifndef BDLRU_CONV_FWD_S8
+#define BDLRU_CONV_FWD_S8 2
+#endif
+#ifndef BDLRU_CONV_FWD_CTAS
+#define BDLRU_CONV_FWD_CTAS 2
+#endif
+constexpr int kConvS8 = BDLRU_CONV_FWD_S8;   // steps per thread of the 8-channel forward
+
+template <typename T, int W, int S, int V>
+static int conv_fwd_launch_v(ConvParams& p, bool silu, cudaStream_t st) {
+  ConvTiling t = conv_tiling(p.B, p.T, p.C, BDLRU_CONV_FWD_CTAS, S, V);
   p.tcn = t.tcn; p.n_chunk = t.n_chunk; p.n_items = (long)p.B * t.n_chunk;
   dim3 grid(t.n_ctile, t.gy), block(t.tcn, t.ny);
   if (silu)
-    conv_fwd_kernel<T, W, kConvS, true><<<grid, block, 0, st>>>(p);
+    conv_fwd_kernel<T, W, S, V, true><<<grid, block, 0, st>>>(p);
   else
-    conv_fwd_kernel<T, W, kConvS, false><<<grid, block, 0, st>>>(p);
+    conv_fwd_kernel<T, W, S, V, false><<<grid, block, 0, st>>>(p);
   BDLRU_LAUNCHED();
   return BDLRU_OK;
+}
+
+static bool conv_wide_ok(const CView& v) {
+  return aligned(v.p, 16) && v.bs % 8 == 0 && v.rs % 8 == 0;
+}
+
+template <typename T, int W>
+static int conv_fwd_launch(ConvParams& p, bool silu, cudaStream_t st) {
+  if constexpr (sizeof(T) == 2) {
+    if (p.C % 8 == 0 && conv_wide_ok(p.x) && conv_wide_ok(p.y)) return conv_fwd_launch_v<T, W, kConvS8, 8>(p, silu, st);
+  }
+  return conv_fwd_launch_v<T, W, kConvS, 4>(p, silu, st);
 }
 
 template <typename T, int W>
