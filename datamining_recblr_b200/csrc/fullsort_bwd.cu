@@ -62,6 +62,12 @@ constexpr bool kDeThreeGroups = BDLRU_CE_DE_THREE_GROUPS != 0;
 #define BDLRU_CE_DE_AUGMENT 1
 #endif
 constexpr bool kDeAugment = BDLRU_CE_DE_AUGMENT != 0;
+// The augmented slab as 32-byte rows (16 K elements, 32-byte swizzle) instead of a 128-byte-swizzled 64-channel slab of
+// which one K step was used: 3 KB instead of 12 KB of TMA traffic per tile.
+#ifndef BDLRU_CE_DE_AUG_NARROW
+#define BDLRU_CE_DE_AUG_NARROW 1
+#endif
+constexpr bool kAugNarrow = BDLRU_CE_DE_AUG_NARROW != 0;
 // Softmax warps: all of S(t) is pulled into registers first and the accumulator stage released BEFORE the exponentials
 // (instead of after the last 32-column chunk was loaded, two thirds into them), and P(t) goes back chunk by chunk.
 #ifndef BDLRU_CE_EARLY_S_RELEASE
@@ -121,13 +127,15 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ C
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_slab = p.D >> 6;
-  const int n_slab_st = n_slab + (AUG ? 1 : 0);   // slabs per ring stage
+  // ring stage: the 64-channel slabs of a Y tile, then (AUG) NT rows x 32 bytes of -lse splits in 32-byte swizzle
+  constexpr uint32_t kAugB = kAugNarrow ? NT * 32 : NT * 128;
+  const uint32_t stage_b = (uint32_t)n_slab * (NT * 128) + (AUG ? kAugB : 0u);
   constexpr uint32_t kSlabB = NT * 128;
   constexpr int NCH = NT / 32;
   constexpr int NG = NSTG;                 // softmax warp groups: group g owns accumulator / P stage g
   uint8_t* sY = smem;
   constexpr uint32_t kXSlabB = kRows * 128;   // one 64-channel slab of an X row block
-  uint8_t* x_stage = sY + (size_t)p.stages * n_slab_st * kSlabB;   // early_x: X slabs (1024-byte aligned: stages are)
+  uint8_t* x_stage = sY + (size_t)p.stages * stage_b;   // early_x: X slabs (1024-byte aligned: stages are)
   // early_x: the drain stage = 4 boxes of 128 rows x 32 fp32 columns; its first half is the X stage
   float* col_lse = reinterpret_cast<float*>(x_stage + (p.early_x ? 4 * kXSlabB : 0));  // [4 * NSTG warps][NT]
   int* col_pos = reinterpret_cast<int*>(col_lse + 4 * NSTG * NT);                       // [4 * NSTG warps][NT]
@@ -222,10 +230,10 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ C
         const uint32_t ph = (uint32_t)(g / p.stages) & 1u;
         tc::mbar_wait(&y_empty[s], ph ^ 1u);
         if (tc::elect_one()) {
-          tc::mbar_arrive_expect_tx(&y_full[s], (uint32_t)n_slab_st * kSlabB);
+          tc::mbar_arrive_expect_tx(&y_full[s], stage_b);
           for (int sl = 0; sl < n_slab; ++sl)
-            tc::tma_load_2d(sY + (size_t)(s * n_slab_st + sl) * kSlabB, &tmY, &y_full[s], sl * 64, (int)(t * NT));
-          if (AUG) tc::tma_load_2d(sY + (size_t)(s * n_slab_st + n_slab) * kSlabB, &tmL, &y_full[s], 0, (int)(t * NT));
+            tc::tma_load_2d(sY + (size_t)s * stage_b + (size_t)sl * kSlabB, &tmY, &y_full[s], sl * 64, (int)(t * NT));
+          if (AUG) tc::tma_load_2d(sY + (size_t)s * stage_b + (size_t)n_slab * kSlabB, &tmL, &y_full[s], 0, (int)(t * NT));
         }
         __syncwarp();
         if (use_pf && t == x_at) {
@@ -269,7 +277,7 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ C
         const long long i2 = FS_CLOCK();
         ti_y += i1 - i0; ti_s += i2 - i1; ++ti_n;
         if (tc::elect_one()) {
-          const uint64_t bd0 = tc::smem_desc_sw128(tc::smem_u32(sY + (size_t)s * n_slab_st * kSlabB), 16, 1024);
+          const uint64_t bd0 = tc::smem_desc_sw128(tc::smem_u32(sY + (size_t)s * stage_b), 16, 1024);
           const uint32_t d_tmem = tmem_base + s_col + (uint32_t)b * NT;
           for (int sl = 0; sl < n_slab; ++sl) {
 #pragma unroll
@@ -279,7 +287,9 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ C
                                (uint32_t)((sl | k4) != 0));
           }
           if (AUG)   // the 16 augmented K elements: X columns D/2 .. D/2+7, first K step of the extra slab
-            tc::umma_bf16_ts(d_tmem, tmem_base + xaug_col, bd0 + (uint64_t)((uint32_t)n_slab * (kSlabB >> 4)),
+            tc::umma_bf16_ts(d_tmem, tmem_base + xaug_col,
+                             kAugNarrow ? tc::smem_desc_sw32(tc::smem_u32(sY + (size_t)s * stage_b + (size_t)n_slab * kSlabB), 16, 256)
+                                        : bd0 + (uint64_t)((uint32_t)n_slab * (kSlabB >> 4)),
                              idesc1, 1u);
           tc::umma_commit(&s_full[b]);
         }
@@ -314,7 +324,7 @@ ce_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ C
         if (tc::elect_one()) {
           // Y tile as the MN-major B operand: leading (MN) stride = one 64-channel slab, K groups of 8 rows are
           // 1024 bytes apart; one MMA consumes 16 rows = 2048 bytes
-          const uint64_t bd0 = tc::smem_desc_sw128(tc::smem_u32(sY + (size_t)s * n_slab_st * kSlabB), kSlabB, 1024);
+          const uint64_t bd0 = tc::smem_desc_sw128(tc::smem_u32(sY + (size_t)s * stage_b), kSlabB, 1024);
           const uint32_t a0 = tmem_base + p_col + (uint32_t)b * (NT / 2);
 #pragma unroll
           for (int kk = 0; kk < NT / 16; ++kk)
@@ -672,13 +682,14 @@ __global__ void __launch_bounds__(256) onehot_sub_kernel(const __nv_bfloat16* __
   }
 }
 
-// L_aug[u, 0..2] = exact three-way bf16 split of -lse[u]; columns 3..63 zero (one 128-byte swizzle row per user)
+// L_aug[u, 0..2] = exact three-way bf16 split of -lse[u], the rest of the row zero; a row is kAugNarrow ? 32 : 128 bytes
 __global__ void lse_aug_kernel(const float* __restrict__ lse, long n_users, __nv_bfloat16* __restrict__ out) {
-  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;   // one thread per (user, 8-channel group)
-  if (i >= n_users * 8) return;
-  const long u = i >> 3;
+  constexpr int CH = kAugNarrow ? 2 : 8;   // 16-byte chunks per row
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;   // one thread per (user, chunk)
+  if (i >= n_users * CH) return;
+  const long u = i / CH;
   uint4 w = make_uint4(0, 0, 0, 0);
-  if ((i & 7) == 0) {
+  if (i % CH == 0) {
     const float v = -lse[u];
     const __nv_bfloat16 hi = __float2bfloat16_rn(v);
     const float r1 = v - __bfloat162float(hi);
@@ -723,7 +734,8 @@ static void bwd_plan(long n_x, long n_y, int D, BwdPlan* pl, bool three_groups =
     if (util > best + 1e-9) { best = util; splits = s; }
     if (util >= 0.95) break;
   }
-  const size_t stage = (size_t)(D / 64 + (aug ? 1 : 0)) * pl->NT * 128;   // aug: one more slab (the -lse columns)
+  // aug: the -lse columns ride along (32-byte rows, or one more 64-channel slab)
+  const size_t stage = (size_t)(D / 64) * pl->NT * 128 + (aug ? (size_t)pl->NT * (kAugNarrow ? 32 : 128) : 0);
   // early_x (dE pass): 64 KB stage for the next X block / the drained dX, out of the full 227 KB instead of the 200 KB
   // budget (4 ring stages instead of 5: no measurable difference, 3 cost 2.5 %).  The bulk stores clip at n_x, which is
   // only the right bound of the output when there is a single column split.
@@ -772,9 +784,10 @@ static int bwd_one(const void* X, long n_x, const void* Y, long n_y, int D, cons
   if (rc) return rc;
   ml = my;
   if (AUG) {   // Y = Q here: one row of -lse splits per user, streamed as a third slab of every stage
-    lse_aug_kernel<<<(unsigned)((n_users * 8 + 255) / 256), 256, 0, st>>>(lse, n_users, laug);
+    lse_aug_kernel<<<(unsigned)((n_users * (kAugNarrow ? 2 : 8) + 255) / 256), 256, 0, st>>>(lse, n_users, laug);
     BDLRU_LAUNCHED();
-    if ((rc = make_rows_map(&ml, laug, n_users, 64, pl.NT))) return rc;
+    if ((rc = kAugNarrow ? make_rows16_map(&ml, laug, n_users, pl.NT) : make_rows_map(&ml, laug, n_users, 64, pl.NT)))
+      return rc;
   }
   BwdParams p = {};
   p.X = X; p.Y = Y; p.n_x = n_x; p.n_y = n_y; p.D = D; p.stages = pl.stages; p.splits = pl.splits;

@@ -159,6 +159,17 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t smem_addr, uint32_t
   return d;
 }
 
+// Same for a K-major operand whose rows are 32 bytes (16 bf16 = one K step) in 32-byte swizzle: 8-row groups 256 bytes apart.
+__device__ __forceinline__ uint64_t smem_desc_sw32(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)6 << 61;                             // layout: SWIZZLE_32B
+  return d;
+}
+
 // Instruction descriptor for kind::f16: D fp32, A/B bf16, dense, no negate.
 //   bits [4,6) D format (1 = f32) | [7,10) A format (1 = bf16) | [10,13) B format (1 = bf16)
 //   bit 15 A major (0 = K) | bit 16 B major (0 = K, 1 = MN) | [17,23) N >> 3 | [24,29) M >> 4

@@ -53,6 +53,27 @@ inline int make_rows_map(CUtensorMap* m, const void* base, long rows, int D, int
   return BDLRU_OK;
 }
 
+// [rows, 16] bf16 row-major (32-byte rows) -> boxes of box_rows rows, 32-byte swizzle, zero fill out of bounds.
+inline int make_rows16_map(CUtensorMap* m, const void* base, long rows, int box_rows) {
+  EncodeTiledFn fn = tma_encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return BDLRU_ERR_CUDA;
+  }
+  cuuint64_t dims[2] = {16, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {32};
+  cuuint32_t box[2] = {16, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (32-byte rows) failed with CUresult %d (rows=%ld)", (int)r, rows);
+    return BDLRU_ERR_CUDA;
+  }
+  return BDLRU_OK;
+}
+
 // [rows, D] fp32 row-major -> boxes of box_rows rows x 32 columns (128 bytes), 128-byte swizzle: the target of TMA stores.
 inline int make_rows_map_f32(CUtensorMap* m, const void* base, long rows, int D, int box_rows) {
   EncodeTiledFn fn = tma_encode_fn();
