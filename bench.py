@@ -67,7 +67,13 @@ class ClockSampler:
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.proc, self.lines, self.t0 = index, None, [], 0.0
+
+    def mark(self):
+        """Samples taken before this call are dropped.  start() is called BEFORE the warm-up steps (the fork of this
+        process and nvidia-smi's NVML start-up stalled kernel launches for ~20 ms, which landed in the first timed step
+        when it was started right in front of the timed region), mark() right in front of the timed region."""
+        self.t0 = time.time()
 
     def start(self):
         try:
@@ -81,7 +87,7 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
     def stop(self):
         if self.proc is None:
@@ -94,7 +100,9 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ts, ln in self.lines:
+            if ts < self.t0:
+                continue
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 8:
                 continue
@@ -370,6 +378,9 @@ def run_train(args):
         return graphed({"item_id_list": batch[0], "item_length": batch[1], "item_id": batch[2]})
 
     model.train()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for i in range(max(args.warmup, 3)):
         step(devb[i % n_batches])
     torch.cuda.synchronize()
@@ -383,9 +394,6 @@ def run_train(args):
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     # per-kernel launch durations: event pairs around the C-ABI calls.  Events cannot be recorded inside a graph
     # replay, so with the graphed step they are taken from eager steps of the same work right before the timed region.
     ktimes = None
@@ -403,6 +411,7 @@ def run_train(args):
     if graphed is None:
         _lib.kernel_timer(timed)
         eager_steps = args.steps
+    sampler.mark()
     evs = []
     for i in range(args.steps):
         flush_l2(dev)
@@ -540,6 +549,7 @@ def run_train(args):
            if sit is not None and world > 1 else (f"dp{world}" if world > 1 else "single"))
     line = dict(metric="bdlru_fwd_bwd_seq_tokens_per_s", value=value, unit="seq-tokens/s", n_gpus=world,
                 steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=ms_per_step, ms_median=med_ms, ms_min=min_ms,
+                step_ms=[round(x, 2) for x in per_step],
                 higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16" if amp else "f32", data="synthetic",
                 config=dict(workload=f"{wname}: RecBLR n_items={w['n_items']} L={L} D={D} C={C} "
                                      f"layers={w['layers']} batch {B}/GPU, train step = zero_grad + calculate_loss "
