@@ -382,6 +382,7 @@ def run_train(args):
     if rank == 0:
         sampler.start()
     for i in range(max(args.warmup, 3)):
+        flush_l2(dev)   # as in the timed loop: the flush buffer is allocated here, not inside the first timed step
         step(devb[i % n_batches])
     torch.cuda.synchronize()
 

@@ -32,7 +32,9 @@ __device__ __forceinline__ float group_sum(float v) {
   return v;
 }
 
-template <typename T, typename TO, int LPR, int VPL>
+// R tokens per warp iteration: their ids are loaded first, then their rows, then the arithmetic — the row read depends on
+// the id read and lands anywhere in the table, so one token per warp left ~8 KB per SM in flight (0.26 of HBM at 10 M rows).
+template <typename T, typename TO, int LPR, int VPL, int R>
 __global__ void __launch_bounds__(256) embed_ln_fwd_kernel(const int64_t* __restrict__ ids, const T* __restrict__ table,
                                                            const float* __restrict__ gamma,
                                                            const float* __restrict__ beta, TO* __restrict__ out,
@@ -45,64 +47,80 @@ __global__ void __launch_bounds__(256) embed_ln_fwd_kernel(const int64_t* __rest
   const long gw = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long nw = ((long)gridDim.x * blockDim.x) >> 5;
   const int nvec = D / 4;
-  for (long n0 = gw * RPW; n0 < n_tokens; n0 += nw * RPW) {
-    const long n = n0 + sub;
-    const bool live = n < n_tokens;
-    long id = live ? ids[n] : 0;
-    id = id < 0 ? 0 : (id >= n_items ? n_items - 1 : id);
-    const T* row = table + id * D;
-    float x[VPL][4];
-    float s = 0.f;
+  for (long n0 = gw * (RPW * R); n0 < n_tokens; n0 += nw * (RPW * R)) {
+    long idv[R];
 #pragma unroll
-    for (int v = 0; v < VPL; ++v) {
-      const int vec = sl + LPR * v;
-      x[v][0] = x[v][1] = x[v][2] = x[v][3] = 0.f;
-      if (live && vec < nvec) {
-        IO<T>::load(row + vec * 4, x[v]);
-        if (p > 0.f) {
-          float m[4];
-          dropout_scale4(seed, n, vec, p, m);
+    for (int j = 0; j < R; ++j) {
+      const long n = n0 + j * RPW + sub;
+      long id = n < n_tokens ? ids[n] : 0;
+      idv[j] = id < 0 ? 0 : (id >= n_items ? n_items - 1 : id);
+    }
+    float x[R][VPL][4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) x[v][e] *= m[e];
+    for (int j = 0; j < R; ++j) {
+      const long n = n0 + j * RPW + sub;
+      const T* row = table + idv[j] * D;
+#pragma unroll
+      for (int v = 0; v < VPL; ++v) {
+        const int vec = sl + LPR * v;
+        x[j][v][0] = x[j][v][1] = x[j][v][2] = x[j][v][3] = 0.f;
+        if (n < n_tokens && vec < nvec) IO<T>::load(row + vec * 4, x[j][v]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      const long n = n0 + j * RPW + sub;
+      const bool live = n < n_tokens;
+      float s = 0.f;
+#pragma unroll
+      for (int v = 0; v < VPL; ++v) {
+        const int vec = sl + LPR * v;
+        if (live && vec < nvec) {
+          if (p > 0.f) {
+            float m[4];
+            dropout_scale4(seed, n, vec, p, m);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) x[j][v][e] *= m[e];
+          }
+          s += (x[j][v][0] + x[j][v][1]) + (x[j][v][2] + x[j][v][3]);
         }
-        s += (x[v][0] + x[v][1]) + (x[v][2] + x[v][3]);
       }
-    }
-    const float mean = group_sum<LPR>(s) / (float)D;
-    float q = 0.f;
+      const float mean = group_sum<LPR>(s) / (float)D;
+      float q = 0.f;
 #pragma unroll
-    for (int v = 0; v < VPL; ++v) {
-      if (sl + LPR * v < nvec) {
+      for (int v = 0; v < VPL; ++v) {
+        if (sl + LPR * v < nvec) {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float d = x[v][e] - mean;
-          q = fmaf(d, d, q);
+          for (int e = 0; e < 4; ++e) {
+            const float d = x[j][v][e] - mean;
+            q = fmaf(d, d, q);
+          }
         }
       }
-    }
-    const float rstd = rsqrtf(group_sum<LPR>(q) / (float)D + eps);
+      const float rstd = rsqrtf(group_sum<LPR>(q) / (float)D + eps);
 #pragma unroll
-    for (int v = 0; v < VPL; ++v) {
-      const int vec = sl + LPR * v;
-      if (live && vec < nvec) {
-        const float4 g4 = *reinterpret_cast<const float4*>(gamma + vec * 4);
-        const float4 b4 = *reinterpret_cast<const float4*>(beta + vec * 4);
-        float o[4];
-        o[0] = fmaf((x[v][0] - mean) * rstd, g4.x, b4.x);
-        o[1] = fmaf((x[v][1] - mean) * rstd, g4.y, b4.y);
-        o[2] = fmaf((x[v][2] - mean) * rstd, g4.z, b4.z);
-        o[3] = fmaf((x[v][3] - mean) * rstd, g4.w, b4.w);
-        IO<TO>::store(out + n * D + vec * 4, o);
+      for (int v = 0; v < VPL; ++v) {
+        const int vec = sl + LPR * v;
+        if (live && vec < nvec) {
+          const float4 g4 = *reinterpret_cast<const float4*>(gamma + vec * 4);
+          const float4 b4 = *reinterpret_cast<const float4*>(beta + vec * 4);
+          float o[4];
+          o[0] = fmaf((x[j][v][0] - mean) * rstd, g4.x, b4.x);
+          o[1] = fmaf((x[j][v][1] - mean) * rstd, g4.y, b4.y);
+          o[2] = fmaf((x[j][v][2] - mean) * rstd, g4.z, b4.z);
+          o[3] = fmaf((x[j][v][3] - mean) * rstd, g4.w, b4.w);
+          IO<TO>::store(out + n * D + vec * 4, o);
+        }
       }
-    }
-    if (live && sl == 0) {
-      mean_out[n] = mean;
-      rstd_out[n] = rstd;
+      if (live && sl == 0) {
+        mean_out[n] = mean;
+        rstd_out[n] = rstd;
+      }
     }
   }
 }
 
-template <typename T, typename TO, int LPR, int VPL>
+template <typename T, typename TO, int LPR, int VPL, int R>
 __global__ void __launch_bounds__(256) embed_ln_bwd_kernel(const int64_t* __restrict__ ids, const T* __restrict__ table,
                                                            const float* __restrict__ gamma, const TO* __restrict__ dy,
                                                            const float* __restrict__ mean_in,
@@ -119,62 +137,91 @@ __global__ void __launch_bounds__(256) embed_ln_bwd_kernel(const int64_t* __rest
   const long gw = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long nw = ((long)gridDim.x * blockDim.x) >> 5;
   const int nvec = D / 4;
-  float dg[VPL][4], db[VPL][4];
+  float dg[VPL][4], db[VPL][4], gm[VPL][4];
 #pragma unroll
-  for (int v = 0; v < VPL; ++v)
+  for (int v = 0; v < VPL; ++v) {
+    const int vec = sl + LPR * v;
+    const float4 g4 = vec < nvec ? *reinterpret_cast<const float4*>(gamma + vec * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    gm[v][0] = g4.x, gm[v][1] = g4.y, gm[v][2] = g4.z, gm[v][3] = g4.w;
 #pragma unroll
     for (int e = 0; e < 4; ++e) dg[v][e] = db[v][e] = 0.f;
+  }
 
-  for (long n0 = gw * RPW; n0 < n_tokens; n0 += nw * RPW) {
-    const long n = n0 + sub;
-    const bool live = n < n_tokens;
-    long id = live ? ids[n] : 0;
-    id = id < 0 ? 0 : (id >= n_items ? n_items - 1 : id);
-    const T* row = table + id * D;
-    const float mean = live ? mean_in[n] : 0.f, rstd = live ? rstd_in[n] : 0.f;
-    float xh[VPL][4], dxh[VPL][4], msk[VPL][4];
-    float s1 = 0.f, s2 = 0.f;
+  for (long n0 = gw * (RPW * R); n0 < n_tokens; n0 += nw * (RPW * R)) {
+    // ids, then the rows / dy / statistics of R tokens, then the arithmetic (the row read depends on the id read)
+    long idv[R];
 #pragma unroll
-    for (int v = 0; v < VPL; ++v) {
-      const int vec = sl + LPR * v;
-#pragma unroll
-      for (int e = 0; e < 4; ++e) xh[v][e] = dxh[v][e] = 0.f, msk[v][e] = 1.f;
-      if (live && vec < nvec) {
-        float x[4], g[4];
-        IO<T>::load(row + vec * 4, x);
-        IO<TO>::load(dy + n * D + vec * 4, g);
-        if (p > 0.f) dropout_scale4(seed, n, vec, p, msk[v]);
-        const float4 g4 = *reinterpret_cast<const float4*>(gamma + vec * 4);
-        const float gm[4] = {g4.x, g4.y, g4.z, g4.w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          xh[v][e] = (x[e] * msk[v][e] - mean) * rstd;
-          dxh[v][e] = g[e] * gm[e];
-          dg[v][e] = fmaf(g[e], xh[v][e], dg[v][e]);
-          db[v][e] += g[e];
-          s1 += dxh[v][e];
-          s2 = fmaf(dxh[v][e], xh[v][e], s2);
-        }
-      }
+    for (int j = 0; j < R; ++j) {
+      const long n = n0 + j * RPW + sub;
+      long id = n < n_tokens ? ids[n] : 0;
+      idv[j] = id < 0 ? 0 : (id >= n_items ? n_items - 1 : id);
     }
-    s1 = group_sum<LPR>(s1) / (float)D;
-    s2 = group_sum<LPR>(s2) / (float)D;
-    if (live && (drows || id != padding_idx)) {
-      const bool pad = id == padding_idx;   // row-gradient mode keeps the slot (zeros): the exchange is dense per token
+    float x[R][VPL][4], g[R][VPL][4], mean[R], rstd[R];
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      const long n = n0 + j * RPW + sub;
+      const bool live = n < n_tokens;
+      const T* row = table + idv[j] * D;
+      mean[j] = live ? mean_in[n] : 0.f;
+      rstd[j] = live ? rstd_in[n] : 0.f;
 #pragma unroll
       for (int v = 0; v < VPL; ++v) {
         const int vec = sl + LPR * v;
-        if (vec < nvec) {
-          float4 d;
-          d.x = rstd * (dxh[v][0] - s1 - xh[v][0] * s2) * msk[v][0];
-          d.y = rstd * (dxh[v][1] - s1 - xh[v][1] * s2) * msk[v][1];
-          d.z = rstd * (dxh[v][2] - s1 - xh[v][2] * s2) * msk[v][2];
-          d.w = rstd * (dxh[v][3] - s1 - xh[v][3] * s2) * msk[v][3];
-          if (drows) {
-            const float o[4] = {pad ? 0.f : d.x, pad ? 0.f : d.y, pad ? 0.f : d.z, pad ? 0.f : d.w};
-            IO<TO>::store(drows + n * D + vec * 4, o);
-          } else {
-            atomicAdd(reinterpret_cast<float4*>(dtable + id * D + vec * 4), d);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) x[j][v][e] = g[j][v][e] = 0.f;
+        if (live && vec < nvec) {
+          IO<T>::load(row + vec * 4, x[j][v]);
+          IO<TO>::load(dy + n * D + vec * 4, g[j][v]);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      const long n = n0 + j * RPW + sub;
+      const bool live = n < n_tokens;
+      const long id = idv[j];
+      float msk[VPL][4];
+      float s1 = 0.f, s2 = 0.f;
+      // x <- normalised row, g <- dy * gamma
+#pragma unroll
+      for (int v = 0; v < VPL; ++v) {
+        const int vec = sl + LPR * v;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) msk[v][e] = 1.f;
+        if (live && vec < nvec) {
+          if (p > 0.f) dropout_scale4(seed, n, vec, p, msk[v]);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float xh = (x[j][v][e] * msk[v][e] - mean[j]) * rstd[j];
+            const float gy = g[j][v][e];
+            dg[v][e] = fmaf(gy, xh, dg[v][e]);
+            db[v][e] += gy;
+            x[j][v][e] = xh;
+            g[j][v][e] = gy * gm[v][e];
+            s1 += g[j][v][e];
+            s2 = fmaf(g[j][v][e], xh, s2);
+          }
+        }
+      }
+      s1 = group_sum<LPR>(s1) / (float)D;
+      s2 = group_sum<LPR>(s2) / (float)D;
+      if (live && (drows || id != padding_idx)) {
+        const bool pad = id == padding_idx;   // row-gradient mode keeps the slot (zeros): the exchange is dense per token
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+          const int vec = sl + LPR * v;
+          if (vec < nvec) {
+            float4 d;
+            d.x = rstd[j] * (g[j][v][0] - s1 - x[j][v][0] * s2) * msk[v][0];
+            d.y = rstd[j] * (g[j][v][1] - s1 - x[j][v][1] * s2) * msk[v][1];
+            d.z = rstd[j] * (g[j][v][2] - s1 - x[j][v][2] * s2) * msk[v][2];
+            d.w = rstd[j] * (g[j][v][3] - s1 - x[j][v][3] * s2) * msk[v][3];
+            if (drows) {
+              const float o[4] = {pad ? 0.f : d.x, pad ? 0.f : d.y, pad ? 0.f : d.z, pad ? 0.f : d.w};
+              IO<TO>::store(drows + n * D + vec * 4, o);
+            } else {
+              atomicAdd(reinterpret_cast<float4*>(dtable + id * D + vec * 4), d);
+            }
           }
         }
       }
@@ -230,16 +277,38 @@ __global__ void __launch_bounds__(256) scatter_rows_kernel(const int64_t* __rest
     else { CALL(32, 4); }                                \
   } while (0)
 
-static int embed_rpw(int D) { const int nv = D / 4; return nv <= 8 ? 4 : (nv <= 16 ? 2 : 1); }
+#ifndef BDLRU_EMBED_FWD_ROWS
+#define BDLRU_EMBED_FWD_ROWS 4
+#endif
+#ifndef BDLRU_EMBED_BWD_ROWS
+#define BDLRU_EMBED_BWD_ROWS 1
+#endif
+constexpr int kEmbedBwdRows = BDLRU_EMBED_BWD_ROWS;   // measured: 2 tokens in flight made the backward slower (0.57 -> 0.68 ms)
+constexpr int kEmbedFwdRows = BDLRU_EMBED_FWD_ROWS;   // tokens in flight per warp iteration (2 / 1 for the widest rows)
+#define EMBED_DISPATCH_R(D, CALL)                                          \
+  do {                                                                     \
+    const int nv_ = (D) / 4;                                               \
+    if (nv_ <= 8) { CALL(8, 1, kEmbedFwdRows); }                           \
+    else if (nv_ <= 16) { CALL(16, 1, kEmbedFwdRows); }                    \
+    else if (nv_ <= 32) { CALL(32, 1, kEmbedFwdRows); }                    \
+    else if (nv_ <= 64) { CALL(32, 2, (kEmbedFwdRows > 2 ? 2 : kEmbedFwdRows)); } \
+    else { CALL(32, 4, 1); }                                               \
+  } while (0)
 
-static int embed_grid(long n_tokens, int D) {
-  const int rpb = 8 * embed_rpw(D);
+// grid-stride kernels: exactly the CTAs that are resident at once
+template <typename K>
+static int embed_grid_occ(K kernel, size_t smem, long n_tokens, int D) {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+  const int nv = D / 4;
+  const int rpb = 8 * (nv <= 8 ? 4 : (nv <= 16 ? 2 : 1));
   long blocks = (n_tokens + rpb - 1) / rpb;
-  const long cap = (long)sm_count() * 4;
+  const long cap = (long)sm_count() * per_sm;
   if (blocks > cap) blocks = cap;
-  if (blocks < 1) blocks = 1;
-  return (int)blocks;
+  return (int)(blocks < 1 ? 1 : blocks);
 }
+
+static int embed_rpw(int D) { const int nv = D / 4; return nv <= 8 ? 4 : (nv <= 16 ? 2 : 1); }
 
 static int embed_check(long n_tokens, long n_items, int D, int dtype, float p) {
   BDLRU_REQUIRE(n_tokens >= 1 && n_items >= 1, "embed_ln: bad sizes n_tokens=%ld n_items=%ld", n_tokens, n_items);
@@ -266,19 +335,22 @@ extern "C" BDLRU_API int bdlru_embed_ln_fwd(const int64_t* ids, const void* tabl
   BDLRU_REQUIRE(aligned(table, 16) && aligned(out, 16) && aligned(gamma, 16) && aligned(beta, 16),
                 "embed_ln_fwd: pointers must be 16-byte aligned");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const int grid = embed_grid(n_tokens, D);
-#define EFWD(TT, TTO, LPR, VPL)                                                                                  \
-  embed_ln_fwd_kernel<TT, TTO, LPR, VPL><<<grid, 256, 0, st>>>(ids, (const TT*)table, gamma, beta, (TTO*)out, mean, rstd, \
-                                                               n_tokens, n_items, D, eps, dropout_p, seed, seed_device)
-#define EFWD_FF(LPR, VPL) EFWD(float, float, LPR, VPL)
-#define EFWD_BB(LPR, VPL) EFWD(__nv_bfloat16, __nv_bfloat16, LPR, VPL)
-#define EFWD_FB(LPR, VPL) EFWD(float, __nv_bfloat16, LPR, VPL)
+#define EFWD(TT, TTO, LPR, VPL, R)                                                                             \
+  {                                                                                                            \
+    auto kern = embed_ln_fwd_kernel<TT, TTO, LPR, VPL, R>;                                                     \
+    kern<<<embed_grid_occ(kern, 0, n_tokens, D), 256, 0, st>>>(ids, (const TT*)table, gamma, beta, (TTO*)out,  \
+                                                               mean, rstd, n_tokens, n_items, D, eps,          \
+                                                               dropout_p, seed, seed_device);                  \
+  }
+#define EFWD_FF(LPR, VPL, R) EFWD(float, float, LPR, VPL, R)
+#define EFWD_BB(LPR, VPL, R) EFWD(__nv_bfloat16, __nv_bfloat16, LPR, VPL, R)
+#define EFWD_FB(LPR, VPL, R) EFWD(float, __nv_bfloat16, LPR, VPL, R)
   if (dtype == BDLRU_F32 && out_dtype == BDLRU_F32) {
-    EMBED_DISPATCH(D, EFWD_FF);
+    EMBED_DISPATCH_R(D, EFWD_FF);
   } else if (dtype == BDLRU_BF16) {
-    EMBED_DISPATCH(D, EFWD_BB);
+    EMBED_DISPATCH_R(D, EFWD_BB);
   } else {
-    EMBED_DISPATCH(D, EFWD_FB);
+    EMBED_DISPATCH_R(D, EFWD_FB);
   }
 #undef EFWD_FF
 #undef EFWD_BB
@@ -307,26 +379,29 @@ static int embed_bwd_impl(const int64_t* ids, const void* table, const float* ga
   BDLRU_REQUIRE(aligned(table, 16) && aligned(grad_out, 16) && aligned(dtable, 16) && aligned(gamma, 16) &&
                     aligned(drows, 16),
                 "embed_ln_bwd: pointers must be 16-byte aligned");
-  const int grid = embed_grid(n_tokens, D);
-  const size_t need = (size_t)grid * 2 * D * sizeof(float);
+  const size_t need = bdlru_embed_ln_bwd_workspace_bytes(n_tokens, D);   // <= 8 resident 256-thread CTAs per SM
   BDLRU_REQUIRE(workspace && workspace_bytes >= need, "embed_ln_bwd: workspace too small (%zu < %zu)", workspace_bytes,
                 need);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   float* part = reinterpret_cast<float*>(workspace);
   const size_t smem = (size_t)8 * embed_rpw(D) * 2 * D * sizeof(float);
-#define EBWD(TT, TTO, LPR, VPL)                                                                                       \
-  embed_ln_bwd_kernel<TT, TTO, LPR, VPL><<<grid, 256, smem, st>>>(ids, (const TT*)table, gamma, (const TTO*)grad_out, mean, \
-                                                                  rstd, dtable, part, n_tokens, n_items, D, dropout_p,      \
-                                                                  seed, seed_device, padding_idx, (TTO*)drows)
-#define EBWD_FF(LPR, VPL) EBWD(float, float, LPR, VPL)
-#define EBWD_BB(LPR, VPL) EBWD(__nv_bfloat16, __nv_bfloat16, LPR, VPL)
-#define EBWD_FB(LPR, VPL) EBWD(float, __nv_bfloat16, LPR, VPL)
+  int grid = 1;
+#define EBWD(TT, TTO, LPR, VPL, R)                                                                                    \
+  {                                                                                                                   \
+    auto kern = embed_ln_bwd_kernel<TT, TTO, LPR, VPL, (R > kEmbedBwdRows ? kEmbedBwdRows : R)>;                                              \
+    grid = embed_grid_occ(kern, smem, n_tokens, D);                                                                   \
+    kern<<<grid, 256, smem, st>>>(ids, (const TT*)table, gamma, (const TTO*)grad_out, mean, rstd, dtable, part,       \
+                                  n_tokens, n_items, D, dropout_p, seed, seed_device, padding_idx, (TTO*)drows);      \
+  }
+#define EBWD_FF(LPR, VPL, R) EBWD(float, float, LPR, VPL, R)
+#define EBWD_BB(LPR, VPL, R) EBWD(__nv_bfloat16, __nv_bfloat16, LPR, VPL, R)
+#define EBWD_FB(LPR, VPL, R) EBWD(float, __nv_bfloat16, LPR, VPL, R)
   if (dtype == BDLRU_F32 && out_dtype == BDLRU_F32) {
-    EMBED_DISPATCH(D, EBWD_FF);
+    EMBED_DISPATCH_R(D, EBWD_FF);
   } else if (dtype == BDLRU_BF16) {
-    EMBED_DISPATCH(D, EBWD_BB);
+    EMBED_DISPATCH_R(D, EBWD_BB);
   } else {
-    EMBED_DISPATCH(D, EBWD_FB);
+    EMBED_DISPATCH_R(D, EBWD_FB);
   }
 #undef EBWD_FF
 #undef EBWD_BB

@@ -776,10 +776,17 @@ static int launch_fwd_v(GScanParams& p, cudaStream_t st) {
 
 // Measured on B200 (tools/scan_bench.py, bf16): 8 channels x 2 steps per thread is SLOWER than 4 x 4 at C = 128
 // (2 048 x 200 x 128 fwd+bwd 0.64 ms vs 0.38 ms: only 16 channel vectors, so 16 time slices per CTA and a 16-long
-// aggregate walk per 16 elements) and equal at C = 256 — the wide instantiation is kept for experiments, off by default.
+// aggregate walk per 16 elements; with 2 / 4 / 8 slices forced: 0.57 / 0.57 / 0.46 of HBM against 0.63).  With a full warp
+// of channel vectors (C a multiple of 256) and the short slice counts of make_tiling it is FASTER: 8 192 x 200 x 256 z-gated
+// fwd 0.94 -> 0.89 ms, bwd 2.06 -> 1.95 ms in tools/scan_bench.py (graph replay); inside the configs[4] training step the
+// forward went 1.12 -> 1.04 ms but the backward 2.12 -> 2.20 ms.  So: wide exactly when C / 8 fills whole warps, forward only
+// (bit 0 = forward, bit 1 = backward).
 #ifndef BDLRU_GSCAN_WIDE
-#define BDLRU_GSCAN_WIDE 0
+#define BDLRU_GSCAN_WIDE 1
 #endif
+static bool use_wide(const GScanParams& p, int dir) {
+  return ((BDLRU_GSCAN_WIDE >> dir) & 1) && p.C % 256 == 0 && p.wide_ok;
+}
 
 template <typename T, bool GATED, bool HAS_Z>
 static int launch_fwd(GScanParams& p, cudaStream_t st) {
@@ -788,8 +795,8 @@ static int launch_fwd(GScanParams& p, cudaStream_t st) {
     if (V == 4) return launch_seq_fwd<T, 4, HAS_Z>(p, st);
     if (V == 2) return launch_seq_fwd<T, 2, HAS_Z>(p, st);
   }
-  if constexpr (sizeof(T) == 2 && BDLRU_GSCAN_WIDE) {
-    if (p.C % 8 == 0 && p.wide_ok) return launch_fwd_v<T, 8, 2, GATED, HAS_Z>(p, st);
+  if constexpr (sizeof(T) == 2) {
+    if (use_wide(p, 0)) return launch_fwd_v<T, 8, 2, GATED, HAS_Z>(p, st);
   }
   return launch_fwd_v<T, 4, 4, GATED, HAS_Z>(p, st);
 }
@@ -836,8 +843,8 @@ static int launch_bwd(GScanParams& p, float* dLambda, float* dh0_out, void* ws, 
     if (V == 4) return launch_seq_bwd<T, 4, HAS_Z>(p, dLambda, dh0_out, ws, ws_bytes, st);
     if (V == 2) return launch_seq_bwd<T, 2, HAS_Z>(p, dLambda, dh0_out, ws, ws_bytes, st);
   }
-  if constexpr (sizeof(T) == 2 && BDLRU_GSCAN_WIDE) {
-    if (p.C % 8 == 0 && p.wide_ok) return launch_bwd_v<T, 8, 2, GATED, HAS_Z>(p, dLambda, dh0_out, ws, ws_bytes, st);
+  if constexpr (sizeof(T) == 2) {
+    if (use_wide(p, 1)) return launch_bwd_v<T, 8, 2, GATED, HAS_Z>(p, dLambda, dh0_out, ws, ws_bytes, st);
   }
   return launch_bwd_v<T, 4, 4, GATED, HAS_Z>(p, dLambda, dh0_out, ws, ws_bytes, st);
 }

@@ -77,9 +77,13 @@ __global__ void __launch_bounds__(256) silu_dropout_kernel(const T* __restrict__
       const float s = sigmoid_f(a[e]);
       o[e] = BWD ? g[e] * m[e] * silu_grad_f(a[e], s) : a[e] * s * m[e];
     }
-    const float o0[4] = {o[0], o[1], o[2], o[3]}, o1[4] = {o[4], o[5], o[6], o[7]};
-    IO<T>::store(out + v * 8, o0);
-    IO<T>::store(out + v * 8 + 4, o1);
+    if constexpr (sizeof(T) == 2) {
+      IOV<T, 8>::store(out + v * 8, o);   // one 16-byte store
+    } else {
+      const float o0[4] = {o[0], o[1], o[2], o[3]}, o1[4] = {o[4], o[5], o[6], o[7]};
+      IO<T>::store(out + v * 8, o0);
+      IO<T>::store(out + v * 8 + 4, o1);
+    }
   }
 }
 
@@ -92,16 +96,20 @@ static int sd_launch(const void* x, const void* dy, void* out, int64_t n, float 
   const size_t al = 16;
   BDLRU_REQUIRE(aligned(x, al) && aligned(out, al) && (!bwd || aligned(dy, al)), "silu_dropout: misaligned pointer");
   const long n_vec = n / 8;
-  long blocks = (n_vec + 255) / 256;
-  const long cap = (long)sm_count() * 16;
-  if (blocks > cap) blocks = cap;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  // grid-stride loop capped at two full waves of the 8 resident 256-thread CTAs per SM (32 registers)
+  auto launch = [&](auto kern, auto xp, auto dyp, auto op) {
+    long blocks = (n_vec + 255) / 256;
+    const long cap = (long)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    kern<<<(int)blocks, 256, 0, st>>>(xp, dyp, op, n_vec, p, seed, seed_dev);
+  };
   if (dtype == BDLRU_F32) {
-    if (bwd) silu_dropout_kernel<float, true><<<(int)blocks, 256, 0, st>>>((const float*)x, (const float*)dy, (float*)out, n_vec, p, seed, seed_dev);
-    else silu_dropout_kernel<float, false><<<(int)blocks, 256, 0, st>>>((const float*)x, nullptr, (float*)out, n_vec, p, seed, seed_dev);
+    if (bwd) launch(silu_dropout_kernel<float, true>, (const float*)x, (const float*)dy, (float*)out);
+    else launch(silu_dropout_kernel<float, false>, (const float*)x, (const float*)nullptr, (float*)out);
   } else {
-    if (bwd) silu_dropout_kernel<__nv_bfloat16, true><<<(int)blocks, 256, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, (__nv_bfloat16*)out, n_vec, p, seed, seed_dev);
-    else silu_dropout_kernel<__nv_bfloat16, false><<<(int)blocks, 256, 0, st>>>((const __nv_bfloat16*)x, nullptr, (__nv_bfloat16*)out, n_vec, p, seed, seed_dev);
+    if (bwd) launch(silu_dropout_kernel<__nv_bfloat16, true>, (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, (__nv_bfloat16*)out);
+    else launch(silu_dropout_kernel<__nv_bfloat16, false>, (const __nv_bfloat16*)x, (const __nv_bfloat16*)nullptr, (__nv_bfloat16*)out);
   }
   BDLRU_LAUNCHED();
   return BDLRU_OK;
