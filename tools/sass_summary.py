@@ -18,7 +18,7 @@ for line in out.splitlines():
     m = re.match(r"\s+/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_]+)", line)
     if m and name:
         per[name][m.group(1)] += 1
-keys = ["UTCHMMA", "UTMALDG", "LDTM", "STTM", "UTCBAR", "SYNCS", "LDGSTS", "MUFU", "HMMA"]
+keys = ["UTCHMMA", "UTMALDG", "UTMASTG", "LDTM", "STTM", "UTCBAR", "SYNCS", "LDGSTS", "MUFU", "HMMA"]
 agg = collections.OrderedDict()
 for n, c in per.items():
     base = re.sub(r"<.*", "", re.sub(r"\(.*", "", n).replace("void ", "").replace("bdlru::", ""))
@@ -29,7 +29,7 @@ for n, c in per.items():
 with open(os.path.join(ROOT, "profiles", "r2_sass_opcodes.md"), "w") as f:
     f.write("# SASS opcode summary of libbdlru.so (round 2)\n\n`cuobjdump -sass datamining_recblr_b200/libbdlru.so` (all cubins "
             "sm_100a), counted per kernel template (summed over its\ninstantiations) by tools/sass_summary.py.  UTCHMMA = "
-            "tcgen05.mma, UTMALDG = TMA tensor load, LDTM/STTM = tcgen05.ld/st (TMEM),\nUTCBAR = tcgen05.commit, SYNCS = "
+            "tcgen05.mma, UTMALDG / UTMASTG = TMA tensor load / store, LDTM/STTM = tcgen05.ld/st (TMEM),\nUTCBAR = tcgen05.commit, SYNCS = "
             "mbarrier ops, LDGSTS = cp.async; HMMA (legacy mma.sync) must be 0.\n\n")
     f.write("| kernel template | instantiations | SASS instructions | " + " | ".join(keys) + " |\n|---|---|---|" + "---|" * len(keys) + "\n")
     for base, (n, tot, vals) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
