@@ -324,6 +324,30 @@ def test_fullsort_rejects_bad_arguments():
         ops.fullsort_topk(q.cpu(), e.cpu(), 5)
 
 
+@pytest.mark.parametrize("B,N,D", [(200, 40_000, 128), (130, 19_001, 64), (96, 37_999, 128), (300, 19_073, 192)])
+def test_ce_de_pass_row_block_handover(B, N, D):
+    """dE pass where every CTA hands over between several 128-row blocks (N > 148 * 128 item rows) and the last block is
+    ragged: the next block's X rows arrive by TMA into the stage the drained dX leaves through (bulk tensor stores clipped
+    at N), D = 64 shares one X slab between the two softmax groups, D = 192 takes the path without the stage.  Reference:
+    float64 softmax gradients of the same bf16 operands (RecBLR.py:99-103 through autograd)."""
+    from datamining_recblr_b200 import ops
+    torch.manual_seed(B + N)
+    q = torch.randn(B, D, device="cuda").to(torch.bfloat16)
+    e = (torch.randn(N, D, device="cuda") * 0.2).to(torch.bfloat16)
+    pos = torch.randint(0, N, (B,), device="cuda")
+    pos[0], pos[1] = N - 1, 0                      # positives in the ragged last block and in the first row
+    m, s, _ = ops.fullsort_ce_stats(q, e, pos)
+    lse = m + torch.log(s)
+    de_guard = torch.full((N + 128, D), 7.0, device="cuda")     # rows past N must stay untouched by the bulk stores
+    dq, de = ops.fullsort_ce_grads(q, e, pos, lse, 1.0 / B, out_de=de_guard[:N])
+    assert torch.all(de_guard[N:] == 7.0)
+    p64 = torch.softmax(q.double() @ e.double().T, -1)
+    p64[torch.arange(B, device="cuda"), pos] -= 1.0
+    de64, dq64 = p64.T @ q.double() / B, p64 @ e.double() / B
+    assert ((de.double() - de64).abs().max() / de64.abs().max()).item() <= 1e-2
+    assert ((dq.double() - dq64).abs().max() / dq64.abs().max()).item() <= 1e-2
+
+
 @pytest.mark.parametrize("B,N,D", [(200, 20000, 64), (20000, 300, 64), (19000, 19500, 128)])
 def test_fused_ce_many_row_blocks(B, N, D):
     """More row blocks than SMs in the dE pass (N > 148 * 128) and in the dQ pass (B > 148 * 128): every CTA of the
