@@ -166,7 +166,9 @@ int bdlru_scatter_add_rows(const int64_t* ids, const void* rows, int64_t n_token
  * (RecurrentLayer.forward RecBLR.py:142 and FeedForward.forward RecBLR.py:221-225).  x, residual, out, grad_out, dx,
  * dresidual are contiguous [n_rows, D] in `dtype`; gamma/beta/dgamma/dbeta/mean/rstd fp32.  Same dropout generator and
  * seed_device convention as bdlru_embed_ln_*.  bwd: dresidual = d(sum), dx = dresidual * mask; dx may alias
- * dresidual when dropout_p == 0.
+ * dresidual when dropout_p == 0.  Alignment: fp32 rows 16 bytes; bf16 rows 8 bytes — with D % 8 == 0 and every row
+ * pointer 16-byte aligned the kernels move 16 bytes per lane, otherwise 8; the dropout mask is the same either way.
+ * bwd workspace: bdlru_add_ln_bwd_workspace_bytes(n_rows, D).
  * ------------------------------------------------------------------------------------------- */
 int bdlru_add_ln_fwd(const void* x, const void* residual, const float* gamma, const float* beta, void* out,
                      float* mean, float* rstd, int64_t n_rows, int D, float eps, float dropout_p, uint64_t seed,
