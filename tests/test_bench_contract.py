@@ -31,3 +31,33 @@ def test_reference_arm_prints_one_json_line_with_contract_keys():
 def test_reference_arm_scoring_workload():
     d = _run(["--impl", "reference", "--workload", "score1m", "--steps", "1", "--warmup", "1", "--cpu-sample", "4"])
     assert d["metric"] == "fullsort_scored_users_per_s" and d["unit"] == "users/s" and d["value"] > 0
+
+
+def test_clock_sampler_drops_samples_before_mark():
+    """The sampler is started before the warm-up steps and mark()ed in front of the timed region: only samples taken after
+    the mark count, throttle reasons included."""
+    import time
+
+    sys.path.insert(0, ROOT)
+    import bench
+
+    class _Done:
+        def terminate(self):
+            pass
+
+        def wait(self, timeout=None):
+            return 0
+
+    s = bench.ClockSampler(0)
+    s.proc = _Done()
+    now = time.time()
+    s.lines = [(now - 10.0, "0, 1200, 1965, 400.0, Active, Not Active, Not Active, Not Active"),   # warm-up: dropped
+               (now + 1.0, "0, 1650, 1965, 990.0, Not Active, Not Active, Not Active, Active"),
+               (now + 1.2, "0, 1670, 1965, 995.0, Not Active, Not Active, Not Active, Active"),
+               (now + 1.4, "garbage")]
+    s.t0 = 0.0
+    allc = s.stop()
+    assert allc["samples"] == 3 and "hw_slowdown" in allc["reasons"]
+    s.t0 = now
+    c = s.stop()
+    assert c["samples"] == 2 and c["sm_mhz"] == 1660.0 and c["sm_max_mhz"] == 1965.0 and c["reasons"] == ["sw_power_cap"]
